@@ -1,0 +1,89 @@
+"""Build the C-ABI CUDA library (libr2l_b200.so) in-tree with nvcc for sm_100a.
+
+Usage: python efficient-nerf_b200/build.py [--force]
+The .so is git-ignored but travels to the GPU box with the source snapshot.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libr2l_b200.so")
+STAMP = os.path.join(LIB_DIR, "build.stamp")
+
+SOURCES = ["rays.cu", "embed.cu", "composite.cu", "sample_pdf.cu", "linear_fp32.cu", "mlp_nerf.cu", "mlp_r2l.cu",
+           "mlp_api.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr", "-Xptxas", "-v", "--extended-lambda",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC or add /usr/local/cuda/bin to PATH)")
+
+
+def _digest():
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(CSRC, name), "rb") as f:
+                h.update(name.encode())
+                h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current():
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() == _digest()
+
+
+def build(force=False, verbose=True):
+    """Compile every .cu under csrc/ and link libr2l_b200.so.  Returns the library path."""
+    if not force and is_current():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src} ==\n{out}")
+        if p.returncode != 0:
+            failed = True
+    with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(log))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    with open(STAMP, "w") as f:
+        f.write(_digest())
+    if verbose:
+        print(f"built {LIB_PATH}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

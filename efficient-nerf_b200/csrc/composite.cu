@@ -1,0 +1,151 @@
+// raw2outputs: alpha compositing along each ray as a warp-level scan.
+// Reference: main.py:556-621 (twins: utils/create_data.py:335-402,
+// model/nerf_raybased.py:226-295, utils/run_nerf_raybased_helpers.py:77-144).
+//
+//   dists_i = z_{i+1}-z_i (last = 1e10), times |rays_d|
+//   alpha_i = 1 - exp(-relu(sigma_i + noise_i) * dists_i)
+//   T_i     = prod_{j<i} (1 - alpha_j + 1e-10)        (reference: ATen CPU cumprod accumulates in double)
+//   w_i     = alpha_i * T_i
+//   rgb_map = sum w_i * sigmoid(rgb_i);  depth = sum w_i z_i;  acc = sum w_i
+//   disp    = 1 / max(1e-10, depth/acc)  with torch.max NaN propagation;  white_bkgd: rgb += 1-acc
+//
+// One warp per ray; lane l owns samples l, l+32, ... so every load/store is a fully
+// coalesced 128/512-byte transaction (raw is read as float4).  The transmittance is an
+// exclusive product scan: 5 shuffle steps per 32-sample chunk in double precision plus a
+// running carry — double so that the result rounds to the same fp32 value as the
+// reference's sequential double-accumulated cumprod.
+// Algorithmic HBM bytes per ray: 16S (raw) + 4S (z) + 12 (d) in, 4S (weights) + 24 out.
+#include "common.cuh"
+
+namespace r2l {
+
+constexpr int kCompWarps = 8;
+
+__device__ __forceinline__ double shfl_up_f64(double v, int delta) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(0xffffffffu, lo, delta);
+  hi = __shfl_up_sync(0xffffffffu, hi, delta);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_idx_f64(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kCompWarps * 32)
+raw2outputs_kernel(long long n_rays, int S, const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                   const float* __restrict__ rays_d, long long d_stride, const float* __restrict__ noise,
+                   int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ disp_map,
+                   float* __restrict__ acc_map, float* __restrict__ weights, float* __restrict__ depth_map) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kCompWarps + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * kCompWarps;
+  const int chunks = (S + 31) / 32;
+  for (long long ray = warp0; ray < n_rays; ray += nwarps) {
+    const float dx = rays_d[ray * d_stride], dy = rays_d[ray * d_stride + 1], dz = rays_d[ray * d_stride + 2];
+    const float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float4* rraw = raw + ray * S;
+    const float* rz = z_vals + ray * S;
+    double carry = 1.0;
+    float ar = 0.f, ag = 0.f, ab = 0.f, adepth = 0.f, aacc = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+      const int i = c * 32 + lane;
+      const bool valid = i < S;
+      float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+      float zi = 0.f, zn = 0.f, nz = 0.f;
+      if (valid) {
+        rv = __ldg(rraw + i);
+        zi = __ldg(rz + i);
+        if (i + 1 < S) zn = __ldg(rz + i + 1);
+        if (noise != nullptr) nz = __ldg(noise + ray * S + i);
+      }
+      float dist = (i == S - 1) ? 1e10f : __fsub_rn(zn, zi);
+      dist = __fmul_rn(dist, dnorm);
+      const float sigma = (noise != nullptr) ? __fadd_rn(rv.w, nz) : rv.w;
+      const float rl = fmaxf(sigma, 0.0f);
+      float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-rl, dist)));
+      if (sigma != sigma) alpha = sigma;  // relu/exp propagate NaN in the reference
+      const float tt = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      double p = valid ? static_cast<double>(tt) : 1.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double q = shfl_up_f64(p, o);
+        if (lane >= o) p *= q;
+      }
+      double excl = shfl_up_f64(p, 1);
+      if (lane == 0) excl = 1.0;
+      const float T = static_cast<float>(carry * excl);
+      carry *= shfl_idx_f64(p, 31);
+      const float w = valid ? __fmul_rn(alpha, T) : 0.0f;
+      if (valid) {
+        if (weights != nullptr) weights[ray * S + i] = w;
+        const float sr = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.x)));
+        const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.y)));
+        const float sb = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.z)));
+        ar = __fadd_rn(ar, __fmul_rn(w, sr));
+        ag = __fadd_rn(ag, __fmul_rn(w, sg));
+        ab = __fadd_rn(ab, __fmul_rn(w, sb));
+        adepth = __fadd_rn(adepth, __fmul_rn(w, zi));
+        aacc = __fadd_rn(aacc, w);
+      }
+    }
+    ar = warp_sum(ar);
+    ag = warp_sum(ag);
+    ab = warp_sum(ab);
+    adepth = warp_sum(adepth);
+    aacc = warp_sum(aacc);
+    if (lane == 0) {
+      if (white_bkgd) {
+        const float bg = __fsub_rn(1.0f, aacc);
+        ar = __fadd_rn(ar, bg);
+        ag = __fadd_rn(ag, bg);
+        ab = __fadd_rn(ab, bg);
+      }
+      if (rgb_map != nullptr) {
+        rgb_map[3 * ray] = ar;
+        rgb_map[3 * ray + 1] = ag;
+        rgb_map[3 * ray + 2] = ab;
+      }
+      if (depth_map != nullptr) depth_map[ray] = adepth;
+      if (acc_map != nullptr) acc_map[ray] = aacc;
+      if (disp_map != nullptr) {
+        const float q = __fdiv_rn(adepth, aacc);
+        // torch.max(1e-10, q) propagates NaN (0/0 when all weights are zero); fmaxf would not
+        const float m = (q != q) ? q : fmaxf(1e-10f, q);
+        disp_map[ray] = __fdiv_rn(1.0f, m);
+      }
+    }
+  }
+}
+
+}  // namespace r2l
+
+using namespace r2l;
+
+extern "C" {
+
+int r2l_raw2outputs(long long n_rays, int S, const float* raw, const float* z_vals, const float* rays_d,
+                    long long d_stride, const float* noise, int white_bkgd, float* rgb_map, float* disp_map,
+                    float* acc_map, float* weights, float* depth_map, void* stream) {
+  R2L_CHECK_ARG(n_rays >= 0 && S > 0 && d_stride >= 3, "r2l_raw2outputs: bad sizes");
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(raw && z_vals && rays_d, "r2l_raw2outputs: null input pointer");
+  R2L_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "r2l_raw2outputs: raw must be 16-byte aligned");
+  long long blocks = (n_rays + kCompWarps - 1) / kCompWarps;
+  const long long cap = static_cast<long long>(sm_count()) * 8;  // 8 resident 256-thread CTAs per SM
+  if (blocks > cap) blocks = cap;
+  raw2outputs_kernel<<<static_cast<int>(blocks), kCompWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      n_rays, S, reinterpret_cast<const float4*>(raw), z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map,
+      disp_map, acc_map, weights, depth_map);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,582 @@
+// C-ABI front end of the fused MLP kernels: weight packing (reference nn.Linear layout ->
+// 16-bit K-chunk-major stage stream), model handles, forward entry points and a minimal
+// tcgen05 GEMM probe used by the GPU unit tests.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "mlp_params.cuh"
+#include "mlp_tc.cuh"
+
+namespace r2l {
+
+// ---------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ---------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------
+// W [N, *] fp32 row-major (row stride ldw)  ->  stage stream of 16-bit values.
+// Logical operand B[n][k], k in [0, Kpad): source column kmap[k] (or k when kmap == nullptr),
+// -1 / out-of-range -> 0.  Stage s holds k in [32s, 32s+32), k-chunk major:
+//   element offset = s*(N*32) + ((k%32)/8)*(N*8) + n*8 + (k%8)
+__global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, int N, int K_src, int Kpad,
+                                  const int* __restrict__ kmap, float scale, uint16_t* __restrict__ dst, int bf16) {
+  const long long total = static_cast<long long>(N) * Kpad;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx / Kpad), k = static_cast<int>(idx % Kpad);
+    const int ks = (kmap != nullptr) ? kmap[k] : k;
+    float v = 0.0f;
+    if (ks >= 0 && ks < K_src) v = W[n * ldw + ks] * scale;
+    uint16_t bits;
+    if (bf16)
+      bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    else
+      bits = __half_as_ushort(__float2half_rn(v));
+    const int s = k >> 5, kk = k & 31;
+    dst[static_cast<long long>(s) * N * 32 + (kk >> 3) * (N * 8) + n * 8 + (kk & 7)] = bits;
+  }
+}
+
+// cb[b][n] = res_scale * sum_{b' <= b} b2[b'][n]  (double accumulate)
+__global__ void cumulative_bias_kernel(const float* const* __restrict__ b2, int n_blocks, int width, double scale,
+                                       float* __restrict__ cb) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= width) return;
+  double acc = 0.0;
+  for (int b = 0; b < n_blocks; ++b) {
+    acc += static_cast<double>(scale * static_cast<double>(b2[b][n]));
+    cb[b * width + n] = static_cast<float>(acc);
+  }
+}
+
+struct Mlp {
+  int kind = 0;  // 0 = NeRF, 1 = R2L ResMLP
+  bool bf16 = false;
+  uint8_t* wstream = nullptr;
+  size_t wbytes = 0;
+  float* aux = nullptr;
+  DebugBuf* dbg_host = nullptr;  // pinned, mapped: readable after a device trap
+  DebugBuf* dbg_dev = nullptr;
+  // NeRF
+  float alpha_b = 0.f, rgb_b[3] = {0.f, 0.f, 0.f};
+  // R2L
+  int n_points = 0, n_blocks = 0, sigmoid_out = 1, outer_skip = 1;
+  float b_tail[3] = {0.f, 0.f, 0.f};
+};
+
+static int alloc_debug(Mlp* m) {
+  R2L_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->dbg_host), sizeof(DebugBuf), cudaHostAllocMapped));
+  memset(m->dbg_host, 0, sizeof(DebugBuf));
+  R2L_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->dbg_dev), m->dbg_host, 0));
+  return R2L_OK;
+}
+
+static int pack_layer(const float* W, long long ldw, int N, int K_src, int Kpad, const std::vector<int>* kmap,
+                      float scale, uint16_t* dst, bool bf16, cudaStream_t st, std::vector<int*>& scratch) {
+  int* d_kmap = nullptr;
+  if (kmap != nullptr) {
+    R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_kmap), sizeof(int) * Kpad));
+    scratch.push_back(d_kmap);
+    R2L_CUDA(cudaMemcpyAsync(d_kmap, kmap->data(), sizeof(int) * Kpad, cudaMemcpyHostToDevice, st));
+  }
+  const long long total = static_cast<long long>(N) * Kpad;
+  const int blocks = static_cast<int>((total + 255) / 256);
+  pack_layer_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K_src, Kpad, d_kmap, scale, dst, bf16 ? 1 : 0);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+static void destroy(Mlp* m) {
+  if (m == nullptr) return;
+  if (m->wstream) cudaFree(m->wstream);
+  if (m->aux) cudaFree(m->aux);
+  if (m->dbg_host) cudaFreeHost(m->dbg_host);
+  delete m;
+}
+
+// NeRF aux layout (floats)
+constexpr int kNerfAuxBias = 0;                    // 9*256
+constexpr int kNerfAuxAlphaW = 9 * 256;            // 256
+constexpr int kNerfAuxRgbW = kNerfAuxAlphaW + 256; // 384
+constexpr int kNerfAuxWvd = kNerfAuxRgbW + 384;    // 128*27
+constexpr int kNerfAuxBv = kNerfAuxWvd + 128 * 27; // 128
+constexpr int kNerfAuxTotal = kNerfAuxBv + 128;
+
+// ---------------------------------------------------------------------------------
+// tcgen05 GEMM probe: D[128, N] = A[128, K] * B[N, K]^T with 16-bit operands, fp32 accumulate.
+// Single CTA, no pipelining; exists to unit-test the descriptor / layout conventions.
+// ---------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(128, 1)
+gemm_probe_kernel(const float* __restrict__ A, int K, const uint16_t* __restrict__ Bpacked, int N,
+                  float* __restrict__ D, int swap_lbo_sbo, DebugBuf* dbg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                  // 128 x K 16-bit, chunk major
+  uint8_t* sB = smem + kTileM * K * 2;                 // N x K 16-bit, stage stream as packed
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + N * K * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  // A -> shared (16-bit, k-chunk major)
+  for (int ch = 0; ch < K / 8; ++ch) {
+    const float* a = A + static_cast<long long>(row) * K + ch * 8;
+    uint4 q;
+    q.x = pack2<BF16>(a[0], a[1]);
+    q.y = pack2<BF16>(a[2], a[3]);
+    q.z = pack2<BF16>(a[4], a[5]);
+    q.w = pack2<BF16>(a[6], a[7]);
+    *reinterpret_cast<uint4*>(sA + ch * kChunkBytes + row * 16) = q;
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = static_cast<uint32_t>(N) * K * 2;
+    mbar_expect_tx(&bars[0], bytes);
+    // bulk copies are limited in size per instruction; move stage by stage
+    const uint32_t stage_bytes = static_cast<uint32_t>(N) * 64;
+    for (uint32_t off = 0; off < bytes; off += stage_bytes)
+      bulk_g2s(sB + off, reinterpret_cast<const uint8_t*>(Bpacked) + off, stage_bytes, &bars[0]);
+    mbar_wait(&bars[0], 0, dbg, 1);
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc_f16(BF16, kTileM, N);
+    const uint32_t lbo_b = static_cast<uint32_t>(N) * 16;
+    for (int s = 0; s < K / 32; ++s) {
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t a_addr = smem_u32(sA) + (s * 4 + j * 2) * kChunkBytes;
+        const uint32_t b_addr = smem_u32(sB) + s * stage_bytes + j * 2 * lbo_b;
+        const uint64_t ad = swap_lbo_sbo ? make_smem_desc(a_addr, kSbo, kLboA) : make_smem_desc(a_addr, kLboA, kSbo);
+        const uint64_t bd = swap_lbo_sbo ? make_smem_desc(b_addr, kSbo, lbo_b) : make_smem_desc(b_addr, lbo_b, kSbo);
+        umma_f16_ss(tmem_base, ad, bd, idesc, (s | j) != 0 ? 1u : 0u);
+      }
+    }
+    umma_commit(&bars[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[1], 0, dbg, 2);
+  tc_fence_after_sync();
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c = 0; c < N; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(lane_taddr + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[static_cast<long long>(row) * N + c + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 256);
+  }
+  (void)lane;
+}
+
+}  // namespace r2l
+
+using namespace r2l;
+
+extern "C" {
+
+const char* r2l_last_error(void) { return g_last_error.c_str(); }
+int r2l_abi_version(void) { return 1; }
+
+// D [128, N] fp32 = A [128, K] fp32 (rounded to 16 bit) x W [N, K]^T fp32 (rounded to 16 bit).
+// K multiple of 32, <= 320; N multiple of 16, 16..256.  dtype: 0 = fp16, 1 = bf16.
+int r2l_tc_gemm_probe(int dtype, int N, int K, const float* A, const float* W, float* D, int swap_lbo_sbo,
+                      void* stream) {
+  R2L_CHECK_ARG(dtype == 0 || dtype == 1, "r2l_tc_gemm_probe: dtype must be 0 (fp16) or 1 (bf16)");
+  R2L_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0, "r2l_tc_gemm_probe: bad N");
+  R2L_CHECK_ARG(K >= 32 && K <= 320 && K % 32 == 0, "r2l_tc_gemm_probe: bad K");
+  R2L_CHECK_ARG(A && W && D, "r2l_tc_gemm_probe: null pointer");
+  auto st = static_cast<cudaStream_t>(stream);
+  uint16_t* packed = nullptr;
+  R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&packed), static_cast<size_t>(N) * K * 2));
+  std::vector<int*> scratch;
+  int rc = pack_layer(W, K, N, K, K, nullptr, 1.0f, packed, dtype == 1, st, scratch);
+  DebugBuf* dbg_host = nullptr;
+  DebugBuf* dbg_dev = nullptr;
+  if (rc == R2L_OK) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&dbg_host), sizeof(DebugBuf), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&dbg_dev), dbg_host, 0) != cudaSuccess)
+      rc = fail(R2L_ERR_CUDA, "r2l_tc_gemm_probe: debug buffer allocation failed");
+    else
+      memset(dbg_host, 0, sizeof(DebugBuf));
+  }
+  if (rc == R2L_OK) {
+    const int smem = kTileM * K * 2 + N * K * 2 + 64;
+    cudaError_t e;
+    if (dtype == 1) {
+      e = cudaFuncSetAttribute(gemm_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) gemm_probe_kernel<true><<<1, 128, smem, st>>>(A, K, packed, N, D, swap_lbo_sbo, dbg_dev);
+    } else {
+      e = cudaFuncSetAttribute(gemm_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) gemm_probe_kernel<false><<<1, 128, smem, st>>>(A, K, packed, N, D, swap_lbo_sbo, dbg_dev);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      rc = fail(R2L_ERR_CUDA, "r2l_tc_gemm_probe: %s (watchdog flag=%u barrier=%u)", cudaGetErrorString(e),
+                dbg_host ? dbg_host->flag : 0u, dbg_host ? dbg_host->barrier_id : 0u);
+    }
+  }
+  if (dbg_host) cudaFreeHost(dbg_host);
+  cudaFree(packed);
+  return rc;
+}
+
+// ------------------------------- NeRF ---------------------------------------------
+// Weights in the reference's nn.Linear layout ([out, in] row-major fp32, device memory):
+//   pts_w[0] [256,63], pts_w[1..4] [256,256], pts_w[5] [256,319], pts_w[6..7] [256,256]   (model:357-360)
+//   views_w [128,283], feature_w [256,256], alpha_w [1,256], rgb_w [3,128]                   (model:363-372)
+int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, const float* const* pts_b,
+                    const float* views_w, const float* views_b, const float* feature_w, const float* feature_b,
+                    const float* alpha_w, const float* alpha_b, const float* rgb_w, const float* rgb_b,
+                    void* stream) {
+  R2L_CHECK_ARG(out_handle != nullptr, "r2l_nerf_create: null out_handle");
+  R2L_CHECK_ARG(dtype == 0 || dtype == 1, "r2l_nerf_create: dtype must be 0 (fp16) or 1 (bf16)");
+  R2L_CHECK_ARG(pts_w && pts_b && views_w && views_b && feature_w && feature_b && alpha_w && alpha_b && rgb_w && rgb_b,
+                "r2l_nerf_create: null weight pointer");
+  for (int i = 0; i < 8; ++i) R2L_CHECK_ARG(pts_w[i] && pts_b[i], "r2l_nerf_create: null pts_linears[%d]", i);
+  auto st = static_cast<cudaStream_t>(stream);
+  Mlp* m = new Mlp();
+  m->kind = 0;
+  m->bf16 = dtype == 1;
+  std::vector<int*> scratch;
+  auto cleanup = [&](int rc) {
+    cudaStreamSynchronize(st);
+    for (int* s : scratch) cudaFree(s);
+    if (rc != R2L_OK) destroy(m);
+    return rc;
+  };
+  // stage stream: L0 (K 64) | L1..4 (K 256) | L5 (K 320) | L6,7 | feature | views (N 128, K 256)
+  const size_t elems = 256ull * (64 + 4 * 256 + 320 + 2 * 256 + 256) + 128ull * 256;
+  m->wbytes = elems * 2;
+  if (cudaMalloc(reinterpret_cast<void**>(&m->wstream), m->wbytes) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&m->aux), sizeof(float) * kNerfAuxTotal) != cudaSuccess)
+    return cleanup(fail(R2L_ERR_CUDA, "r2l_nerf_create: cudaMalloc failed"));
+  int rc = alloc_debug(m);
+  if (rc != R2L_OK) return cleanup(rc);
+  uint16_t* dst = reinterpret_cast<uint16_t*>(m->wstream);
+  std::vector<int> kmap0(64), kmap5(320);
+  for (int k = 0; k < 64; ++k) kmap0[k] = (k < 63) ? k : -1;
+  for (int k = 0; k < 320; ++k) kmap5[k] = (k < 256) ? (63 + k) : ((k < 319) ? (k - 256) : -1);
+  size_t off = 0;
+  for (int l = 0; l < 8 && rc == R2L_OK; ++l) {
+    if (l == 0) {
+      rc = pack_layer(pts_w[0], 63, 256, 63, 64, &kmap0, 1.0f, dst + off, m->bf16, st, scratch);
+      off += 256ull * 64;
+    } else if (l == 5) {
+      rc = pack_layer(pts_w[5], 319, 256, 319, 320, &kmap5, 1.0f, dst + off, m->bf16, st, scratch);
+      off += 256ull * 320;
+    } else {
+      rc = pack_layer(pts_w[l], 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
+      off += 256ull * 256;
+    }
+  }
+  if (rc == R2L_OK) {
+    rc = pack_layer(feature_w, 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
+    off += 256ull * 256;
+  }
+  if (rc == R2L_OK) {
+    rc = pack_layer(views_w, 283, 128, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
+    off += 128ull * 256;
+  }
+  if (rc != R2L_OK) return cleanup(rc);
+  cudaError_t e = cudaSuccess;
+  for (int l = 0; l < 8 && e == cudaSuccess; ++l)
+    e = cudaMemcpyAsync(m->aux + kNerfAuxBias + l * 256, pts_b[l], 256 * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(m->aux + kNerfAuxBias + 8 * 256, feature_b, 256 * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxAlphaW, alpha_w, 256 * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxRgbW, rgb_w, 384 * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(m->aux + kNerfAuxWvd, 27 * 4, views_w + 256, 283 * 4, 27 * 4, 128, cudaMemcpyDeviceToDevice,
+                          st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxBv, views_b, 128 * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&m->alpha_b, alpha_b, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->rgb_b, rgb_b, 12, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cleanup(fail(R2L_ERR_CUDA, "r2l_nerf_create: %s", cudaGetErrorString(e)));
+  *out_handle = m;
+  return cleanup(R2L_OK);
+}
+
+static int check_dbg(Mlp* m, const char* who) {
+  if (m->dbg_host && m->dbg_host->flag != 0)
+    return fail(R2L_ERR_DEVICE_TRAP, "%s: kernel watchdog fired earlier (block %u thread %u barrier %u parity %u)", who,
+                m->dbg_host->block, m->dbg_host->thread, m->dbg_host->barrier_id, m->dbg_host->parity);
+  return R2L_OK;
+}
+
+// Fused positional encoding + NeRF MLP on n_rays*S samples: raw[r, s, :] = NeRF(embed(o_r + d_r z_rs), embed(v_r)).
+// view_bias_ws: caller-provided workspace of n_rays*128 floats.
+int r2l_nerf_forward(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
+                     const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
+                     const float* z_vals, float* view_bias_ws, float* raw, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_forward: not a NeRF handle");
+  R2L_CHECK_ARG(n_rays >= 0 && S > 0, "r2l_nerf_forward: bad sizes");
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(rays_o && rays_d && viewdirs && z_vals && view_bias_ws && raw, "r2l_nerf_forward: null pointer");
+  R2L_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "r2l_nerf_forward: raw must be 16-byte aligned");
+  int rc = check_dbg(m, "r2l_nerf_forward");
+  if (rc != R2L_OK) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  rc = nerf_view_bias_launch(n_rays, viewdirs, v_stride, 0, m->aux + kNerfAuxWvd, m->aux + kNerfAuxBv, view_bias_ws, st);
+  if (rc != R2L_OK) return rc;
+  NerfParams p{};
+  p.wstream = m->wstream;
+  p.bias = m->aux + kNerfAuxBias;
+  p.alpha_w = m->aux + kNerfAuxAlphaW;
+  p.rgb_w = m->aux + kNerfAuxRgbW;
+  p.alpha_b = m->alpha_b;
+  for (int i = 0; i < 3; ++i) p.rgb_b[i] = m->rgb_b[i];
+  p.vb = view_bias_ws;
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.o_stride = o_stride;
+  p.d_stride = d_stride;
+  p.z_vals = z_vals;
+  p.S = S;
+  p.n_rows = n_rays * S;
+  p.raw = raw;
+  const long long n_tiles = (p.n_rows + kTileM - 1) / kTileM;
+  R2L_CHECK_ARG(n_tiles < (1LL << 31), "r2l_nerf_forward: too many samples for one call");
+  p.n_tiles = static_cast<int>(n_tiles);
+  p.dbg = m->dbg_dev;
+  p.embedded = nullptr;
+  p.emb_stride = 0;
+  const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  return nerf_mlp_launch(m->bf16, p, grid, st);
+}
+
+// NeRF.forward(x) API path: x [M, ldx] holds 63 embedded-point features followed by 27
+// embedded-view features per row (model/nerf_raybased.py:377-401).  out [M, 4] = (rgb, sigma).
+int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long long ldx, float* view_bias_ws,
+                              float* out, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_forward_embedded: not a NeRF handle");
+  R2L_CHECK_ARG(M >= 0 && ldx >= 90, "r2l_nerf_forward_embedded: bad sizes");
+  if (M == 0) return R2L_OK;
+  R2L_CHECK_ARG(x && view_bias_ws && out, "r2l_nerf_forward_embedded: null pointer");
+  R2L_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "r2l_nerf_forward_embedded: out must be 16-byte aligned");
+  int rc = check_dbg(m, "r2l_nerf_forward_embedded");
+  if (rc != R2L_OK) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  rc = nerf_view_bias_launch(M, x + 63, ldx, 1, m->aux + kNerfAuxWvd, m->aux + kNerfAuxBv, view_bias_ws, st);
+  if (rc != R2L_OK) return rc;
+  NerfParams p{};
+  p.wstream = m->wstream;
+  p.bias = m->aux + kNerfAuxBias;
+  p.alpha_w = m->aux + kNerfAuxAlphaW;
+  p.rgb_w = m->aux + kNerfAuxRgbW;
+  p.alpha_b = m->alpha_b;
+  for (int i = 0; i < 3; ++i) p.rgb_b[i] = m->rgb_b[i];
+  p.vb = view_bias_ws;
+  p.S = 1;
+  p.n_rows = M;
+  p.raw = out;
+  const long long n_tiles = (M + kTileM - 1) / kTileM;
+  R2L_CHECK_ARG(n_tiles < (1LL << 31), "r2l_nerf_forward_embedded: too many rows for one call");
+  p.n_tiles = static_cast<int>(n_tiles);
+  p.dbg = m->dbg_dev;
+  p.embedded = x;
+  p.emb_stride = ldx;
+  const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  return nerf_mlp_launch(m->bf16, p, grid, st);
+}
+
+// ------------------------------- R2L ----------------------------------------------
+// head_w [256, n_points*63] (reference PositionalEmbedder feature order, model:198-208),
+// w1[b]/w2[b] [256,256] = body.{b}.body.{0,2}.weight (model:443-465), tail_w [3,256].
+int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, const float* head_w,
+                      const float* head_b, const float* const* w1, const float* const* b1, const float* const* w2,
+                      const float* const* b2, double res_scale, const float* tail_w, const float* tail_b,
+                      int sigmoid_out, int outer_skip, void* stream) {
+  R2L_CHECK_ARG(out_handle != nullptr, "r2l_resmlp_create: null out_handle");
+  R2L_CHECK_ARG(dtype == 0 || dtype == 1, "r2l_resmlp_create: dtype must be 0 (fp16) or 1 (bf16)");
+  R2L_CHECK_ARG(n_points >= 4 && n_points % 4 == 0 && n_points <= 256,
+                "r2l_resmlp_create: n_points must be a multiple of 4 in [4,256] (got %d)", n_points);
+  R2L_CHECK_ARG(n_blocks >= 1 && n_blocks <= 1024, "r2l_resmlp_create: bad n_blocks");
+  R2L_CHECK_ARG(head_w && head_b && w1 && b1 && w2 && b2 && tail_w && tail_b, "r2l_resmlp_create: null pointer");
+  auto st = static_cast<cudaStream_t>(stream);
+  Mlp* m = new Mlp();
+  m->kind = 1;
+  m->bf16 = dtype == 1;
+  m->n_points = n_points;
+  m->n_blocks = n_blocks;
+  m->sigmoid_out = sigmoid_out;
+  m->outer_skip = outer_skip;
+  std::vector<int*> scratch;
+  const float** d_b2 = nullptr;
+  auto cleanup = [&](int rc) {
+    cudaStreamSynchronize(st);
+    for (int* s : scratch) cudaFree(s);
+    if (d_b2) cudaFree(d_b2);
+    if (rc != R2L_OK) destroy(m);
+    return rc;
+  };
+  const int K_head = n_points * 64;
+  const size_t elems = 256ull * K_head + static_cast<size_t>(n_blocks) * 2 * 256 * 256;
+  m->wbytes = elems * 2;
+  const size_t aux_floats = 256 + 2ull * n_blocks * 256 + 768;
+  if (cudaMalloc(reinterpret_cast<void**>(&m->wstream), m->wbytes) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&m->aux), sizeof(float) * aux_floats) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&d_b2), sizeof(float*) * n_blocks) != cudaSuccess)
+    return cleanup(fail(R2L_ERR_CUDA, "r2l_resmlp_create: cudaMalloc failed"));
+  int rc = alloc_debug(m);
+  if (rc != R2L_OK) return cleanup(rc);
+  // head K order: point block s, in-block index i (see encode_point_block) <- reference column (3s+c)*21 + f'
+  std::vector<int> kmap(K_head);
+  for (int s = 0; s < n_points; ++s) {
+    for (int i = 0; i < 64; ++i) {
+      int ref = -1;
+      if (i < 3) {
+        ref = (3 * s + i) * 21 + 20;
+      } else if (i < 63) {
+        const int f = (i - 3) / 6, rem = (i - 3) % 6;
+        ref = (rem < 3) ? ((3 * s + rem) * 21 + f) : ((3 * s + rem - 3) * 21 + 10 + f);
+      }
+      kmap[s * 64 + i] = ref;
+    }
+  }
+  uint16_t* dst = reinterpret_cast<uint16_t*>(m->wstream);
+  size_t off = 0;
+  rc = pack_layer(head_w, static_cast<long long>(n_points) * 63, 256, n_points * 63, K_head, &kmap, 1.0f, dst, m->bf16,
+                  st, scratch);
+  off += 256ull * K_head;
+  for (int b = 0; b < n_blocks && rc == R2L_OK; ++b) {
+    R2L_CHECK_ARG(w1[b] && b1[b] && w2[b] && b2[b], "r2l_resmlp_create: null block %d", b);
+    rc = pack_layer(w1[b], 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
+    off += 256ull * 256;
+    if (rc == R2L_OK)
+      rc = pack_layer(w2[b], 256, 256, 256, 256, nullptr, static_cast<float>(res_scale), dst + off, m->bf16, st,
+                      scratch);
+    off += 256ull * 256;
+  }
+  if (rc != R2L_OK) return cleanup(rc);
+  float* a_bhead = m->aux;
+  float* a_b1 = m->aux + 256;
+  float* a_cb = a_b1 + static_cast<size_t>(n_blocks) * 256;
+  float* a_wt = a_cb + static_cast<size_t>(n_blocks) * 256;
+  cudaError_t e = cudaMemcpyAsync(a_bhead, head_b, 256 * 4, cudaMemcpyDeviceToDevice, st);
+  for (int b = 0; b < n_blocks && e == cudaSuccess; ++b)
+    e = cudaMemcpyAsync(a_b1 + static_cast<size_t>(b) * 256, b1[b], 256 * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(a_wt, tail_w, 768 * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_b2, b2, sizeof(float*) * n_blocks, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    cumulative_bias_kernel<<<1, 256, 0, st>>>(d_b2, n_blocks, 256, res_scale, a_cb);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->b_tail, tail_b, 12, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cleanup(fail(R2L_ERR_CUDA, "r2l_resmlp_create: %s", cudaGetErrorString(e)));
+  *out_handle = m;
+  return cleanup(R2L_OK);
+}
+
+static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_stride, const float* embedded,
+                      long long emb_stride, float* rgb, cudaStream_t st) {
+  R2lParams p{};
+  p.wstream = m->wstream;
+  p.b_head = m->aux;
+  p.b1 = m->aux + 256;
+  p.cb = p.b1 + static_cast<size_t>(m->n_blocks) * 256;
+  p.w_tail = p.cb + static_cast<size_t>(m->n_blocks) * 256;
+  for (int i = 0; i < 3; ++i) p.b_tail[i] = m->b_tail[i];
+  p.n_blocks = m->n_blocks;
+  p.n_points = m->n_points;
+  p.pts = pts;
+  p.pts_stride = pts_stride;
+  p.n_rays = n_rays;
+  p.rgb = rgb;
+  p.sigmoid_out = m->sigmoid_out;
+  p.outer_skip = m->outer_skip;
+  const long long n_tiles = (n_rays + kTileM - 1) / kTileM;
+  R2L_CHECK_ARG(n_tiles < (1LL << 31), "r2l_resmlp_forward: too many rays for one call");
+  p.n_tiles = static_cast<int>(n_tiles);
+  p.dbg = m->dbg_dev;
+  p.embedded = embedded;
+  p.emb_stride = emb_stride;
+  const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  return r2l_mlp_launch(m->bf16, p, grid, st);
+}
+
+// Fused PositionalEmbedder + NeRF_v3_2 on sampled points: pts [n_rays, n_points*3] -> rgb [n_rays, 3].
+int r2l_resmlp_forward(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
+                       void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 1, "r2l_resmlp_forward: not an R2L handle");
+  R2L_CHECK_ARG(n_rays >= 0 && pts_stride >= 3LL * m->n_points, "r2l_resmlp_forward: bad sizes");
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(pts && rgb, "r2l_resmlp_forward: null pointer");
+  int rc = check_dbg(m, "r2l_resmlp_forward");
+  if (rc != R2L_OK) return rc;
+  return resmlp_run(m, n_rays, pts, pts_stride, nullptr, 0, rgb, static_cast<cudaStream_t>(stream));
+}
+
+// NeRF_v3_2.forward(x) API path: x [n_rays, ldx] is the reference-layout embedding (n_points*63 features).
+int r2l_resmlp_forward_embedded(void* handle, long long n_rays, const float* x, long long ldx, float* rgb,
+                                void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 1, "r2l_resmlp_forward_embedded: not an R2L handle");
+  R2L_CHECK_ARG(n_rays >= 0 && ldx >= 63LL * m->n_points, "r2l_resmlp_forward_embedded: bad sizes");
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(x && rgb, "r2l_resmlp_forward_embedded: null pointer");
+  int rc = check_dbg(m, "r2l_resmlp_forward_embedded");
+  if (rc != R2L_OK) return rc;
+  return resmlp_run(m, n_rays, nullptr, 0, x, ldx, rgb, static_cast<cudaStream_t>(stream));
+}
+
+int r2l_mlp_destroy(void* handle) {
+  destroy(static_cast<Mlp*>(handle));
+  return R2L_OK;
+}
+
+// 0 = healthy; otherwise the watchdog record of the first barrier that timed out.
+int r2l_mlp_status(void* handle, unsigned int* out8) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr, "r2l_mlp_status: null handle");
+  if (out8 != nullptr && m->dbg_host != nullptr) memcpy(out8, m->dbg_host, sizeof(DebugBuf));
+  return (m->dbg_host && m->dbg_host->flag) ? R2L_ERR_DEVICE_TRAP : R2L_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+// Hierarchical inverse-CDF sampling (sample_pdf) and the sorted merge of coarse and
+// fine depths.  Reference: utils/run_nerf_raybased_helpers.py:283-330, called from
+// main.py:722-732 (the reference runs this on the HOST with ATen CPU kernels and
+// round-trips through PCIe every chunk; here it stays on the device).
+//
+// Bit-exactness contract (restated and pinned against torch CPU in oracle/sample_pdf_np.py):
+//   w      = weights + 1e-5f                      one fp32 add
+//   total  = sum(w) in ATen `vectorized_inner_sum` order: 8 vector lanes x 4 interleaved
+//            accumulators, folded 0+=1,2,3; scalar tail summed first, then the 8 lanes
+//            added left to right (rows shorter than 8: the same 4-accumulator scheme on scalars)
+//   pdf    = w / total                            correctly rounded fp32 divide
+//   cdf    = [0, cumsum(pdf)] accumulated in DOUBLE, each entry rounded to fp32.  All partial
+//            sums of these fp32 values are exact in double (values >= ~1e-7, sum <= ~1, < 53
+//            bits of span), so a warp prefix scan gives the same bits as the sequential loop.
+//   inds   = searchsorted(cdf, u, right=True) = #{cdf_j <= u}     branch-free bisection
+//   t      = (u - cdf[below]) / denom ; sample = bins[below] + t*(bins[above]-bins[below])
+//            with separately rounded fp32 sub/div/mul/add (no FMA contraction).
+//
+// One warp per ray: coalesced loads of bins/weights into a per-warp shared-memory row,
+// prefix sum by warp shuffles, every lane then inverts the CDF for Ni/32 samples.
+// Algorithmic HBM bytes per ray: 4*(nb + nb-1) in, 4*Ni out (+ 4*Ni when u is per-ray).
+#include "common.cuh"
+
+namespace r2l {
+
+constexpr int kPdfWarps = 8;
+
+__device__ __forceinline__ double shfl_up_f64_(double v, int delta) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(0xffffffffu, lo, delta);
+  hi = __shfl_up_sync(0xffffffffu, hi, delta);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_idx_f64_(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+// Sum of w[0..n) in ATen-CPU order.  Executed by the whole warp; result valid on every lane.
+__device__ __forceinline__ float aten_row_sum(const float* w, int n, int lane) {
+  float total = 0.0f;
+  if (n < 8) {
+    if (lane == 0) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const int m = n / 4;
+      for (int i = 0; i < m; ++i) {
+        a0 = __fadd_rn(a0, w[4 * i]);
+        a1 = __fadd_rn(a1, w[4 * i + 1]);
+        a2 = __fadd_rn(a2, w[4 * i + 2]);
+        a3 = __fadd_rn(a3, w[4 * i + 3]);
+      }
+      for (int i = 4 * m; i < n; ++i) a0 = __fadd_rn(a0, w[i]);
+      a0 = __fadd_rn(a0, a1);
+      a0 = __fadd_rn(a0, a2);
+      a0 = __fadd_rn(a0, a3);
+      total = a0;
+    }
+    return __shfl_sync(0xffffffffu, total, 0);
+  }
+  const int vec_size = n >> 3;
+  const int size_ilp = vec_size >> 2;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (lane < 8) {
+    for (int i = 0; i < size_ilp; ++i) {
+      const float* p = w + (i * 4) * 8 + lane;
+      a0 = __fadd_rn(a0, p[0]);
+      a1 = __fadd_rn(a1, p[8]);
+      a2 = __fadd_rn(a2, p[16]);
+      a3 = __fadd_rn(a3, p[24]);
+    }
+    for (int i = size_ilp * 4; i < vec_size; ++i) a0 = __fadd_rn(a0, w[i * 8 + lane]);
+    a0 = __fadd_rn(a0, a1);
+    a0 = __fadd_rn(a0, a2);
+    a0 = __fadd_rn(a0, a3);
+  }
+  if (lane == 0) {
+    for (int k = vec_size * 8; k < n; ++k) total = __fadd_rn(total, w[k]);
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const float part = __shfl_sync(0xffffffffu, a0, m);
+    if (lane == 0) total = __fadd_rn(total, part);
+  }
+  return __shfl_sync(0xffffffffu, total, 0);
+}
+
+__global__ void __launch_bounds__(kPdfWarps * 32)
+sample_pdf_kernel(long long n_rays, int nb, int Ni, const float* __restrict__ bins, long long bins_stride,
+                  const float* __restrict__ weights, long long w_stride, const float* __restrict__ u,
+                  int u_per_ray, float* __restrict__ samples, long long* __restrict__ inds_out, int row_pad) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float* s_w = sm + static_cast<size_t>(wib) * 3 * row_pad;
+  float* s_cdf = s_w + row_pad;
+  float* s_bins = s_cdf + row_pad;
+  const int nw = nb - 1;
+  // largest power of two <= nb, first bisection step
+  int p2 = 1;
+  while ((p2 << 1) <= nb) p2 <<= 1;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kPdfWarps + wib;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kPdfWarps;
+  for (long long ray = warp0; ray < n_rays; ray += nwarps) {
+    const float* rb = bins + ray * bins_stride;
+    const float* rw = weights + ray * w_stride;
+    for (int j = lane; j < nb; j += 32) s_bins[j] = __ldg(rb + j);
+    for (int j = lane; j < nw; j += 32) s_w[j] = __fadd_rn(__ldg(rw + j), 1e-5f);
+    __syncwarp();
+    const float total = aten_row_sum(s_w, nw, lane);
+    // cdf = [0, cumsum(pdf)] in double
+    double carry = 0.0;
+    if (lane == 0) s_cdf[0] = 0.0f;
+    for (int c0 = 0; c0 < nw; c0 += 32) {
+      const int j = c0 + lane;
+      double p = (j < nw) ? static_cast<double>(__fdiv_rn(s_w[j], total)) : 0.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double q = shfl_up_f64_(p, o);
+        if (lane >= o) p += q;
+      }
+      if (j < nw) s_cdf[j + 1] = static_cast<float>(carry + p);
+      carry += shfl_idx_f64_(p, 31);
+    }
+    __syncwarp();
+    for (int k = lane; k < Ni; k += 32) {
+      const float uk = u_per_ray ? __ldg(u + ray * Ni + k) : __ldg(u + k);
+      int pos = 0;
+      for (int s = p2; s > 0; s >>= 1) {
+        const int np = pos + s;
+        if (np <= nb && s_cdf[np - 1] <= uk) pos = np;
+      }
+      const int below = max(pos - 1, 0);
+      const int above = min(pos, nb - 1);
+      const float cb = s_cdf[below], ca = s_cdf[above];
+      const float bb = s_bins[below], ba = s_bins[above];
+      float denom = __fsub_rn(ca, cb);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(uk, cb), denom);
+      samples[ray * Ni + k] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+      if (inds_out != nullptr) inds_out[ray * Ni + k] = pos;
+    }
+    __syncwarp();
+  }
+}
+
+// z_out = sort(cat[z_a, z_b]) per ray (values only, ascending; main.py:730-732) and
+// z_std = std(z_b, unbiased=False) (main.py:750).  Warp-level bitonic sort in shared memory.
+__global__ void __launch_bounds__(kPdfWarps * 32)
+merge_sort_kernel(long long n_rays, int na, int nbv, const float* __restrict__ za, const float* __restrict__ zb,
+                  float* __restrict__ z_out, float* __restrict__ z_std, int P) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float* s = sm + static_cast<size_t>(wib) * P;
+  const int n = na + nbv;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kPdfWarps + wib;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kPdfWarps;
+  for (long long ray = warp0; ray < n_rays; ray += nwarps) {
+    for (int j = lane; j < na; j += 32) s[j] = __ldg(za + ray * na + j);
+    double sum = 0.0;
+    for (int j = lane; j < nbv; j += 32) {
+      const float v = __ldg(zb + ray * nbv + j);
+      s[na + j] = v;
+      sum += static_cast<double>(v);
+    }
+    for (int j = n + lane; j < P; j += 32) s[j] = __int_as_float(0x7f800000);  // +inf padding
+    __syncwarp();
+    if (z_std != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int lo = __double2loint(sum), hi = __double2hiint(sum);
+        lo = __shfl_xor_sync(0xffffffffu, lo, o);
+        hi = __shfl_xor_sync(0xffffffffu, hi, o);
+        sum += __hiloint2double(hi, lo);
+      }
+      const double mean = sum / nbv;
+      double ss = 0.0;
+      for (int j = lane; j < nbv; j += 32) {
+        const double d = static_cast<double>(s[na + j]) - mean;
+        ss += d * d;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int lo = __double2loint(ss), hi = __double2hiint(ss);
+        lo = __shfl_xor_sync(0xffffffffu, lo, o);
+        hi = __shfl_xor_sync(0xffffffffu, hi, o);
+        ss += __hiloint2double(hi, lo);
+      }
+      if (lane == 0) z_std[ray] = static_cast<float>(sqrt(ss / nbv));
+    }
+    // bitonic sort of P elements
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < P; i += 32) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const float a = s[i], b = s[ixj];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) {
+              s[i] = b;
+              s[ixj] = a;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (int j = lane; j < n; j += 32) z_out[ray * n + j] = s[j];
+    __syncwarp();
+  }
+}
+
+}  // namespace r2l
+
+using namespace r2l;
+
+extern "C" {
+
+int r2l_sample_pdf(long long n_rays, int nb, int Ni, const float* bins, long long bins_stride,
+                   const float* weights, long long w_stride, const float* u, int u_per_ray, float* samples,
+                   long long* inds_out, void* stream) {
+  R2L_CHECK_ARG(n_rays >= 0 && nb >= 2 && Ni > 0, "r2l_sample_pdf: bad sizes");
+  R2L_CHECK_ARG(nb - 1 < 512, "r2l_sample_pdf: rows of >= 512 weights are not supported (ATen cascade sum)");
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(bins && weights && u && samples, "r2l_sample_pdf: null pointer");
+  R2L_CHECK_ARG(bins_stride >= nb && w_stride >= nb - 1, "r2l_sample_pdf: bad strides");
+  const int row_pad = ((nb + 31) / 32) * 32;
+  const size_t smem = static_cast<size_t>(kPdfWarps) * 3 * row_pad * sizeof(float);
+  long long blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (smem > 48 * 1024)
+    R2L_CUDA(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sample_pdf_kernel<<<static_cast<int>(blocks), kPdfWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      n_rays, nb, Ni, bins, bins_stride, weights, w_stride, u, u_per_ray, samples, inds_out, row_pad);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+int r2l_merge_sorted(long long n_rays, int na, int nbv, const float* za, const float* zb, float* z_out,
+                     float* z_std, void* stream) {
+  R2L_CHECK_ARG(n_rays >= 0 && na >= 0 && nbv > 0, "r2l_merge_sorted: bad sizes");
+  R2L_CHECK_ARG(na + nbv <= 4096, "r2l_merge_sorted: more than 4096 depths per ray");
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG((za || na == 0) && zb && z_out, "r2l_merge_sorted: null pointer");
+  int P = 32;
+  while (P < na + nbv) P <<= 1;
+  const size_t smem = static_cast<size_t>(kPdfWarps) * P * sizeof(float);
+  long long blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (smem > 48 * 1024)
+    R2L_CUDA(cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_sort_kernel<<<static_cast<int>(blocks), kPdfWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      n_rays, na, nbv, za, zb, z_out, z_std, P);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+}  // extern "C"
