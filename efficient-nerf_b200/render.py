@@ -1,0 +1,217 @@
+"""B200-native stand-in for the render glue of the reference's main.py / utils/create_data.py:
+
+  batchify       main.py:51-62        run_network   main.py:65-87
+  batchify_rays  main.py:90-104       render        main.py:107-186
+  raw2outputs    main.py:556-621      render_rays   main.py:624-756
+  (utils/create_data.py:41-176, 335-544 are identical copies whose render_rays also returns
+   'depth_map' — pass return_depth=True, or use `render_rays_create_data`.)
+
+`render_rays` keeps the reference signature.  When `network_fn` / `network_fine` are this package's
+`NeRF` modules on the tensor-core path and the ray batch carries view directions, the whole
+coarse -> composite -> sample_pdf -> merge -> fine -> composite chain runs as fused CUDA kernels
+(positional encoding never touches HBM, sample_pdf never leaves the device) and
+`network_query_fn`'s Python chunking is bypassed.  Otherwise `network_query_fn` is called like the
+reference does.  Random draws (perturb, raw_noise_std, non-deterministic u) come from the CPU
+generator in the reference's order (t_rand -> coarse noise -> u -> fine noise) and may be injected.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .nerf_raybased import NeRF
+from .run_nerf_raybased_helpers import (get_rays, ndc_rays, normalize_dirs, raw2outputs, sample_pdf, merge_sorted,
+                                        _host_noise, _make_u)
+
+# rays processed per launch when nothing stochastic forces the reference's chunking
+MAX_RAYS_PER_LAUNCH = 1 << 20
+
+
+def batchify(fn, chunk):
+    """Constructs a version of 'fn' that applies to smaller batches (main.py:51-62)."""
+    if chunk is None:
+        return fn
+
+    def ret(inputs):
+        return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+
+    return ret
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """Prepares inputs and applies network 'fn' (main.py:65-87)."""
+    inputs_flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(inputs_flat)
+    if viewdirs is not None:
+        input_dirs = viewdirs[:, None].expand(inputs.shape)
+        input_dirs_flat = torch.reshape(input_dirs, [-1, input_dirs.shape[-1]])
+        embedded_dirs = embeddirs_fn(input_dirs_flat)
+        embedded = torch.cat([embedded, embedded_dirs], -1)
+    outputs_flat = batchify(fn, netchunk)(embedded)
+    outputs = torch.reshape(outputs_flat, list(inputs.shape[:-1]) + [outputs_flat.shape[-1]])
+    return outputs
+
+
+def _z_vals(near, far, t_vals, lindisp, t_rand):
+    """near/far [N,1] device tensors -> z_vals [N, S] (main.py:676-699)."""
+    N = near.shape[0]
+    S = t_vals.shape[0]
+    dev = near.device
+    nf = torch.cat([near.reshape(N, 1), far.reshape(N, 1)], -1).contiguous()
+    z = torch.empty((N, S), dtype=torch.float32, device=dev)
+    tr = _lib.as_f32_cuda(t_rand, dev, "t_rand") if t_rand is not None else None
+    with torch.cuda.device(dev):
+        _lib.call("r2l_z_vals", N, S, _lib.ptr(nf), _lib.ptr(nf[:, 1:]), 2, _lib.ptr(t_vals), int(bool(lindisp)),
+                  _lib.ptr(tr), _lib.ptr(z), _lib.stream_ptr(dev))
+    return z
+
+
+def _points(rays_o, rays_d, z_vals):
+    N, S = z_vals.shape
+    pts = torch.empty((N, S, 3), dtype=torch.float32, device=z_vals.device)
+    with torch.cuda.device(z_vals.device):
+        _lib.call("r2l_points_from_rays", N, S, _lib.ptr(rays_o), rays_o.stride(0), _lib.ptr(rays_d),
+                  rays_d.stride(0), _lib.ptr(z_vals), S, _lib.ptr(pts), _lib.stream_ptr(z_vals.device))
+    return pts
+
+
+def _fused_ok(net, viewdirs):
+    return (isinstance(net, NeRF) and viewdirs is not None and net.precision != "fp32"
+            and net.supports_tensor_core_path())
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
+                return_depth=False, t_rand=None, u=None, noise0=None, noise1=None, return_debug=False):
+    """Volumetric rendering of a batch of rays (main.py:624-756).  Returns the reference's dict."""
+    rb = _lib.as_f32_cuda(ray_batch, name="ray_batch")
+    dev = rb.device
+    N_rays = rb.shape[0]
+    rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]
+    viewdirs = rb[:, -3:] if rb.shape[-1] > 8 else None
+    near, far = rb[:, 6:7], rb[:, 7:8]
+
+    t_vals = torch.linspace(0., 1., steps=N_samples).to(dev)  # host linspace, uploaded (main.py:676)
+    if perturb > 0. and t_rand is None:
+        if pytest:
+            np.random.seed(0)
+            t_rand = torch.Tensor(np.random.rand(N_rays, N_samples))
+        else:
+            t_rand = torch.rand((N_rays, N_samples))  # CPU generator (main.py:691)
+    z_vals = _z_vals(near, far, t_vals, lindisp, t_rand if perturb > 0. else None)
+
+    def query(z, net):
+        if _fused_ok(net, viewdirs):
+            return net.forward_samples(rays_o, rays_d, viewdirs, z)
+        return network_query_fn(_points(rays_o, rays_d, z), viewdirs, net)
+
+    raw = query(z_vals, network_fn)
+    if noise0 is None and raw_noise_std > 0.:
+        noise0 = _host_noise((N_rays, N_samples), raw_noise_std, pytest)
+    rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd,
+                                                                 pytest=pytest, noise=noise0)
+    debug = {}
+    if N_importance > 0:
+        rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
+        z_vals_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        if u is None:
+            u, _ = _make_u([N_rays], N_importance, det=(perturb == 0.), pytest=pytest)
+        if return_debug:
+            z_samples, inds = sample_pdf(z_vals_mid, weights[..., 1:-1], N_importance, u=u, return_inds=True)
+            debug.update(z_vals0=z_vals, weights0=weights, raw0=raw, inds=inds, z_samples=z_samples)
+        else:
+            z_samples = sample_pdf(z_vals_mid, weights[..., 1:-1], N_importance, u=u)
+        z_vals, z_std = merge_sorted(z_vals, z_samples, want_std=True)
+        run_fn = network_fn if network_fine is None else network_fine
+        raw = query(z_vals, run_fn)
+        if noise1 is None and raw_noise_std > 0.:
+            noise1 = _host_noise((N_rays, N_samples + N_importance), raw_noise_std, pytest)
+        rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd,
+                                                                     pytest=pytest, noise=noise1)
+
+    ret = {'rgb_map': rgb_map, 'disp_map': disp_map, 'acc_map': acc_map}
+    if return_depth:
+        ret['depth_map'] = depth_map
+    if retraw:
+        ret['raw'] = raw
+    if N_importance > 0:
+        ret['rgb0'] = rgb_map_0
+        ret['disp0'] = disp_map_0
+        ret['acc0'] = acc_map_0
+        ret['z_std'] = z_std
+    if return_debug:
+        debug.update(z_vals=z_vals, weights=weights)
+        ret['debug'] = debug
+    return ret
+
+
+def render_rays_create_data(ray_batch, network_fn, network_query_fn, N_samples, **kwargs):
+    """utils/create_data.py:405-544 flavour: same as render_rays plus 'depth_map'."""
+    kwargs['return_depth'] = True
+    return render_rays(ray_batch, network_fn, network_query_fn, N_samples, **kwargs)
+
+
+def _is_stochastic(kwargs):
+    return kwargs.get('perturb', 0.) > 0. or kwargs.get('raw_noise_std', 0.) > 0.
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """Render rays in minibatches (main.py:90-104).  Results do not depend on `chunk`; when nothing
+    stochastic pins the reference's draw order the batch is rendered in as few launches as possible."""
+    if not _is_stochastic(kwargs):
+        chunk = max(int(chunk), MAX_RAYS_PER_LAUNCH)
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k in ret:
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
+
+
+def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, **kwargs):
+    """Render a full image (c2w) or a ray batch (main.py:107-186).
+    Returns [rgb_map, disp_map, acc_map, extras-dict] with the reference's shapes."""
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, focal, c2w)
+    else:
+        rays_o, rays_d = rays
+        rays_o = _lib.as_f32_cuda(rays_o, name="rays_o")
+        rays_d = _lib.as_f32_cuda(rays_d, rays_o.device, "rays_d")
+    viewdirs = None
+    if use_viewdirs:
+        viewdirs = rays_d
+        if c2w_staticcam is not None:
+            rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
+        viewdirs = normalize_dirs(viewdirs)  # [N, 3]
+    sh = rays_d.shape
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near_t, far_t = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    rays_flat = torch.cat([rays_o, rays_d, near_t, far_t], -1)
+    if use_viewdirs:
+        rays_flat = torch.cat([rays_flat, viewdirs], -1)
+    all_ret = batchify_rays(rays_flat, chunk, **kwargs)
+    for k in all_ret:
+        if k == 'debug':
+            continue
+        k_sh = list(sh[:-1]) + list(all_ret[k].shape[1:])
+        all_ret[k] = torch.reshape(all_ret[k], k_sh)
+    k_extract = ['rgb_map', 'disp_map', 'acc_map']
+    ret_list = [all_ret[k] for k in k_extract]
+    ret_dict = {k: all_ret[k] for k in all_ret if k not in k_extract}
+    return ret_list + [ret_dict]
+
+
+def render_r2l(model, point_sampler, c2w, positional_embedder=None):
+    """R2L branch of render_path (main.py:285-325): one frame = one un-chunked forward.
+    Uses the fused encode+MLP kernel when the model supports it; returns rgb [H*W, 3]."""
+    pts = point_sampler.sample_test(c2w)
+    if model.precision != "fp32" and model.supports_tensor_core_path():
+        L = positional_embedder.L if positional_embedder is not None else 10
+        if L == 10 and pts.shape[-1] * 21 == model.input_dim:
+            return model.forward_points(pts)
+    if positional_embedder is None:
+        raise ValueError("positional_embedder is required for the non-fused path")
+    return model(positional_embedder(pts))

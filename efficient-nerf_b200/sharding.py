@@ -1,0 +1,70 @@
+"""Multi-GPU sharding of the rendering path (one process per GPU, torch.distributed).
+
+Every ray is independent, so the path shards with no data-path collective:
+  * many poses (R2L test set, create_data):  rank r renders poses r, r+G, r+2G, ...
+  * one frame:  contiguous ray blocks, multiples of 128 rays so MMA tiles stay full
+The only collective is one all_gather of the finished image tiles (NCCL on GPUs, gloo in CPU tests).
+The reference's equivalent is nn.DataParallel scatter/gather per forward (main.py:37-42, 472-479).
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_poses(n_poses, rank=None, world_size=None):
+    """Indices of the poses this rank renders (round-robin, like a strided test split)."""
+    if rank is None:
+        rank, world_size = world()
+    return list(range(rank, n_poses, world_size))
+
+
+def shard_rays(n_rays, rank=None, world_size=None, multiple=128):
+    """[start, stop) of this rank's contiguous ray block; every block but the last is a multiple of
+    `multiple` rays.  Blocks cover [0, n_rays) exactly once and differ by at most `multiple` rays."""
+    if rank is None:
+        rank, world_size = world()
+    n_units = (n_rays + multiple - 1) // multiple
+    base, rem = divmod(n_units, world_size)
+    u0 = rank * base + min(rank, rem)
+    u1 = u0 + base + (1 if rank < rem else 0)
+    return min(u0 * multiple, n_rays), min(u1 * multiple, n_rays)
+
+
+def gather_rays(local, n_rays, multiple=128, group=None):
+    """All-gather per-rank ray blocks [n_local, C] into the full [n_rays, C] tensor on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    bounds = [shard_rays(n_rays, r, ws, multiple) for r in range(ws)]
+    max_len = max(b[1] - b[0] for b in bounds)
+    C = local.shape[1:]
+    pad = torch.zeros((max_len,) + tuple(C), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    outs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:b[1] - b[0]] for o, b in zip(outs, bounds)], 0)
+
+
+def gather_frames(local_frames, n_poses, group=None):
+    """local_frames: list of [H*W, C] tensors for shard_poses(n_poses).  Returns the list of all
+    n_poses frames in pose order on every rank (one all_gather per round of G poses)."""
+    rank, ws = world()
+    if ws == 1:
+        return list(local_frames)
+    frames = [None] * n_poses
+    rounds = (n_poses + ws - 1) // ws
+    proto = local_frames[0]
+    for r in range(rounds):
+        mine = local_frames[r] if r < len(local_frames) else torch.zeros_like(proto)
+        outs = [torch.empty_like(proto) for _ in range(ws)]
+        dist.all_gather(outs, mine.contiguous(), group=group)
+        for k in range(ws):
+            idx = r * ws + k
+            if idx < n_poses:
+                frames[idx] = outs[k]
+    return frames

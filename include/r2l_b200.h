@@ -1,0 +1,142 @@
+/* r2l_b200 — C ABI of the B200-native per-ray rendering hot path (R2L / NeRF).
+ *
+ * Drop-in boundary.  The reference (MingSun-Tse/Efficient-NeRF) has no FFI or operator
+ * registry: its boundary is the Python call surface of utils/run_nerf_raybased_helpers.py,
+ * model/nerf_raybased.py and the render functions in main.py.  Each entry point below is the
+ * device-side body of one of those functions; the Python mirror in efficient-nerf_b200/
+ * (same names and signatures as the reference) allocates outputs with torch and calls these
+ * through ctypes.  See INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; r2l_last_error() gives the text
+ *     (thread-local).  No exceptions cross the ABI.  There is NO CPU fallback.
+ *   - all pointers are DEVICE pointers to fp32 data unless stated otherwise; tensors are
+ *     row-major and contiguous, `*_stride` arguments are row strides in ELEMENTS.
+ *   - `stream` is a cudaStream_t (as void*); calls are asynchronous on that stream.
+ *   - the library never allocates on the hot path: workspaces are passed in by the caller;
+ *     only the *_create functions allocate (packed weights).
+ */
+#ifndef R2L_B200_H_
+#define R2L_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* r2l_last_error(void);
+int r2l_abi_version(void);
+
+/* ---- rays --------------------------------------------------------------------------------- */
+
+/* get_rays(H, W, focal, c2w) -> rays_o, rays_d  [H*W, 3]
+ * replaces utils/run_nerf_raybased_helpers.py:231-257 (and get_rays_np :428-441).
+ * c2w: device [3,4] row-major. */
+int r2l_get_rays(int H, int W, double focal, const float* c2w, float* rays_o, float* rays_d, void* stream);
+
+/* ndc_rays(H, W, focal, near, rays_o, rays_d) -> (o, d)  [n, 3]
+ * replaces utils/run_nerf_raybased_helpers.py:260-279. */
+int r2l_ndc_rays(long long n, int H, int W, double focal, double near, const float* rays_o, const float* rays_d,
+                 float* out_o, float* out_d, void* stream);
+
+/* viewdirs = rays_d / |rays_d|   replaces main.py:148-157. */
+int r2l_normalize_dirs(long long n, const float* dirs, long long stride, float* out, void* stream);
+
+/* z_vals = near*(1-t) + far*t (or lindisp), optional stratified perturbation with caller-supplied
+ * t_rand [n,S] (may be NULL).  replaces main.py:676-699.  near/far: per-ray, stride nf_stride. */
+int r2l_z_vals(long long n, int S, const float* near, const float* far, long long nf_stride, const float* t_vals,
+               int lindisp, const float* t_rand, float* z_out, void* stream);
+
+/* pts[r,s,:] = o_r + d_r * z_rs   replaces main.py:701,733 and model/nerf_raybased.py:114-126
+ * (PointSampler.sample_train; z_stride = 0 shares one z row between all rays). */
+int r2l_points_from_rays(long long n, int S, const float* rays_o, long long o_stride, const float* rays_d,
+                         long long d_stride, const float* z, long long z_stride, float* pts, void* stream);
+
+/* PointSampler.sample_test(c2w) -> pts [H*W, S*3]   replaces model/nerf_raybased.py:76-102. */
+int r2l_point_sample(int H, int W, double focal, const float* c2w, const float* z_vals, int S, float* pts,
+                     void* stream);
+
+/* ---- positional encoding ------------------------------------------------------------------ */
+
+/* layout 0: Embedder.embed (utils/run_nerf_raybased_helpers.py:24-74), x [rows, D] -> [rows, D*(1+2L)]
+ * layout 1: PositionalEmbedder.__call__ (model/nerf_raybased.py:191-208), x [rows, D] -> [rows, D*(2L+1)] */
+int r2l_embed(long long rows, int D, int L, int include_input, int layout, const float* x, float* out,
+              void* stream);
+
+/* ---- compositing and hierarchical sampling ------------------------------------------------ */
+
+/* raw2outputs(raw, z_vals, rays_d, noise, white_bkgd) -> rgb_map [n,3], disp_map [n], acc_map [n],
+ * weights [n,S], depth_map [n] (any output may be NULL).  replaces main.py:556-621 and its twins
+ * (utils/create_data.py:335-402, model/nerf_raybased.py:226-295, helpers:77-144).
+ * noise: optional [n,S] already scaled by raw_noise_std. */
+int r2l_raw2outputs(long long n_rays, int S, const float* raw, const float* z_vals, const float* rays_d,
+                    long long d_stride, const float* noise, int white_bkgd, float* rgb_map, float* disp_map,
+                    float* acc_map, float* weights, float* depth_map, void* stream);
+
+/* sample_pdf(bins [n,nb], weights [n,nb-1], u) -> samples [n,Ni] (+ optional searchsorted indices,
+ * int64 [n,Ni]).  replaces utils/run_nerf_raybased_helpers.py:283-330.  u: [Ni] shared by all rays
+ * (det=True linspace) or [n,Ni] (u_per_ray=1); built by the caller exactly like the reference does
+ * on the host.  Bin indices are bit-exact with the reference's CPU path. */
+int r2l_sample_pdf(long long n_rays, int nb, int Ni, const float* bins, long long bins_stride,
+                   const float* weights, long long w_stride, const float* u, int u_per_ray, float* samples,
+                   long long* inds_out, void* stream);
+
+/* z_out = sort(cat[za, zb]) per ray; z_std = std(zb, unbiased=False) (may be NULL).
+ * replaces main.py:730-732 and :750. */
+int r2l_merge_sorted(long long n_rays, int na, int nbv, const float* za, const float* zb, float* z_out,
+                     float* z_std, void* stream);
+
+/* ---- MLPs ---------------------------------------------------------------------------------- */
+
+/* Y = act(X W^T + b [+ R]) in fp32 on CUDA cores (act: 0 none, 1 relu, 2 sigmoid); the
+ * precision="fp32" path of NeRF / ResMLP / NeRF_v3_2 forward (model/nerf_raybased.py:377-401,
+ * 461-465, 539-544) for any architecture.  K, ldx, ldw multiples of 4. */
+int r2l_linear_fp32(long long M, int N, int K, const float* X, long long ldx, const float* W, long long ldw,
+                    const float* bias, float* Y, long long ldy, int act, const float* R, long long ldr,
+                    void* stream);
+
+/* Packed NeRF (D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs) for the fused
+ * tcgen05 kernel.  Weights: reference nn.Linear layout, device fp32 (model/nerf_raybased.py:357-372).
+ * dtype: 0 = fp16 operands, 1 = bf16 operands (fp32 accumulate either way). */
+int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, const float* const* pts_b,
+                    const float* views_w, const float* views_b, const float* feature_w, const float* feature_b,
+                    const float* alpha_w, const float* alpha_b, const float* rgb_w, const float* rgb_b,
+                    void* stream);
+
+/* run_network + NeRF.forward fused (main.py:65-87, model/nerf_raybased.py:377-401):
+ * raw[r,s,:] = NeRF(embed(o_r + d_r z_rs), embed(viewdir_r)).  view_bias_ws: n_rays*128 floats. */
+int r2l_nerf_forward(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
+                     const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
+                     const float* z_vals, float* view_bias_ws, float* raw, void* stream);
+
+/* NeRF.forward(x [M, >=90]) -> [M,4]   (model/nerf_raybased.py:377-401).  view_bias_ws: M*128 floats. */
+int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long long ldx, float* view_bias_ws,
+                              float* out, void* stream);
+
+/* Packed NeRF_v3_2 with ResMLP body (model/nerf_raybased.py:443-544): head Linear(n_points*63, 256),
+ * n_blocks x ResMLP(256, n_learnable=2), tail Linear(256, 3) [+ Sigmoid]. */
+int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, const float* head_w,
+                      const float* head_b, const float* const* w1, const float* const* b1, const float* const* w2,
+                      const float* const* b2, double res_scale, const float* tail_w, const float* tail_b,
+                      int sigmoid_out, int outer_skip, void* stream);
+
+/* model(positional_embedder(pts)) fused (main.py:297-309): pts [n_rays, n_points*3] -> rgb [n_rays,3]. */
+int r2l_resmlp_forward(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
+                       void* stream);
+
+/* NeRF_v3_2.forward(x [n_rays, n_points*63]) -> [n_rays,3]   (model/nerf_raybased.py:539-544). */
+int r2l_resmlp_forward_embedded(void* handle, long long n_rays, const float* x, long long ldx, float* rgb,
+                                void* stream);
+
+int r2l_mlp_destroy(void* handle);
+
+/* 0 = healthy; non-zero if a kernel watchdog fired.  out8: optional 8 x uint32 debug record. */
+int r2l_mlp_status(void* handle, unsigned int* out8);
+
+/* Unit-test probe: D [128,N] = A [128,K] x W [N,K]^T with 16-bit operands on tcgen05. */
+int r2l_tc_gemm_probe(int dtype, int N, int K, const float* A, const float* W, float* D, int swap_lbo_sbo,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2L_B200_H_ */

@@ -1,0 +1,283 @@
+"""GPU parity tests for the MLP kernels (tcgen05 fused NeRF / R2L and the fp32 CUDA-core path) and the
+fused render path, against the CPU oracle and the golden vectors produced by the reference's own code.
+
+Tolerances (north_star): rgb maps within 2e-3 max-abs of the reference, PSNR delta <= 0.05 dB;
+sample_pdf bin indices bit-exact when fed the reference's weights (tests/test_gpu_ops.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import t
+
+pytestmark = pytest.mark.gpu
+
+RGB_TOL = 2e-3
+
+
+def maxabs(a, b):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu() if isinstance(b, torch.Tensor) else t(b)
+    return float((a - b).abs().max())
+
+
+def load_nerf(E, sd, precision):
+    net = E.NeRF(8, 256, 63, 27, 5, [4], True, precision=precision)
+    net.load_state_dict(sd)
+    return net.cuda().eval()
+
+
+def load_r2l(E, O, sd, precision):
+    net = E.NeRF_v3_2(O.r2l_args(), 1008, 3, precision=precision)
+    net.load_state_dict(sd)
+    return net.cuda().eval()
+
+
+# ------------------------------------------------------------------ building blocks
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (256, 320), (128, 256), (16, 32)])
+def test_tcgen05_gemm_probe(E, dtype, N, K):
+    """One tcgen05 GEMM with the operand layout / descriptors the fused kernels use."""
+    torch.manual_seed(N + K)
+    A = torch.randn(128, K, device="cuda")
+    W = torch.randn(N, K, device="cuda")
+    D = torch.full((128, N), float("nan"), device="cuda")
+    E._lib.call("r2l_tc_gemm_probe", dtype, N, K, E._lib.ptr(A), E._lib.ptr(W), E._lib.ptr(D), 0, E._lib.stream_ptr())
+    torch.cuda.synchronize()
+    cast = torch.bfloat16 if dtype == 1 else torch.float16
+    ref = A.to(cast).double() @ W.to(cast).double().t()
+    err = float((D.double() - ref).abs().max())
+    assert err < 1e-3 * K**0.5, f"probe N={N} K={K} dtype={dtype}: max err {err}"
+
+
+def test_linear_fp32(E):
+    from efficient_nerf_b200.nerf_raybased import _linear_fp32
+    torch.manual_seed(0)
+    for M, N, K in ((1000, 256, 63), (513, 128, 283), (300, 3, 128), (257, 1, 256), (4096, 256, 1008)):
+        x, w, b = torch.randn(M, K), torch.randn(N, K) / K**0.5, torch.randn(N)
+        r = torch.randn(M, N)
+        for act, fn in ((0, lambda v: v), (1, torch.relu), (2, torch.sigmoid)):
+            y = _linear_fp32(x.cuda(), w.cuda(), b.cuda(), act)
+            assert maxabs(y, fn(torch.nn.functional.linear(x.double(), w.double(), b.double())).float()) < 2e-5
+        y = _linear_fp32(x.cuda(), w.cuda(), b.cuda(), 0, residual=r.cuda(), scale=0.5)
+        assert maxabs(y, (torch.nn.functional.linear(x, w, b) * 0.5 + r)) < 2e-5
+
+
+# ------------------------------------------------------------------ NeRF
+def test_module_parity_with_reference_layout(E, O):
+    """Same state_dict keys / shapes / seeded init as the reference modules (checkpoints are drop-in)."""
+    sdc, sdf = O.nerf_state_dicts(0)
+    torch.manual_seed(0)
+    c = E.NeRF(8, 256, 63, 27, 5, [4], True)
+    f = E.NeRF(8, 256, 63, 27, 5, [4], True)
+    for net, sd in ((c, sdc), (f, sdf)):
+        msd = net.state_dict()
+        assert set(msd) == set(sd)
+        assert all(torch.equal(msd[k], sd[k]) for k in sd)
+    sd = O.r2l_state_dict(0)
+    torch.manual_seed(0)
+    r = E.NeRF_v3_2(O.r2l_args(), 1008, 3)
+    msd = r.state_dict()
+    assert set(msd) == set(sd) and all(torch.equal(msd[k], sd[k]) for k in sd)
+
+
+def test_nerf_forward_fp32_path(E, O):
+    sdc, _ = O.nerf_state_dicts(0)
+    net = load_nerf(E, sdc, "fp32")
+    torch.manual_seed(1)
+    x = torch.cat([O.embed_nerf((torch.rand(700, 3) * 2 - 1) * 4, 10),
+                   O.embed_nerf(torch.nn.functional.normalize(torch.randn(700, 3), dim=-1), 4)], -1)
+    with torch.no_grad():
+        ref = O.nerf_forward(sdc, x)
+        out = net(x.cuda())
+    assert maxabs(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 2e-3), ("bf16", 2e-2)])
+def test_nerf_forward_tensor_core(E, O, precision, tol):
+    """NeRF.forward(x) API path on tcgen05 vs the fp32 oracle (raw network outputs, pre-compositing)."""
+    sdc, _ = O.nerf_state_dicts(0)
+    net = load_nerf(E, sdc, precision)
+    torch.manual_seed(2)
+    for M in (128, 1000, 129):
+        x = torch.cat([O.embed_nerf((torch.rand(M, 3) * 2 - 1) * 4, 10),
+                       O.embed_nerf(torch.nn.functional.normalize(torch.randn(M, 3), dim=-1), 4)], -1)
+        with torch.no_grad():
+            ref = O.nerf_forward(sdc, x)
+            out = net(x.cuda())
+        torch.cuda.synchronize()
+        assert out.shape == ref.shape
+        assert maxabs(out, ref) < tol, (precision, M, maxabs(out, ref))
+
+
+def test_nerf_fused_encode_matches_api_path(E, O):
+    """forward_samples (encoding fused in-kernel) == forward(embedded) on the same points."""
+    sdc, _ = O.nerf_state_dicts(0)
+    net = load_nerf(E, sdc, "fp16")
+    torch.manual_seed(3)
+    N, S = 37, 64
+    c2w = O.pose_spherical(40., -30., 4.)[:3, :4]
+    ro, rd = O.get_rays(400, 400, O.LEGO["focal"], c2w)
+    idx = torch.arange(0, 160000, 4321)[:N]
+    ro, rd = ro.reshape(-1, 3)[idx].contiguous(), rd.reshape(-1, 3)[idx].contiguous()
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    z = torch.sort(torch.rand(N, S) * 4 + 2, -1)[0]
+    with torch.no_grad():
+        raw = net.forward_samples(ro.cuda(), rd.cuda(), vd.cuda(), z.cuda())
+        pts = ro[:, None, :] + rd[:, None, :] * z[..., None]
+        ref = O.run_network(pts, vd, sdc)
+    assert maxabs(raw, ref) < 2e-3
+
+
+def render_golden(E, O, golden, name, precision):
+    g = golden(name)
+    sdc, sdf = O.nerf_state_dicts(0)
+    coarse, fine = load_nerf(E, sdc, precision), load_nerf(E, sdf, precision)
+    fern = name.endswith("fern")
+    cam = O.FERN if fern else O.LEGO
+    rays = torch.stack([t(g["rays_o"]), t(g["rays_d"])], 0).cuda()
+    kw = dict(network_query_fn=None, perturb=0., N_importance=64 if fern else 128, network_fine=fine, N_samples=64,
+              network_fn=coarse, use_viewdirs=True, white_bkgd=not fern, raw_noise_std=0., ndc=fern, lindisp=False,
+              near=0. if fern else 2., far=1. if fern else 6., retraw=True)
+    with torch.no_grad():
+        rgb, disp, acc, extras = E.render_image(cam["H"], cam["W"], cam["focal"], chunk=32768, rays=rays, **kw)
+    return g, rgb, disp, acc, extras
+
+
+@pytest.mark.parametrize("name", ["nerf_render_lego", "nerf_render_fern"])
+def test_render_rays_fused_vs_reference(E, O, golden, name):
+    """Full hierarchical render (coarse 64 + fine 128|64) vs the reference's outputs: rgb within 2e-3."""
+    g, rgb, disp, acc, extras = render_golden(E, O, golden, name, "fp16")
+    assert set(extras) >= {"raw", "rgb0", "disp0", "acc0", "z_std"}
+    assert maxabs(rgb, g["rgb_map"]) <= RGB_TOL, maxabs(rgb, g["rgb_map"])
+    assert maxabs(extras["rgb0"], g["rgb0"]) <= RGB_TOL
+    assert maxabs(acc, g["acc_map"]) <= RGB_TOL
+    assert maxabs(extras["z_std"], g["z_std"]) <= 5e-3
+    # PSNR delta against a common target (the reference frame of the OTHER config's pixels is not available
+    # here; use a fixed pseudo-target so that the delta is defined): <= 0.05 dB
+    torch.manual_seed(0)
+    target = torch.rand_like(t(g["rgb_map"]))
+    assert abs(O.psnr(rgb.cpu(), target) - O.psnr(t(g["rgb_map"]), target)) <= 0.05
+
+
+def test_render_rays_fp32_path_matches_reference_tightly(E, O, golden):
+    """precision='fp32' goes through network_query_fn (run_network + Embedder + NeRF.forward on CUDA cores):
+    every stage then matches the reference to ~1e-5, which pins the glue (z_vals, compositing, sample_pdf,
+    merge) independently of tensor-core rounding."""
+    g = golden("nerf_render_lego")
+    sdc, sdf = O.nerf_state_dicts(0)
+    coarse, fine = load_nerf(E, sdc, "fp32"), load_nerf(E, sdf, "fp32")
+    embed_fn, _ = E.get_embedder(10, 0)
+    embeddirs_fn, _ = E.get_embedder(4, 0)
+    nq = lambda i, v, f: E.run_network(i, v, f, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn, netchunk=65536)
+    rays = torch.stack([t(g["rays_o"]), t(g["rays_d"])], 0).cuda()
+    kw = dict(network_query_fn=nq, perturb=0., N_importance=128, network_fine=fine, N_samples=64, network_fn=coarse,
+              use_viewdirs=True, white_bkgd=True, raw_noise_std=0., ndc=False, lindisp=False, near=2., far=6.,
+              retraw=True)
+    with torch.no_grad():
+        rgb, disp, acc, extras = E.render_image(400, 400, O.LEGO["focal"], chunk=32768, rays=rays, **kw)
+    assert maxabs(extras["rgb0"], g["rgb0"]) < 2e-5
+    assert maxabs(rgb, g["rgb_map"]) < 1e-4
+    assert maxabs(acc, g["acc_map"]) < 1e-4
+
+
+def test_render_stochastic_path_with_injected_draws(E, O, golden):
+    """create_data flavour (perturb=1, raw_noise_std=1): same CPU-generator draws as the reference."""
+    g = golden("nerf_render_lego")
+    gp = golden("nerf_render_perturb")
+    sdc, sdf = O.nerf_state_dicts(0)
+    coarse, fine = load_nerf(E, sdc, "fp16"), load_nerf(E, sdf, "fp16")
+    batch = O.pack_rays(t(g["rays_o"])[:16], t(g["rays_d"])[:16], 2., 6.)
+    torch.manual_seed(int(gp["seed"]))
+    with torch.no_grad():
+        ret = E.render_rays_create_data(batch.cuda(), coarse, None, 64, perturb=1., N_importance=128,
+                                        network_fine=fine, white_bkgd=True, raw_noise_std=1.0)
+    assert "depth_map" in ret
+    # sigma noise of std 1 on random-init (tiny) densities dominates the image, so agreement here
+    # shows that the draws were consumed in the reference's order
+    assert maxabs(ret["rgb_map"], gp["rgb_map"]) <= 5e-3
+    assert maxabs(ret["z_std"], gp["z_std"]) <= 5e-3
+
+
+def test_render_chunk_invariance_and_tail_tiles(E, O):
+    sdc, sdf = O.nerf_state_dicts(0)
+    coarse, fine = load_nerf(E, sdc, "fp16"), load_nerf(E, sdf, "fp16")
+    c2w = O.pose_spherical(10., -30., 4.)[:3, :4]
+    ro, rd = O.get_rays(400, 400, O.LEGO["focal"], c2w)
+    idx = torch.arange(0, 160000, 531)[:301]   # 301 rays: 64*301 and 192*301 are not multiples of 128
+    batch = O.pack_rays(ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx], 2., 6.).cuda()
+    kw = dict(network_query_fn=None, N_samples=64, N_importance=128, network_fine=fine, white_bkgd=True)
+    with torch.no_grad():
+        a = E.render_rays(batch, coarse, **kw)
+        b1 = E.render_rays(batch[:100], coarse, **kw)
+        b2 = E.render_rays(batch[100:], coarse, **kw)
+    for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "z_std"):
+        assert torch.equal(a[k], torch.cat([b1[k], b2[k]], 0)), k   # independent of chunking, bit for bit
+    assert bool(torch.isfinite(a["rgb_map"]).all())
+
+
+# ------------------------------------------------------------------ R2L
+def test_r2l_fp32_path(E, O, golden):
+    g = golden("r2l_lego")
+    sd = O.r2l_state_dict(0)
+    net = load_r2l(E, O, sd, "fp32")
+    pe = E.PositionalEmbedder(L=10)
+    with torch.no_grad():
+        rgb = net(pe(t(g["pts"]).cuda()))
+    assert maxabs(rgb, g["rgb"]) < 2e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", RGB_TOL), ("bf16", 1.5e-2)])
+def test_r2l_fused_vs_reference(E, O, golden, precision, tol):
+    """PointSampler -> (fused PositionalEmbedder + W256 D88 ResMLP) vs the reference's rgb."""
+    g = golden("r2l_lego")
+    sd = O.r2l_state_dict(0)
+    net = load_r2l(E, O, sd, precision)
+    pts = t(g["pts"]).cuda()
+    with torch.no_grad():
+        rgb = net.forward_points(pts)
+        torch.cuda.synchronize()
+        assert maxabs(rgb, g["rgb"]) <= tol, (precision, maxabs(rgb, g["rgb"]))
+        # API path: model(positional_embedder(pts)) with a materialised embedding, and the lazy handle
+        pe = E.PositionalEmbedder(L=10)
+        rgb_api = net(pe(pts))
+        assert maxabs(rgb_api, g["rgb"]) <= tol
+        rgb_lazy = net(E.PositionalEmbedder(L=10, lazy=True)(pts))
+        assert torch.equal(rgb_lazy, rgb)
+        # ragged batch (tail tile) and a single ray
+        rgb_r = net.forward_points(pts[:77])
+        assert torch.equal(rgb_r, rgb[:77])
+        assert torch.equal(net.forward_points(pts[5:6]), rgb[5:6])
+
+
+def test_r2l_full_frame_properties(E, O):
+    """BASELINE size: one 400x400 frame in one un-chunked forward; sharded == unsharded."""
+    sd = O.r2l_state_dict(0)
+    net = load_r2l(E, O, sd, "fp16")
+    c2w = O.pose_spherical(-180., -30., 4.)[:3, :4].cuda()
+    ps = E.PointSampler(400, 400, O.LEGO["focal"], 16, 2., 6.)
+    with torch.no_grad():
+        rgb = E.render_r2l(net, ps, c2w)
+        assert tuple(rgb.shape) == (160000, 3)
+        assert bool(torch.isfinite(rgb).all()) and float(rgb.min()) >= 0. and float(rgb.max()) <= 1.
+        pts = ps.sample_test(c2w)
+        parts = []
+        for r in range(8):
+            s0, s1 = E.sharding.shard_rays(160000, r, 8)
+            parts.append(net.forward_points(pts[s0:s1]))
+        assert torch.equal(torch.cat(parts, 0), rgb)
+        ref = O.render_r2l(sd, 400, 400, O.LEGO["focal"], 2., 6., c2w.cpu(), rows=torch.arange(0, 160000, 1601))
+    assert maxabs(rgb[::1601], ref) <= RGB_TOL
+
+
+def test_nerf_full_frame_properties(E, O):
+    """BASELINE config 1 at full size (160 000 rays, 64 + 128 samples)."""
+    sdc, sdf = O.nerf_state_dicts(0)
+    coarse, fine = load_nerf(E, sdc, "fp16"), load_nerf(E, sdf, "fp16")
+    c2w = O.pose_spherical(-180., -30., 4.)[:3, :4].cuda()
+    kw = dict(network_query_fn=None, perturb=0., N_importance=128, network_fine=fine, N_samples=64, network_fn=coarse,
+              use_viewdirs=True, white_bkgd=True, raw_noise_std=0., ndc=False, near=2., far=6.)
+    with torch.no_grad():
+        rgb, disp, acc, extras = E.render_image(400, 400, O.LEGO["focal"], chunk=32768, c2w=c2w, **kw)
+    assert tuple(rgb.shape) == (400, 400, 3) and tuple(extras["z_std"].shape) == (400, 400)
+    assert bool(torch.isfinite(rgb).all()) and float(rgb.min()) >= -1e-6 and float(rgb.max()) <= 1. + 1e-5
+    assert float(acc.max()) <= 1. + 1e-5
