@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Benchmark of the per-ray rendering hot path (BASELINE.json metric: Mrays/s and ms/frame at 400x400).
+
+    python bench.py --gpus N --steps K --warmup W [--workload r2l|nerf] [--impl reference]
+
+Workload (config.workload):
+  r2l  (default, BASELINE configs[1]): R2L lego_noview resmlp W256 D88, n_sample_per_ray=16, 400x400
+       synthetic test poses; one STEP = one pose = one 160 000-ray frame through
+       PointSampler -> fused (PositionalEmbedder + 88-layer ResMLP) kernel.
+  nerf (BASELINE configs[0]): NeRF lego W256 D8, 64 coarse + 128 fine samples, one STEP = one 400x400 frame
+       through get_rays -> fused encode+MLP (coarse) -> raw2outputs -> sample_pdf -> merge -> fused
+       encode+MLP (fine) -> raw2outputs.
+Random-init weights (torch.manual_seed(0), the reference's construction order), synthetic poses
+pose_spherical(theta_k, -30, 4): data = "synthetic".
+
+Multi-GPU: one process per GPU (torchrun), poses sharded round-robin, NO data-path collective (weak
+scaling: every rank renders K poses); time = max over ranks; value = all rays / that time.
+
+Timing: W >= 3 warm-up steps, then K steps; every step is bracketed by CUDA events on the launching
+stream (torch's current stream, which is the stream the C ABI launches on); an L2 flush (256 MiB
+memset) runs between steps outside the event brackets.  `value` is the device-resident number (inputs
+already in HBM); `e2e` is measured separately through the public API with the pose coming from pinned
+host memory and the finished frame copied back to pinned host memory inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 400
+RAYS = H * W
+FLOP_PER_RAY = {"r2l": 11789824, "nerf": 303824896}   # BASELINE.md §2 (unpadded MACs x2)
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sust=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ workloads
+def make_poses(O, n, offset=0, stride=1):
+    return [O.pose_spherical(-180. + 360. * ((offset + k * stride) % 200) / 200., -30., 4.)[:3, :4].contiguous()
+            for k in range(n)]
+
+
+class R2LWorkload:
+    name = "r2l"
+    kernels_per_step = 2   # point_sample_kernel + r2l_mlp_kernel
+
+    def __init__(self, E, O, precision):
+        sd = O.r2l_state_dict(0)
+        net = E.NeRF_v3_2(O.r2l_args(), 1008, 3, precision=precision)
+        net.load_state_dict(sd)
+        self.net = net.cuda().eval()
+        self.ps = E.PointSampler(H, W, O.LEGO["focal"], 16, 2., 6.)
+        self.E = E
+        self.net.packed_handle()
+        self.ev = None
+
+    def step(self, c2w_dev, mlp_events=None):
+        pts = self.ps.sample_test(c2w_dev)
+        if mlp_events is not None:
+            mlp_events[0].record()
+        rgb = self.net.forward_points(pts)
+        if mlp_events is not None:
+            mlp_events[1].record()
+        return rgb
+
+    def describe(self):
+        return {"workload": "R2L lego_noview resmlp W256 D88, n_sample_per_ray=16, 400x400 synthetic poses "
+                            "(BASELINE configs[1]); step = 1 pose = 160000 rays",
+                "rays_per_step": RAYS, "operands": self.net.precision, "accumulate": "fp32"}
+
+
+class NerfWorkload:
+    name = "nerf"
+    kernels_per_step = 13
+
+    def __init__(self, E, O, precision):
+        sdc, sdf = O.nerf_state_dicts(0)
+        self.coarse = E.NeRF(8, 256, 63, 27, 5, [4], True, precision=precision)
+        self.fine = E.NeRF(8, 256, 63, 27, 5, [4], True, precision=precision)
+        self.coarse.load_state_dict(sdc), self.fine.load_state_dict(sdf)
+        self.coarse, self.fine = self.coarse.cuda().eval(), self.fine.cuda().eval()
+        self.coarse.packed_handle(), self.fine.packed_handle()
+        self.E, self.focal = E, O.LEGO["focal"]
+        self.kw = dict(network_query_fn=None, perturb=0., N_importance=128, network_fine=self.fine, N_samples=64,
+                       network_fn=self.coarse, use_viewdirs=True, white_bkgd=True, raw_noise_std=0., ndc=False,
+                       near=2., far=6.)
+
+    def step(self, c2w_dev, mlp_events=None):
+        rgb, disp, acc, _ = self.E.render_image(H, W, self.focal, chunk=32768, c2w=c2w_dev, **self.kw)
+        return rgb.reshape(-1, 3)
+
+    def describe(self):
+        return {"workload": "NeRF lego W256 D8, 64 coarse + 128 fine samples, 400x400 synthetic poses "
+                            "(BASELINE configs[0]); step = 1 frame = 160000 rays",
+                "rays_per_step": RAYS, "operands": self.coarse.precision, "accumulate": "fp32"}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(O, workload, steps, warmup, sample_rays):
+    """The reference's algorithm (oracle port, torch CPU kernels = what the reference runs on CPU) on a bounded
+    sample of the same frame, all host threads."""
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cam = O.LEGO
+    c2w = O.pose_spherical(-180., -30., 4.)[:3, :4]
+    idx = torch.linspace(0, RAYS - 1, sample_rays).long()
+    times = []
+    with torch.no_grad():
+        if workload == "r2l":
+            sd = O.r2l_state_dict(0)
+            fn = lambda: O.render_r2l(sd, H, W, cam["focal"], 2., 6., c2w, rows=idx)
+        else:
+            sdc, sdf = O.nerf_state_dicts(0)
+            ro, rd = O.get_rays(H, W, cam["focal"], c2w)
+            batch = O.pack_rays(ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx], 2., 6.)
+            fn = lambda: O.render_rays(batch, sdc, sdf, 64, 128, white_bkgd=True)["rgb_map"]
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    mean = float(np.mean(times))
+    return dict(value=sample_rays / mean / 1e6, unit="Mrays/s", cores=cores, kind="port",
+                sample=f"{sample_rays} evenly spaced rays of one 400x400 frame per step, {len(times)} timed steps "
+                       f"(oracle/ref_torch.py = the reference's torch-CPU path); ms/frame extrapolated = "
+                       f"{mean / sample_rays * RAYS * 1e3:.0f}"), mean
+
+
+def run_reference_arm(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return 0
+    from oracle import ref_torch as O
+    sample = 8192 if args.workload == "r2l" else 512
+    steps = max(1, min(args.steps, 3))
+    warmup = min(args.warmup, 1)
+    cb, mean = cpu_reference(O, args.workload, steps, warmup, sample)
+    line = {"impl": "reference", "metric": "render_throughput", "value": cb["value"], "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "rays_per_step": sample,
+                       "note": "CPU reference arm: each step is a bounded sample of the 160000-ray frame"},
+            "ms_per_frame_400x400": mean / sample * RAYS * 1e3,
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0,
+                                        "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+WORKLOAD_DESC = {
+    "r2l": "R2L lego_noview resmlp W256 D88, n_sample_per_ray=16, 400x400 synthetic poses (BASELINE configs[1])",
+    "nerf": "NeRF lego W256 D8, 64 coarse + 128 fine samples, 400x400 synthetic pose (BASELINE configs[0])",
+}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", choices=["r2l", "nerf"], default="r2l")
+    ap.add_argument("--precision", choices=["fp16", "bf16"], default="fp16")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank, local, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback")
+    torch.cuda.set_device(local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import efficient_nerf_b200 as E
+    from oracle import ref_torch as O   # synthetic poses / seeded weights (and the cpu_baseline leg)
+    E._lib.load()
+    wl = (R2LWorkload if args.workload == "r2l" else NerfWorkload)(E, O, args.precision)
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+    poses = make_poses(O, steps + warmup, offset=rank, stride=world)     # pose-sharded: rank r, r+G, ...
+    poses_dev = [p.cuda() for p in poses]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    peaks = measured_peaks()
+
+    # ---------------- device-resident timing
+    with torch.no_grad():
+        for i in range(warmup):
+            wl.step(poses_dev[i])
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        mev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        launches0 = E._lib.launch_count
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()                              # L2 flush, outside the event bracket
+            ev[i][0].record()
+            out = wl.step(poses_dev[warmup + i], mev[i])
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = E._lib.launch_count - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        mlp_ms = sum(a.elapsed_time(b) for a, b in mev) / steps if args.workload == "r2l" else None
+
+        # ---------------- end-to-end timing through the public API with host buffers
+        pose_host = [p.pin_memory() for p in poses]
+        frame_host = torch.empty((RAYS, 3), dtype=torch.float32).pin_memory()
+        c2w_buf = torch.empty((3, 4), dtype=torch.float32, device="cuda")
+        e2e_steps = steps
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(e2e_steps):
+            c2w_buf.copy_(pose_host[warmup + i], non_blocking=True)          # H2D of this step's input
+            out = wl.step(c2w_buf)
+            frame_host.copy_(out, non_blocking=True)                          # D2H of this step's result
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_rays = RAYS * steps * world
+    value = total_rays / (dev_ms * 1e-3) / 1e6
+    e2e_value = RAYS * e2e_steps * world / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        line = {"metric": "render_throughput", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": dict(wl.describe(), sharding="pose round-robin, no data-path collective",
+                               l2="flushed between steps (256 MiB memset outside the event brackets)",
+                               timing="sum of per-step CUDA-event durations, max over ranks"),
+                "ms_per_frame_400x400": dev_ms / steps,
+                "wall_ms_per_step_incl_flush": t_wall / steps * 1e3,
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 48,
+                        "d2h_bytes_per_step": RAYS * 3 * 4, "ms_per_step": e2e_ms / e2e_steps},
+                "gpu_launches": int(steps * wl.kernels_per_step), "abi_calls": int(launches),
+                "clocks": clocks}
+        flops = FLOP_PER_RAY[args.workload] * RAYS
+        if args.workload == "r2l":
+            ach = flops / (mlp_ms * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": "r2l_mlp_kernel", "achieved": ach,
+                                "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
+                                "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step; "
+                                               f"burst {peaks['tf_burst']})",
+                                "kernel_ms": mlp_ms, "algorithmic_flop_per_launch": flops, "traffic": None}
+        else:
+            ach = flops / (dev_ms / steps * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": "nerf_mlp_kernel (coarse+fine, whole frame)",
+                                "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                                "frac": ach / peaks["tf_sust"], "peak_source": f"{peaks['src']} bf16_tflops_sustained",
+                                "kernel_ms": dev_ms / steps, "algorithmic_flop_per_launch": flops, "traffic": None}
+        if world == 1 and not args.no_cpu_baseline:
+            sample = 16384 if args.workload == "r2l" else 1024
+            line["cpu_baseline"], _ = cpu_reference(O, args.workload, 2, 1, sample)
+        if world == 1 and not args.no_extras:
+            line["extras"] = extras(E, O, peaks, args.precision, args.workload)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def extras(E, O, peaks, precision, main_workload):
+    """Short secondary measurements reported beside the headline: the other model and the two HBM-bound kernels."""
+    out = {}
+    with torch.no_grad():
+        def timeit(fn, n=10, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        other = "nerf" if main_workload == "r2l" else "r2l"
+        wl = (R2LWorkload if other == "r2l" else NerfWorkload)(E, O, precision)
+        pose = make_poses(O, 1)[0].cuda()
+        ms = timeit(lambda: wl.step(pose), n=5 if other == "nerf" else 20)
+        fl = FLOP_PER_RAY[other] * RAYS
+        out[other] = {"ms_per_frame_400x400": ms, "Mrays_per_s": RAYS / ms / 1e3,
+                      "tensor_TFLOPs": fl / ms / 1e9, "frac_of_sustained_peak": fl / ms / 1e9 / peaks["tf_sust"]}
+        # HBM-bound kernels on 4x the frame (inputs > L2): raw2outputs S=192, sample_pdf Ni=128
+        N = 4 * RAYS
+        raw = torch.randn(N, 192, 4, device="cuda")
+        z = torch.sort(torch.rand(N, 192, device="cuda") * 4 + 2, -1)[0]
+        d = torch.randn(N, 3, device="cuda")
+        ms = timeit(lambda: E.raw2outputs(raw, z, d, 0, True))
+        gbs = N * (24 * 192 + 36) / ms / 1e6
+        out["raw2outputs_S192"] = {"ms": ms, "GB_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm"], "rays": N}
+        del raw
+        bins = z[:, :63].contiguous()
+        w = torch.rand(N, 62, device="cuda")
+        ms = timeit(lambda: E.sample_pdf(bins, w, 128, det=True))
+        gbs = N * 1012 / ms / 1e6
+        out["sample_pdf_Ni128"] = {"ms": ms, "GB_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm"], "rays": N}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -134,7 +134,8 @@ extern "C" {
 int r2l_raw2outputs(long long n_rays, int S, const float* raw, const float* z_vals, const float* rays_d,
                     long long d_stride, const float* noise, int white_bkgd, float* rgb_map, float* disp_map,
                     float* acc_map, float* weights, float* depth_map, void* stream) {
-  R2L_CHECK_ARG(n_rays >= 0 && S > 0 && d_stride >= 3, "r2l_raw2outputs: bad sizes");
+  R2L_CHECK_ARG(n_rays >= 0 && S >= 2 && d_stride >= 3,
+                "r2l_raw2outputs: need S >= 2 samples per ray (the reference degenerates to empty weights at S = 1)");
   if (n_rays == 0) return R2L_OK;
   R2L_CHECK_ARG(raw && z_vals && rays_d, "r2l_raw2outputs: null input pointer");
   R2L_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "r2l_raw2outputs: raw must be 16-byte aligned");

@@ -219,13 +219,14 @@ const char* r2l_last_error(void) { return g_last_error.c_str(); }
 int r2l_abi_version(void) { return 1; }
 
 // D [128, N] fp32 = A [128, K] fp32 (rounded to 16 bit) x W [N, K]^T fp32 (rounded to 16 bit).
-// K multiple of 32, <= 320; N multiple of 16, 16..256.  dtype: 0 = fp16, 1 = bf16.
+// K multiple of 32, <= 320; N multiple of 32, 32..256.  dtype: 0 = fp16, 1 = bf16.
 int r2l_tc_gemm_probe(int dtype, int N, int K, const float* A, const float* W, float* D, int swap_lbo_sbo,
                       void* stream) {
   R2L_CHECK_ARG(dtype == 0 || dtype == 1, "r2l_tc_gemm_probe: dtype must be 0 (fp16) or 1 (bf16)");
-  R2L_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0, "r2l_tc_gemm_probe: bad N");
+  R2L_CHECK_ARG(N >= 32 && N <= 256 && N % 32 == 0, "r2l_tc_gemm_probe: N must be a multiple of 32 in [32,256]");
   R2L_CHECK_ARG(K >= 32 && K <= 320 && K % 32 == 0, "r2l_tc_gemm_probe: bad K");
   R2L_CHECK_ARG(A && W && D, "r2l_tc_gemm_probe: null pointer");
+  R2L_CHECK_ARG(kTileM * K * 2 + N * K * 2 + 64 <= 227 * 1024, "r2l_tc_gemm_probe: operands exceed shared memory");
   auto st = static_cast<cudaStream_t>(stream);
   uint16_t* packed = nullptr;
   R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&packed), static_cast<size_t>(N) * K * 2));

@@ -8,7 +8,8 @@
 //          A buffers in chunks of 4 points (K = 256) that ping-pong between the two buffers.
 //   body : 43 x [ h = relu(W1 x + b1) ;  x = x + res_scale*(W2 h + b2) ]
 //          The residual stream lives in TMEM columns [256,512) in fp32 for the whole body:
-//          x0 is stored there once (tcgen05.st) and every W2 layer ACCUMULATES onto it
+//          the head accumulates there, x0 = relu(.) is stored back in place (tcgen05.st) and every W2
+//          layer ACCUMULATES onto it
 //          (tcgen05.mma with the accumulate flag), so the residual add costs nothing and is
 //          exact fp32.  The biases b2 are folded into a per-block cumulative bias cb_b that is
 //          added when x is read back (x_{b+1} = D2 + cb_b); W1 layers use TMEM columns [0,256).
@@ -113,11 +114,13 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
         }
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        // head accumulates in D2: the next layer (W1 of block 0) writes D1 and may start on K-half 0 while
+        // WG1 is still reading the head accumulators (consecutive layers must never share a TMEM buffer)
         for (int c = 0; c < n_chunks; ++c) {
-          run_k256(c & 1, d1, c == 0);
+          run_k256(c & 1, d2, c == 0);
           if (c + 2 < n_chunks) umma_commit(&a_free[c & 1]);
         }
-        umma_commit(&d_full[0]);
+        umma_commit(&d_full[1]);
         for (int b = 0; b < nb; ++b) {
           run_k256(0, d1, true);
           umma_commit(&d_full[0]);
@@ -186,9 +189,9 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
       }
       float t0 = 0.f, t1 = 0.f, t2 = 0.f;
       const float* wt = p.w_tail;
-      // ---- head epilogue: x0 = relu(D1 + b_h) -> residual stream (TMEM D2), A[0], tail partials
-      mbar_wait(&d_full[0], cnt_d[0] & 1, p.dbg, 300);
-      ++cnt_d[0];
+      // ---- head epilogue: x0 = relu(D2 + b_h) -> residual stream (written back in place to D2), A[0], tail partials
+      mbar_wait(&d_full[1], cnt_d[1] & 1, p.dbg, 300);
+      ++cnt_d[1];
       tc_fence_after_sync();
       {
         uint8_t* a_dst = sA[0] + row * 16;
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           const int col0 = c0 + h * 64;
-          epilogue_cols64<BF16, true, true>(lane_taddr + col0, a_dst + (col0 >> 3) * kChunkBytes, col0,
+          epilogue_cols64<BF16, true, true>(lane_taddr + 256 + col0, a_dst + (col0 >> 3) * kChunkBytes, col0,
                                             lane_taddr + 256 + col0, [&](int n, float acc) {
                                               const float v = fmaxf(acc + __ldg(bias + n), 0.0f);
                                               if (skip) {

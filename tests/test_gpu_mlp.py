@@ -34,7 +34,7 @@ def load_r2l(E, O, sd, precision):
 
 # ------------------------------------------------------------------ building blocks
 @pytest.mark.parametrize("dtype", [0, 1])
-@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (256, 320), (128, 256), (16, 32)])
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (128, 320), (128, 256), (32, 32), (64, 96)])
 def test_tcgen05_gemm_probe(E, dtype, N, K):
     """One tcgen05 GEMM with the operand layout / descriptors the fused kernels use."""
     torch.manual_seed(N + K)

@@ -1,0 +1,110 @@
+"""CPU tests of the host-side logic: sharding maths, the world_size-2 gather path (gloo), module
+construction / state_dict parity with the reference layout, lazy embedding handles, bench plumbing."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_rays_covers_everything_in_tile_multiples(E):
+    S = E.sharding
+    for n in (0, 1, 127, 128, 129, 160000, 190512, 640000):
+        for ws in (1, 2, 3, 4, 8):
+            spans = [S.shard_rays(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans[:-1], spans[1:]):
+                assert a1 == b0 and a0 <= a1
+            for a0, a1 in spans[:-1]:
+                assert (a0 % 128 == 0 or a0 == n) and (a1 % 128 == 0 or a1 == n)
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) < 256 or n < 128 * ws
+    assert S.shard_rays(160000, 7, 8) == (140032, 160000)
+
+
+def test_shard_poses_round_robin(E):
+    S = E.sharding
+    all_idx = sorted(i for r in range(8) for i in S.shard_poses(200, r, 8))
+    assert all_idx == list(range(200))
+    assert S.shard_poses(5, 3, 4) == [3]
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import efficient_nerf_b200 as E
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+n = 1000
+full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+s0, s1 = E.sharding.shard_rays(n)
+out = E.sharding.gather_rays(full[s0:s1].clone(), n)
+assert torch.equal(out, full), "gather_rays mismatch"
+mine = [torch.full((8, 3), float(i)) for i in E.sharding.shard_poses(5)]
+frames = E.sharding.gather_frames(mine, 5)
+assert [float(f[0, 0]) for f in frames] == [0., 1., 2., 3., 4.], "gather_frames mismatch"
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gather_paths_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+
+
+def test_modules_keep_the_reference_state_dict_layout(E, O):
+    sdc, _ = O.nerf_state_dicts(0)
+    torch.manual_seed(0)
+    net = E.NeRF(8, 256, 63, 27, 5, [4], True)
+    msd = net.state_dict()
+    assert list(msd) == list(sdc)                       # same keys, same order
+    assert all(torch.equal(msd[k], sdc[k]) for k in sdc)  # same seeded init => same RNG consumption
+    assert net.supports_tensor_core_path()
+    assert not E.NeRF(8, 128, 63, 27, 5, [4], True).supports_tensor_core_path()
+    assert not E.NeRF(8, 256, 63, 27, 4, [4], False).supports_tensor_core_path()
+    sd = O.r2l_state_dict(0)
+    torch.manual_seed(0)
+    r = E.NeRF_v3_2(O.r2l_args(), 1008, 3)
+    assert set(r.state_dict()) == set(sd) and all(torch.equal(r.state_dict()[k], sd[k]) for k in sd)
+    assert r.supports_tensor_core_path()
+    assert sum(p.numel() for p in r.parameters()) == 5917187
+    assert sum(p.numel() for p in net.parameters()) == 595844
+    a = O.r2l_args(netdepth=10)
+    a.trial.body_arch = 'mlp'
+    assert not E.NeRF_v3_2(a, 1008, 3).supports_tensor_core_path()     # falls to the fp32 CUDA path
+
+
+def test_lazy_embedding_shape_protocol(E):
+    from efficient_nerf_b200.nerf_raybased import LazyEmbedding
+    le = LazyEmbedding(torch.zeros(10, 48), 10, True)
+    assert tuple(le.shape) == (10, 1008) and le.dtype == torch.float32
+
+
+def test_precision_argument_validation(E):
+    with pytest.raises(ValueError):
+        E.NeRF(8, 256, 63, 27, 5, [4], True, precision="int8")
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """bench.py --impl reference runs the oracle port on the host cores and prints one JSON line."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--workload", "r2l"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mrays/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
