@@ -515,7 +515,8 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
 }
 
 static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_stride, const float* embedded,
-                      long long emb_stride, float* rgb, cudaStream_t st) {
+                      long long emb_stride, float* rgb, cudaStream_t st, float* dbg_acc = nullptr,
+                      float* dbg_x0 = nullptr, void* dbg_a = nullptr) {
   R2lParams p{};
   p.wstream = m->wstream;
   p.b_head = m->aux;
@@ -537,6 +538,9 @@ static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_
   p.dbg = m->dbg_dev;
   p.embedded = embedded;
   p.emb_stride = emb_stride;
+  p.dbg_head_acc = dbg_acc;
+  p.dbg_head_x0 = dbg_x0;
+  (void)dbg_a;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   return r2l_mlp_launch(m->bf16, p, grid, st);
 }
@@ -565,6 +569,28 @@ int r2l_resmlp_forward_embedded(void* handle, long long n_rays, const float* x, 
   int rc = check_dbg(m, "r2l_resmlp_forward_embedded");
   if (rc != R2L_OK) return rc;
   return resmlp_run(m, n_rays, nullptr, 0, x, ldx, rgb, static_cast<cudaStream_t>(stream));
+}
+
+// Debug hook (tests only): like r2l_resmlp_forward, additionally dumping the head layer's raw accumulators and
+// x0 = relu(acc + b_head) as [ceil(n_rays/128)*128, 256] fp32.
+int r2l_resmlp_debug_head(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
+                          float* head_acc, float* head_x0, void* head_a, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 1, "r2l_resmlp_debug_head: not an R2L handle");
+  R2L_CHECK_ARG(n_rays > 0 && pts && rgb && head_acc && head_x0, "r2l_resmlp_debug_head: bad arguments");
+  return resmlp_run(m, n_rays, pts, pts_stride, nullptr, 0, rgb, static_cast<cudaStream_t>(stream), head_acc, head_x0, head_a);
+}
+
+// Debug hook (tests only): copy the packed 16-bit weight stream to host memory; returns its size via *bytes.
+int r2l_mlp_debug_wstream(void* handle, void* out_host, unsigned long long capacity, unsigned long long* bytes) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && bytes != nullptr, "r2l_mlp_debug_wstream: bad arguments");
+  *bytes = m->wbytes;
+  if (out_host != nullptr) {
+    R2L_CHECK_ARG(capacity >= m->wbytes, "r2l_mlp_debug_wstream: buffer too small");
+    R2L_CUDA(cudaMemcpy(out_host, m->wstream, m->wbytes, cudaMemcpyDeviceToHost));
+  }
+  return R2L_OK;
 }
 
 int r2l_mlp_destroy(void* handle) {

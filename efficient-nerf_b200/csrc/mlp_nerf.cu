@@ -42,7 +42,8 @@ __device__ __forceinline__ int nerf_stages_in_step(int step) { return step == 0 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_kernel(const NerfParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA[2] = {smem + kNerfOffA0, smem + kNerfOffA1};
+  uint8_t* const sA0 = smem + kNerfOffA0;   // A buffers: sA0 + buf*kABufBytes (no dynamically indexed local arrays:
+                                             // nvcc 12.9 overlapped two such stack arrays in the R2L kernel)
   uint8_t* sP = smem + kNerfOffP;
   uint8_t* sRing = smem + kNerfOffRing;
   float* sBias = reinterpret_cast<float*>(smem + kNerfOffBias);
@@ -103,11 +104,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_kernel(const NerfParams 
     if (lane == 0) {
       const uint32_t idesc256 = make_idesc_f16(BF16, kTileM, 256);
       const uint32_t idesc128 = make_idesc_f16(BF16, kTileM, 128);
-      const uint32_t aA[2] = {smem_u32(sA[0]), smem_u32(sA[1])};
+      const uint32_t aA0 = smem_u32(sA0);
       const uint32_t aP = smem_u32(sP);
       const uint32_t aRing = smem_u32(sRing);
       uint32_t g = 0, cnt_p = 0;
-      uint32_t cnt_a[4] = {0, 0, 0, 0};
+      uint32_t par_a = 0;   // bit (buf*2+half): parity of the next a_ready phase to wait for
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int step = 0; step < kNerfSteps; ++step) {
           const int nst = nerf_stages_in_step(step);
@@ -128,10 +129,10 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_kernel(const NerfParams 
             } else {
               if (st == 0 || st == 4) {
                 const int bi = abuf * 2 + (st >> 2);
-                mbar_wait(&a_ready[bi], cnt_a[bi] & 1, p.dbg, 210 + bi);
-                ++cnt_a[bi];
+                mbar_wait(&a_ready[bi], (par_a >> bi) & 1u, p.dbg, 210 + bi);
+                par_a ^= 1u << bi;
               }
-              a_addr = aA[abuf] + st * 4 * kChunkBytes;
+              a_addr = aA0 + abuf * kABufBytes + st * 4 * kChunkBytes;
             }
             const uint32_t slot = g % kNerfRing;
             mbar_wait(&w_full[slot], (g / kNerfRing) & 1, p.dbg, 220 + slot);
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_kernel(const NerfParams 
     const int wg = warp >> 2;                       // 0 | 1 : output column half
     const int row = (warp & 3) * 32 + lane;         // tile row == TMEM lane
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    uint32_t cnt_d[2] = {0, 0};
+    uint32_t par_d = 0;   // bit dbuf: parity of the next d_full phase
     bool first = true;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long g_row = static_cast<long long>(tile) * kTileM + row;
@@ -191,12 +192,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_kernel(const NerfParams 
       float sigma_part = 0.0f;
       for (int step = 0; step < kNerfSteps; ++step) {
         const int db = step & 1;
-        mbar_wait(&d_full[db], cnt_d[db] & 1, p.dbg, 300 + step);
-        ++cnt_d[db];
+        mbar_wait(&d_full[db], (par_d >> db) & 1u, p.dbg, 300 + step);
+        par_d ^= 1u << db;
         tc_fence_after_sync();
         const uint32_t d_taddr = lane_taddr + db * 256;
         if (step <= 8) {
-          uint8_t* a_dst = sA[step & 1] + row * 16;
+          uint8_t* a_dst = sA0 + (step & 1) * kABufBytes + row * 16;
           const float* bias = sBias + step * 256;
           const int c0 = wg * 128;
           if (step == 7) {

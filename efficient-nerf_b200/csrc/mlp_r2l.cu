@@ -36,7 +36,8 @@ static_assert(kR2lSmemBytes <= 227 * 1024, "R2L kernel shared memory exceeds 227
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA[2] = {smem + kR2lOffA0, smem + kR2lOffA1};
+  uint8_t* const sA0 = smem + kR2lOffA0;   // A buffers are addressed as sA0 + buf*kABufBytes (no local arrays:
+                                            // dynamically indexed stack arrays were mis-overlapped by nvcc 12.9)
   uint8_t* sRing = smem + kR2lOffRing;
   float* sPart = reinterpret_cast<float*>(smem + kR2lOffPart);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kR2lOffBars);
@@ -91,23 +92,23 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(BF16, kTileM, 256);
-      const uint32_t aA[2] = {smem_u32(sA[0]), smem_u32(sA[1])};
+      const uint32_t aA0 = smem_u32(sA0);
       const uint32_t aRing = smem_u32(sRing);
       const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
       uint32_t g = 0;
-      uint32_t cnt_a[4] = {0, 0, 0, 0};
+      uint32_t par_a = 0;   // bit (buf*2+half): parity of the next a_ready phase to wait for
       // 8 stages (K = 256) from A[buf] into d_tmem
       auto run_k256 = [&](int buf, uint32_t d_tmem, bool fresh) {
         for (int st = 0; st < 8; ++st) {
           if (st == 0 || st == 4) {
             const int bi = buf * 2 + (st >> 2);
-            mbar_wait(&a_ready[bi], cnt_a[bi] & 1, p.dbg, 210 + bi);
-            ++cnt_a[bi];
+            mbar_wait(&a_ready[bi], (par_a >> bi) & 1u, p.dbg, 210 + bi);
+            par_a ^= 1u << bi;
           }
           const uint32_t slot = g % kR2lRing;
           mbar_wait(&w_full[slot], (g / kR2lRing) & 1, p.dbg, 220 + slot);
           tc_fence_after_sync();
-          issue_stage(d_tmem, aA[buf] + st * 4 * kChunkBytes, aRing + slot * kStageBytes, 256 * 16, idesc,
+          issue_stage(d_tmem, aA0 + buf * kABufBytes + st * 4 * kChunkBytes, aRing + slot * kStageBytes, 256 * 16, idesc,
                       fresh && st == 0);
           umma_commit(&w_empty[slot]);
           ++g;
@@ -135,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int c0 = wg * 128;
-    uint32_t cnt_d[2] = {0, 0};
-    uint32_t cnt_free[2] = {0, 0};
+    uint32_t par_d = 0;      // bit dbuf: parity of the next d_full phase
+    uint32_t par_free = 0;   // bit buf: parity of the next a_free phase
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long ray = static_cast<long long>(tile) * kTileM + row;
       const bool valid = ray < p.n_rays;
@@ -147,13 +148,13 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
       for (int c = 0; c < n_chunks; ++c) {
         const int buf = c & 1;
         if (c >= 2) {
-          mbar_wait(&a_free[buf], cnt_free[buf] & 1, p.dbg, 400 + buf);
-          ++cnt_free[buf];
+          mbar_wait(&a_free[buf], (par_free >> buf) & 1u, p.dbg, 400 + buf);
+          par_free ^= 1u << buf;
         }
 #pragma unroll 1
         for (int bl = 0; bl < 2; ++bl) {
           const int pt = c * 4 + wg * 2 + bl;
-          uint8_t* blk = sA[buf] + (wg * 2 + bl) * 8 * kChunkBytes;
+          uint8_t* blk = sA0 + buf * kABufBytes + (wg * 2 + bl) * 8 * kChunkBytes;
           if (erow == nullptr) {
             const float px = __ldg(prow + 3 * pt), py = __ldg(prow + 3 * pt + 1), pz = __ldg(prow + 3 * pt + 2);
             encode_point_block<BF16>(blk, row, px, py, pz);
@@ -190,11 +191,11 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
       float t0 = 0.f, t1 = 0.f, t2 = 0.f;
       const float* wt = p.w_tail;
       // ---- head epilogue: x0 = relu(D2 + b_h) -> residual stream (written back in place to D2), A[0], tail partials
-      mbar_wait(&d_full[1], cnt_d[1] & 1, p.dbg, 300);
-      ++cnt_d[1];
+      mbar_wait(&d_full[1], (par_d >> 1) & 1u, p.dbg, 300);
+      par_d ^= 2u;
       tc_fence_after_sync();
       {
-        uint8_t* a_dst = sA[0] + row * 16;
+        uint8_t* a_dst = sA0 + row * 16;
         const float* bias = p.b_head;
         const bool skip = p.outer_skip != 0;
 #pragma unroll 1
@@ -203,6 +204,11 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
           epilogue_cols64<BF16, true, true>(lane_taddr + 256 + col0, a_dst + (col0 >> 3) * kChunkBytes, col0,
                                             lane_taddr + 256 + col0, [&](int n, float acc) {
                                               const float v = fmaxf(acc + __ldg(bias + n), 0.0f);
+                                              if (p.dbg_head_acc != nullptr) {
+                                                const long long o = (static_cast<long long>(tile) * kTileM + row) * 256 + n;
+                                                p.dbg_head_acc[o] = acc;
+                                                p.dbg_head_x0[o] = v;
+                                              }
                                               if (skip) {
                                                 t0 = fmaf(__ldg(wt + n), v, t0);
                                                 t1 = fmaf(__ldg(wt + 256 + n), v, t1);
@@ -219,11 +225,11 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
       // ---- body
       for (int b = 0; b < nb; ++b) {
         // W1: h = relu(D1 + b1) -> A[1]
-        mbar_wait(&d_full[0], cnt_d[0] & 1, p.dbg, 310);
-        ++cnt_d[0];
+        mbar_wait(&d_full[0], par_d & 1u, p.dbg, 310);
+        par_d ^= 1u;
         tc_fence_after_sync();
         {
-          uint8_t* a_dst = sA[1] + row * 16;
+          uint8_t* a_dst = sA0 + kABufBytes + row * 16;
           const float* bias = p.b1 + b * 256;
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
@@ -236,11 +242,11 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
           mbar_arrive(&a_ready[1 * 2 + wg]);
         }
         // W2: x = D2 + cb_b -> A[0]   (last block: tail partials instead)
-        mbar_wait(&d_full[1], cnt_d[1] & 1, p.dbg, 320);
-        ++cnt_d[1];
+        mbar_wait(&d_full[1], (par_d >> 1) & 1u, p.dbg, 320);
+        par_d ^= 2u;
         tc_fence_after_sync();
         {
-          uint8_t* a_dst = sA[0] + row * 16;
+          uint8_t* a_dst = sA0 + row * 16;
           const float* bias = p.cb + b * 256;
           if (b + 1 < nb) {
 #pragma unroll 1

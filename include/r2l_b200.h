@@ -127,6 +127,14 @@ int r2l_resmlp_forward(void* handle, long long n_rays, const float* pts, long lo
 int r2l_resmlp_forward_embedded(void* handle, long long n_rays, const float* x, long long ldx, float* rgb,
                                 void* stream);
 
+/* Debug hook for the tests: r2l_resmlp_forward that also dumps the head layer's accumulators and x0
+ * ([ceil(n_rays/128)*128, 256] fp32 each). */
+int r2l_resmlp_debug_head(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
+                          float* head_acc, float* head_x0, void* head_a, void* stream);
+
+/* Debug hook for the tests: copy the packed 16-bit weight stage stream to HOST memory. */
+int r2l_mlp_debug_wstream(void* handle, void* out_host, unsigned long long capacity, unsigned long long* bytes);
+
 int r2l_mlp_destroy(void* handle);
 
 /* 0 = healthy; non-zero if a kernel watchdog fired.  out8: optional 8 x uint32 debug record. */
