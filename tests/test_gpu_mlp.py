@@ -249,6 +249,44 @@ def test_r2l_fused_vs_reference(E, O, golden, precision, tol):
         assert torch.equal(net.forward_points(pts[5:6]), rgb[5:6])
 
 
+@pytest.mark.parametrize("n_points", [4, 8, 16])
+def test_r2l_head_accumulators_and_packed_weights(E, O, n_points):
+    """Debug hooks: the packed weight stream is the expected permutation, and the head layer's raw tcgen05
+    accumulators equal the fp16-rounded reference product (K = 64 per point, accumulated over chunks)."""
+    import ctypes
+    L = E._lib
+    torch.manual_seed(n_points)
+    net = E.NeRF_v3_2(O.r2l_args(netdepth=6), n_points * 63, 3, precision="fp16").cuda().eval()
+    pts = ((torch.rand(200, n_points * 3) * 2 - 1) * 4).cuda()
+    h = net.packed_handle()
+    rgb = torch.empty(200, 3, device="cuda")
+    acc = torch.zeros(256, 256, device="cuda")
+    x0 = torch.zeros(256, 256, device="cuda")
+    L.call("r2l_resmlp_debug_head", h.h, 200, L.ptr(pts), pts.stride(0), L.ptr(rgb), L.ptr(acc), L.ptr(x0), None,
+           L.stream_ptr())
+    torch.cuda.synchronize()
+    x = O.embed_r2l(pts.cpu(), 10)
+    W, b = net.head[0].weight.detach().cpu(), net.head[0].bias.detach().cpu()
+    acc_ref = torch.nn.functional.linear(x.half().double(), W.half().double()).float()
+    assert maxabs(acc[:200], acc_ref) < 2e-3
+    assert maxabs(x0[:200], torch.relu(acc_ref + b)) < 2e-3
+    with torch.no_grad():
+        assert maxabs(rgb, net._forward_fp32(x.cuda())) < 2e-3
+    n = ctypes.c_ulonglong(0)
+    L.call("r2l_mlp_debug_wstream", h.h, None, 0, ctypes.byref(n))
+    assert n.value == 2 * (256 * n_points * 64 + 2 * 2 * 256 * 256)
+    buf = np.zeros(n.value // 2, dtype=np.float16)
+    L.call("r2l_mlp_debug_wstream", h.h, buf.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n))
+    K = n_points * 64
+    Wp = torch.from_numpy(buf[:256 * K]).float().reshape(K // 32, 4, 256, 8).permute(2, 0, 1, 3).reshape(256, K)
+    for s_ in range(n_points):          # block order: k = 64 s + i ; i<3 identity, then (sin, cos) per frequency
+        for c in range(3):
+            assert torch.equal(Wp[:, 64 * s_ + c], W[:, (3 * s_ + c) * 21 + 20].half().float())
+            assert torch.equal(Wp[:, 64 * s_ + 3 + 6 * 4 + c], W[:, (3 * s_ + c) * 21 + 4].half().float())
+            assert torch.equal(Wp[:, 64 * s_ + 3 + 6 * 4 + 3 + c], W[:, (3 * s_ + c) * 21 + 14].half().float())
+        assert float(Wp[:, 64 * s_ + 63].abs().max()) == 0.
+
+
 def test_r2l_full_frame_properties(E, O):
     """BASELINE size: one 400x400 frame in one un-chunked forward; sharded == unsharded."""
     sd = O.r2l_state_dict(0)
