@@ -516,7 +516,7 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
 
 static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_stride, const float* embedded,
                       long long emb_stride, float* rgb, cudaStream_t st, float* dbg_acc = nullptr,
-                      float* dbg_x0 = nullptr, void* dbg_a = nullptr) {
+                      float* dbg_x0 = nullptr, void* dbg_a = nullptr, long long* prof = nullptr) {
   R2lParams p{};
   p.wstream = m->wstream;
   p.b_head = m->aux;
@@ -541,6 +541,7 @@ static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_
   p.dbg_head_acc = dbg_acc;
   p.dbg_head_x0 = dbg_x0;
   (void)dbg_a;
+  p.prof = prof;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   return r2l_mlp_launch(m->bf16, p, grid, st);
 }
@@ -579,6 +580,18 @@ int r2l_resmlp_debug_head(void* handle, long long n_rays, const float* pts, long
   R2L_CHECK_ARG(m != nullptr && m->kind == 1, "r2l_resmlp_debug_head: not an R2L handle");
   R2L_CHECK_ARG(n_rays > 0 && pts && rgb && head_acc && head_x0, "r2l_resmlp_debug_head: bad arguments");
   return resmlp_run(m, n_rays, pts, pts_stride, nullptr, 0, rgb, static_cast<cudaStream_t>(stream), head_acc, head_x0, head_a);
+}
+
+// Profiling hook: r2l_resmlp_forward that also fills per-CTA cycle counters prof[n_CTAs][8] (device int64):
+// [0] MMA thread total, [1] MMA waiting for A operands, [2] MMA waiting for weight stages,
+// [3]/[5] WG0/WG1 waiting for accumulators, [4]/[6] WG0/WG1 epilogue work, [7] WG0 encode time.
+int r2l_resmlp_profile(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
+                       long long* prof, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 1, "r2l_resmlp_profile: not an R2L handle");
+  R2L_CHECK_ARG(n_rays > 0 && pts && rgb && prof, "r2l_resmlp_profile: bad arguments");
+  return resmlp_run(m, n_rays, pts, pts_stride, nullptr, 0, rgb, static_cast<cudaStream_t>(stream), nullptr, nullptr,
+                    nullptr, prof);
 }
 
 // Debug hook (tests only): copy the packed 16-bit weight stream to host memory; returns its size via *bytes.

@@ -47,6 +47,7 @@ struct R2lParams {
   DebugBuf* dbg;
   const float* embedded;    // optional [n_rays][emb_stride]: reference-layout PositionalEmbedder output
   long long emb_stride;
+  long long* prof;          // optional [gridDim.x][8] cycle counters (see r2l_resmlp_profile)
   float* dbg_head_acc;      // optional debug dump [n_tiles*128][256]: raw head accumulators
   float* dbg_head_x0;       // optional debug dump [n_tiles*128][256]: x0 = relu(acc + b_head)
 };

@@ -97,16 +97,22 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
       const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
       uint32_t g = 0;
       uint32_t par_a = 0;   // bit (buf*2+half): parity of the next a_ready phase to wait for
+      const bool prof = p.prof != nullptr;
+      long long t_a = 0, t_w = 0, t_start = prof ? clock64() : 0;
       // 8 stages (K = 256) from A[buf] into d_tmem
       auto run_k256 = [&](int buf, uint32_t d_tmem, bool fresh) {
         for (int st = 0; st < 8; ++st) {
           if (st == 0 || st == 4) {
             const int bi = buf * 2 + (st >> 2);
+            const long long c0 = prof ? clock64() : 0;
             mbar_wait(&a_ready[bi], (par_a >> bi) & 1u, p.dbg, 210 + bi);
+            if (prof) t_a += clock64() - c0;
             par_a ^= 1u << bi;
           }
           const uint32_t slot = g % kR2lRing;
+          const long long c1 = prof ? clock64() : 0;
           mbar_wait(&w_full[slot], (g / kR2lRing) & 1, p.dbg, 220 + slot);
+          if (prof) t_w += clock64() - c1;
           tc_fence_after_sync();
           issue_stage(d_tmem, aA0 + buf * kABufBytes + st * 4 * kChunkBytes, aRing + slot * kStageBytes, 256 * 16, idesc,
                       fresh && st == 0);
@@ -129,6 +135,12 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
           umma_commit(&d_full[1]);
         }
       }
+      if (prof) {
+        long long* o = p.prof + blockIdx.x * 8;
+        o[0] = clock64() - t_start;   // MMA thread: total
+        o[1] = t_a;                   // waiting for A (epilogues / encoders)
+        o[2] = t_w;                   // waiting for weight stages
+      }
     }
   } else {
     // ===================== epilogue / encoder warpgroups =====================
@@ -136,6 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int c0 = wg * 128;
+    const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
+    long long t_d = 0, t_enc = 0, t_start = prof ? clock64() : 0;
     uint32_t par_d = 0;      // bit dbuf: parity of the next d_full phase
     uint32_t par_free = 0;   // bit buf: parity of the next a_free phase
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -145,6 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
       const float* prow = (p.pts != nullptr) ? p.pts + ray_c * p.pts_stride : nullptr;
       const float* erow = (p.embedded != nullptr) ? p.embedded + ray_c * p.emb_stride : nullptr;
       // ---- head: encode chunks of 4 points (K = 256); this WG owns points 2*wg, 2*wg+1 of each chunk
+      const long long ce = prof ? clock64() : 0;
       for (int c = 0; c < n_chunks; ++c) {
         const int buf = c & 1;
         if (c >= 2) {
@@ -188,10 +203,15 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
         fence_proxy_async_smem();
         mbar_arrive(&a_ready[buf * 2 + wg]);
       }
+      if (prof) t_enc += clock64() - ce;
       float t0 = 0.f, t1 = 0.f, t2 = 0.f;
       const float* wt = p.w_tail;
       // ---- head epilogue: x0 = relu(D2 + b_h) -> residual stream (written back in place to D2), A[0], tail partials
-      mbar_wait(&d_full[1], (par_d >> 1) & 1u, p.dbg, 300);
+      {
+        const long long cd = prof ? clock64() : 0;
+        mbar_wait(&d_full[1], (par_d >> 1) & 1u, p.dbg, 300);
+        if (prof) t_d += clock64() - cd;
+      }
       par_d ^= 2u;
       tc_fence_after_sync();
       {
@@ -225,7 +245,11 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
       // ---- body
       for (int b = 0; b < nb; ++b) {
         // W1: h = relu(D1 + b1) -> A[1]
-        mbar_wait(&d_full[0], par_d & 1u, p.dbg, 310);
+        {
+          const long long cd = prof ? clock64() : 0;
+          mbar_wait(&d_full[0], par_d & 1u, p.dbg, 310);
+          if (prof) t_d += clock64() - cd;
+        }
         par_d ^= 1u;
         tc_fence_after_sync();
         {
@@ -242,7 +266,11 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
           mbar_arrive(&a_ready[1 * 2 + wg]);
         }
         // W2: x = D2 + cb_b -> A[0]   (last block: tail partials instead)
-        mbar_wait(&d_full[1], (par_d >> 1) & 1u, p.dbg, 320);
+        {
+          const long long cd = prof ? clock64() : 0;
+          mbar_wait(&d_full[1], (par_d >> 1) & 1u, p.dbg, 320);
+          if (prof) t_d += clock64() - cd;
+        }
         par_d ^= 2u;
         tc_fence_after_sync();
         {
@@ -299,6 +327,12 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
           p.rgb[3 * ray + 2] = o2;
         }
       }
+    }
+    if (prof) {
+      long long* o = p.prof + blockIdx.x * 8 + 3 + wg * 2;
+      o[0] = t_d;                                  // WG: waiting for accumulators
+      o[1] = (clock64() - t_start) - t_d - t_enc;  // WG: epilogue work (everything else)
+      if (wg == 0) p.prof[blockIdx.x * 8 + 7] = t_enc;
     }
   }
 

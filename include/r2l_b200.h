@@ -132,6 +132,11 @@ int r2l_resmlp_forward_embedded(void* handle, long long n_rays, const float* x, 
 int r2l_resmlp_debug_head(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
                           float* head_acc, float* head_x0, void* head_a, void* stream);
 
+/* Profiling hook: r2l_resmlp_forward + per-CTA cycle counters prof[n_CTAs][8] (device int64): MMA-thread total /
+ * wait-for-A / wait-for-weights, WG0 and WG1 wait-for-accumulator / epilogue work, WG0 encode time. */
+int r2l_resmlp_profile(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
+                       long long* prof, void* stream);
+
 /* Debug hook for the tests: copy the packed 16-bit weight stage stream to HOST memory. */
 int r2l_mlp_debug_wstream(void* handle, void* out_host, unsigned long long capacity, unsigned long long* bytes);
 
