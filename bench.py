@@ -327,7 +327,7 @@ def main():
                 "wall_ms_per_step_incl_flush": t_wall / steps * 1e3,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 48,
                         "d2h_bytes_per_step": RAYS * 3 * 4, "ms_per_step": e2e_ms / e2e_steps},
-                "gpu_launches": int(steps * wl.kernels_per_step), "abi_calls": int(launches),
+                "gpu_launches": int(launches), "abi_calls": int(launches),
                 "clocks": clocks}
         flops = FLOP_PER_RAY[args.workload] * RAYS
         if args.workload == "r2l":

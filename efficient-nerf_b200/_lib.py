@@ -38,8 +38,10 @@ SIGNATURES = {
     "r2l_nerf_create": [ctypes.POINTER(_c_vp), _c_int, ctypes.POINTER(_c_vp), ctypes.POINTER(_c_vp), _c_f32p,
                         _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_vp],
     "r2l_nerf_forward": [_c_vp, _c_ll, _c_int, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_f32p,
-                         _c_f32p, _c_vp],
-    "r2l_nerf_forward_embedded": [_c_vp, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_f32p, _c_vp],
+                         _c_vp],
+    "r2l_nerf_forward_embedded": [_c_vp, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_vp],
+    "r2l_nerf_profile": [_c_vp, _c_ll, _c_int, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_f32p,
+                         _c_vp, _c_vp],
     "r2l_resmlp_create": [ctypes.POINTER(_c_vp), _c_int, _c_int, _c_int, _c_f32p, _c_f32p, ctypes.POINTER(_c_vp),
                           ctypes.POINTER(_c_vp), ctypes.POINTER(_c_vp), ctypes.POINTER(_c_vp), _c_dbl, _c_f32p,
                           _c_f32p, _c_int, _c_int, _c_vp],

@@ -65,16 +65,43 @@ __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, in
   }
 }
 
-// cb[b][n] = res_scale * sum_{b' <= b} b2[b'][n]  (double accumulate)
-__global__ void cumulative_bias_kernel(const float* const* __restrict__ b2, int n_blocks, int width, double scale,
-                                       float* __restrict__ cb) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= width) return;
-  double acc = 0.0;
-  for (int b = 0; b < n_blocks; ++b) {
-    acc += static_cast<double>(scale * static_cast<double>(b2[b][n]));
-    cb[b * width + n] = static_cast<float>(acc);
+// 16-bit hi / lo split of a bias value: hi = rn16(b), lo = rn16(b - hi); hi + lo reproduces b to ~2^-22 relative
+// (fp16) / 2^-16 (bf16).  Both are multiplied by exact 1.0 operands and accumulated in fp32 by the MMA.
+__device__ __forceinline__ uint16_t bias_part(float b, int part, int bf16) {
+  if (bf16) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    return (part == 0) ? __bfloat16_as_ushort(hi) : __bfloat16_as_ushort(__float2bfloat16_rn(b - __bfloat162float(hi)));
   }
+  const __half hi = __float2half_rn(b);
+  return (part == 0) ? __half_as_ushort(hi) : __half_as_ushort(__float2half_rn(b - __half2float(hi)));
+}
+
+// Bias step of a layer: one K=16 stage [N x 16] whose k=0 / k=1 columns hold the hi / lo split of scale*bias
+// (the matching A operand is the constant ones block), all other columns zero.
+__global__ void pack_bias_kernel(const float* __restrict__ bias, int N, float scale, uint16_t* __restrict__ dst,
+                                 int bf16) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 16) return;
+  const int n = idx / 16, k = idx % 16;
+  const uint16_t bits = (k < 2) ? bias_part(bias[n] * scale, k, bf16) : static_cast<uint16_t>(0);
+  dst[(k >> 3) * (N * 8) + n * 8 + (k & 7)] = bits;
+}
+
+// View stage of the NeRF view branch: [128 x 32], k < 27 -> views_w[n][256 + k] (embedded view direction),
+// k = 27 / 28 -> hi / lo split of views_b[n] (the V block holds 1.0 there), k = 29..31 -> 0.
+__global__ void pack_view_stage_kernel(const float* __restrict__ views_w, long long ldw, const float* __restrict__ views_b,
+                                       uint16_t* __restrict__ dst, int bf16) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * 32) return;
+  const int n = idx / 32, k = idx % 32;
+  uint16_t bits = 0;
+  if (k < 27) {
+    const float v = views_w[n * ldw + 256 + k];
+    bits = bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+  } else if (k < 29) {
+    bits = bias_part(views_b[n], k - 27, bf16);
+  }
+  dst[(k >> 3) * (128 * 8) + n * 8 + (k & 7)] = bits;
 }
 
 struct Mlp {
@@ -114,6 +141,12 @@ static int pack_layer(const float* W, long long ldw, int N, int K_src, int Kpad,
   return R2L_OK;
 }
 
+static int pack_bias(const float* bias, int N, float scale, uint16_t* dst, bool bf16, cudaStream_t st) {
+  pack_bias_kernel<<<(N * 16 + 255) / 256, 256, 0, st>>>(bias, N, scale, dst, bf16 ? 1 : 0);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
 static void destroy(Mlp* m) {
   if (m == nullptr) return;
   if (m->wstream) cudaFree(m->wstream);
@@ -122,13 +155,10 @@ static void destroy(Mlp* m) {
   delete m;
 }
 
-// NeRF aux layout (floats)
-constexpr int kNerfAuxBias = 0;                    // 9*256
-constexpr int kNerfAuxAlphaW = 9 * 256;            // 256
+// NeRF aux layout (floats): the two heads that run on CUDA cores
+constexpr int kNerfAuxAlphaW = 0;                  // 256
 constexpr int kNerfAuxRgbW = kNerfAuxAlphaW + 256; // 384
-constexpr int kNerfAuxWvd = kNerfAuxRgbW + 384;    // 128*27
-constexpr int kNerfAuxBv = kNerfAuxWvd + 128 * 27; // 128
-constexpr int kNerfAuxTotal = kNerfAuxBv + 128;
+constexpr int kNerfAuxTotal = kNerfAuxRgbW + 384;
 
 // ---------------------------------------------------------------------------------
 // tcgen05 GEMM probe: D[128, N] = A[128, K] * B[N, K]^T with 16-bit operands, fp32 accumulate.
@@ -216,7 +246,7 @@ using namespace r2l;
 extern "C" {
 
 const char* r2l_last_error(void) { return g_last_error.c_str(); }
-int r2l_abi_version(void) { return 1; }
+int r2l_abi_version(void) { return 2; }
 
 // D [128, N] fp32 = A [128, K] fp32 (rounded to 16 bit) x W [N, K]^T fp32 (rounded to 16 bit).
 // K multiple of 32, <= 320; N multiple of 32, 32..256.  dtype: 0 = fp16, 1 = bf16.
@@ -287,8 +317,9 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
     if (rc != R2L_OK) destroy(m);
     return rc;
   };
-  // stage stream: L0 (K 64) | L1..4 (K 256) | L5 (K 320) | L6,7 | feature | views (N 128, K 256)
-  const size_t elems = 256ull * (64 + 4 * 256 + 320 + 2 * 256 + 256) + 128ull * 256;
+  // stage stream in consumption order; every 256-wide layer is [K=16 bias stage][K/32 weight stages]:
+  //   L0 (K 64) | L1..4 (K 256) | L5 (K 64 point part + 256) | L6,7 | feature | views: V stage (N 128, K 32) + K 256
+  const size_t elems = 256ull * (64 + 4 * 256 + 320 + 2 * 256 + 256) + 9ull * 256 * 16 + 128ull * (32 + 256);
   m->wbytes = elems * 2;
   if (cudaMalloc(reinterpret_cast<void**>(&m->wstream), m->wbytes) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&m->aux), sizeof(float) * kNerfAuxTotal) != cudaSuccess)
@@ -298,9 +329,13 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
   uint16_t* dst = reinterpret_cast<uint16_t*>(m->wstream);
   std::vector<int> kmap0(64), kmap5(320);
   for (int k = 0; k < 64; ++k) kmap0[k] = (k < 63) ? k : -1;
-  for (int k = 0; k < 320; ++k) kmap5[k] = (k < 256) ? (63 + k) : ((k < 319) ? (k - 256) : -1);
+  // skip layer: reference input is cat[pts(63), h(256)]; the kernel feeds the point block first, then h
+  for (int k = 0; k < 320; ++k) kmap5[k] = (k < 63) ? k : ((k == 63) ? -1 : (63 + (k - 64)));
   size_t off = 0;
   for (int l = 0; l < 8 && rc == R2L_OK; ++l) {
+    rc = pack_bias(pts_b[l], 256, 1.0f, dst + off, m->bf16, st);
+    off += 256ull * 16;
+    if (rc != R2L_OK) break;
     if (l == 0) {
       rc = pack_layer(pts_w[0], 63, 256, 63, 64, &kmap0, 1.0f, dst + off, m->bf16, st, scratch);
       off += 256ull * 64;
@@ -313,25 +348,26 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
     }
   }
   if (rc == R2L_OK) {
+    rc = pack_bias(feature_b, 256, 1.0f, dst + off, m->bf16, st);
+    off += 256ull * 16;
+  }
+  if (rc == R2L_OK) {
     rc = pack_layer(feature_w, 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
     off += 256ull * 256;
+  }
+  if (rc == R2L_OK) {
+    pack_view_stage_kernel<<<(128 * 32 + 255) / 256, 256, 0, st>>>(views_w, 283, views_b, dst + off, m->bf16 ? 1 : 0);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(R2L_ERR_CUDA, "r2l_nerf_create: pack_view_stage launch failed");
+    off += 128ull * 32;
   }
   if (rc == R2L_OK) {
     rc = pack_layer(views_w, 283, 128, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
     off += 128ull * 256;
   }
   if (rc != R2L_OK) return cleanup(rc);
-  cudaError_t e = cudaSuccess;
-  for (int l = 0; l < 8 && e == cudaSuccess; ++l)
-    e = cudaMemcpyAsync(m->aux + kNerfAuxBias + l * 256, pts_b[l], 256 * 4, cudaMemcpyDeviceToDevice, st);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(m->aux + kNerfAuxBias + 8 * 256, feature_b, 256 * 4, cudaMemcpyDeviceToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxAlphaW, alpha_w, 256 * 4, cudaMemcpyDeviceToDevice, st);
+  if (off != elems) return cleanup(fail(R2L_ERR_INVALID, "r2l_nerf_create: internal stream size mismatch"));
+  cudaError_t e = cudaMemcpyAsync(m->aux + kNerfAuxAlphaW, alpha_w, 256 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxRgbW, rgb_w, 384 * 4, cudaMemcpyDeviceToDevice, st);
-  if (e == cudaSuccess)
-    e = cudaMemcpy2DAsync(m->aux + kNerfAuxWvd, 27 * 4, views_w + 256, 283 * 4, 27 * 4, 128, cudaMemcpyDeviceToDevice,
-                          st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxBv, views_b, 128 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&m->alpha_b, alpha_b, 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->rgb_b, rgb_b, 12, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -347,82 +383,89 @@ static int check_dbg(Mlp* m, const char* who) {
   return R2L_OK;
 }
 
-// Fused positional encoding + NeRF MLP on n_rays*S samples: raw[r, s, :] = NeRF(embed(o_r + d_r z_rs), embed(v_r)).
-// view_bias_ws: caller-provided workspace of n_rays*128 floats.
-int r2l_nerf_forward(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
-                     const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
-                     const float* z_vals, float* view_bias_ws, float* raw, void* stream) {
-  Mlp* m = static_cast<Mlp*>(handle);
-  R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_forward: not a NeRF handle");
-  R2L_CHECK_ARG(n_rays >= 0 && S > 0, "r2l_nerf_forward: bad sizes");
-  if (n_rays == 0) return R2L_OK;
-  R2L_CHECK_ARG(rays_o && rays_d && viewdirs && z_vals && view_bias_ws && raw, "r2l_nerf_forward: null pointer");
-  R2L_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "r2l_nerf_forward: raw must be 16-byte aligned");
-  int rc = check_dbg(m, "r2l_nerf_forward");
-  if (rc != R2L_OK) return rc;
-  auto st = static_cast<cudaStream_t>(stream);
-  rc = nerf_view_bias_launch(n_rays, viewdirs, v_stride, 0, m->aux + kNerfAuxWvd, m->aux + kNerfAuxBv, view_bias_ws, st);
-  if (rc != R2L_OK) return rc;
-  NerfParams p{};
+static int nerf_run(Mlp* m, NerfParams& p, cudaStream_t st) {
   p.wstream = m->wstream;
-  p.bias = m->aux + kNerfAuxBias;
   p.alpha_w = m->aux + kNerfAuxAlphaW;
   p.rgb_w = m->aux + kNerfAuxRgbW;
   p.alpha_b = m->alpha_b;
   for (int i = 0; i < 3; ++i) p.rgb_b[i] = m->rgb_b[i];
-  p.vb = view_bias_ws;
-  p.rays_o = rays_o;
-  p.rays_d = rays_d;
-  p.o_stride = o_stride;
-  p.d_stride = d_stride;
-  p.z_vals = z_vals;
-  p.S = S;
-  p.n_rows = n_rays * S;
-  p.raw = raw;
   const long long n_tiles = (p.n_rows + kTileM - 1) / kTileM;
   R2L_CHECK_ARG(n_tiles < (1LL << 31), "r2l_nerf_forward: too many samples for one call");
   p.n_tiles = static_cast<int>(n_tiles);
   p.dbg = m->dbg_dev;
-  p.embedded = nullptr;
-  p.emb_stride = 0;
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   return nerf_mlp_launch(m->bf16, p, grid, st);
 }
 
+// Fused positional encoding + NeRF MLP on n_rays*S samples: raw[r, s, :] = NeRF(embed(o_r + d_r z_rs), embed(v_r)).
+int r2l_nerf_forward(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
+                     const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
+                     const float* z_vals, float* raw, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_forward: not a NeRF handle");
+  R2L_CHECK_ARG(n_rays >= 0 && S > 0, "r2l_nerf_forward: bad sizes");
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(rays_o && rays_d && viewdirs && z_vals && raw, "r2l_nerf_forward: null pointer");
+  R2L_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "r2l_nerf_forward: raw must be 16-byte aligned");
+  int rc = check_dbg(m, "r2l_nerf_forward");
+  if (rc != R2L_OK) return rc;
+  NerfParams p{};
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.viewdirs = viewdirs;
+  p.o_stride = o_stride;
+  p.d_stride = d_stride;
+  p.v_stride = v_stride;
+  p.z_vals = z_vals;
+  p.S = S;
+  p.n_rows = n_rays * S;
+  p.raw = raw;
+  return nerf_run(m, p, static_cast<cudaStream_t>(stream));
+}
+
 // NeRF.forward(x) API path: x [M, ldx] holds 63 embedded-point features followed by 27
 // embedded-view features per row (model/nerf_raybased.py:377-401).  out [M, 4] = (rgb, sigma).
-int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long long ldx, float* view_bias_ws,
-                              float* out, void* stream) {
+int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long long ldx, float* out, void* stream) {
   Mlp* m = static_cast<Mlp*>(handle);
   R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_forward_embedded: not a NeRF handle");
   R2L_CHECK_ARG(M >= 0 && ldx >= 90, "r2l_nerf_forward_embedded: bad sizes");
   if (M == 0) return R2L_OK;
-  R2L_CHECK_ARG(x && view_bias_ws && out, "r2l_nerf_forward_embedded: null pointer");
+  R2L_CHECK_ARG(x && out, "r2l_nerf_forward_embedded: null pointer");
   R2L_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "r2l_nerf_forward_embedded: out must be 16-byte aligned");
   int rc = check_dbg(m, "r2l_nerf_forward_embedded");
   if (rc != R2L_OK) return rc;
-  auto st = static_cast<cudaStream_t>(stream);
-  rc = nerf_view_bias_launch(M, x + 63, ldx, 1, m->aux + kNerfAuxWvd, m->aux + kNerfAuxBv, view_bias_ws, st);
-  if (rc != R2L_OK) return rc;
   NerfParams p{};
-  p.wstream = m->wstream;
-  p.bias = m->aux + kNerfAuxBias;
-  p.alpha_w = m->aux + kNerfAuxAlphaW;
-  p.rgb_w = m->aux + kNerfAuxRgbW;
-  p.alpha_b = m->alpha_b;
-  for (int i = 0; i < 3; ++i) p.rgb_b[i] = m->rgb_b[i];
-  p.vb = view_bias_ws;
   p.S = 1;
   p.n_rows = M;
   p.raw = out;
-  const long long n_tiles = (M + kTileM - 1) / kTileM;
-  R2L_CHECK_ARG(n_tiles < (1LL << 31), "r2l_nerf_forward_embedded: too many rows for one call");
-  p.n_tiles = static_cast<int>(n_tiles);
-  p.dbg = m->dbg_dev;
   p.embedded = x;
   p.emb_stride = ldx;
-  const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  return nerf_mlp_launch(m->bf16, p, grid, st);
+  return nerf_run(m, p, static_cast<cudaStream_t>(stream));
+}
+
+// Profiling hook: r2l_nerf_forward + per-CTA cycle counters prof[n_CTAs][8] (device int64): [0] MMA thread total,
+// [1] waiting for A groups, [2] waiting for weight stages, [3]/[5] WG0/WG1 waiting for accumulators,
+// [4]/[6] WG0/WG1 epilogue work, [7] MMA thread waiting for the encoder.
+int r2l_nerf_profile(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
+                     const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
+                     const float* z_vals, float* raw, long long* prof, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_profile: not a NeRF handle");
+  R2L_CHECK_ARG(n_rays > 0 && S > 0 && rays_o && rays_d && viewdirs && z_vals && raw && prof,
+                "r2l_nerf_profile: bad arguments");
+  NerfParams p{};
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.viewdirs = viewdirs;
+  p.o_stride = o_stride;
+  p.d_stride = d_stride;
+  p.v_stride = v_stride;
+  p.z_vals = z_vals;
+  p.S = S;
+  p.n_rows = n_rays * S;
+  p.raw = raw;
+  p.prof = prof;
+  return nerf_run(m, p, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------- R2L ----------------------------------------------
@@ -447,21 +490,19 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
   m->sigmoid_out = sigmoid_out;
   m->outer_skip = outer_skip;
   std::vector<int*> scratch;
-  const float** d_b2 = nullptr;
   auto cleanup = [&](int rc) {
     cudaStreamSynchronize(st);
     for (int* s : scratch) cudaFree(s);
-    if (d_b2) cudaFree(d_b2);
     if (rc != R2L_OK) destroy(m);
     return rc;
   };
   const int K_head = n_points * 64;
-  const size_t elems = 256ull * K_head + static_cast<size_t>(n_blocks) * 2 * 256 * 256;
+  // stage stream in consumption order; every layer is [K=16 bias stage][K/32 weight stages]
+  const size_t elems = 256ull * 16 + 256ull * K_head + static_cast<size_t>(n_blocks) * 2 * (256 * 16 + 256 * 256);
   m->wbytes = elems * 2;
-  const size_t aux_floats = 256 + 2ull * n_blocks * 256 + 768;
+  const size_t aux_floats = 768;
   if (cudaMalloc(reinterpret_cast<void**>(&m->wstream), m->wbytes) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&m->aux), sizeof(float) * aux_floats) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&d_b2), sizeof(float*) * n_blocks) != cudaSuccess)
+      cudaMalloc(reinterpret_cast<void**>(&m->aux), sizeof(float) * aux_floats) != cudaSuccess)
     return cleanup(fail(R2L_ERR_CUDA, "r2l_resmlp_create: cudaMalloc failed"));
   int rc = alloc_debug(m);
   if (rc != R2L_OK) return cleanup(rc);
@@ -481,32 +522,30 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
   }
   uint16_t* dst = reinterpret_cast<uint16_t*>(m->wstream);
   size_t off = 0;
-  rc = pack_layer(head_w, static_cast<long long>(n_points) * 63, 256, n_points * 63, K_head, &kmap, 1.0f, dst, m->bf16,
-                  st, scratch);
+  rc = pack_bias(head_b, 256, 1.0f, dst + off, m->bf16, st);
+  off += 256ull * 16;
+  if (rc == R2L_OK)
+    rc = pack_layer(head_w, static_cast<long long>(n_points) * 63, 256, n_points * 63, K_head, &kmap, 1.0f, dst + off,
+                    m->bf16, st, scratch);
   off += 256ull * K_head;
   for (int b = 0; b < n_blocks && rc == R2L_OK; ++b) {
-    R2L_CHECK_ARG(w1[b] && b1[b] && w2[b] && b2[b], "r2l_resmlp_create: null block %d", b);
-    rc = pack_layer(w1[b], 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
+    if (!(w1[b] && b1[b] && w2[b] && b2[b])) {
+      rc = fail(R2L_ERR_INVALID, "r2l_resmlp_create: null block %d", b);
+      break;
+    }
+    rc = pack_bias(b1[b], 256, 1.0f, dst + off, m->bf16, st);
+    off += 256ull * 16;
+    if (rc == R2L_OK) rc = pack_layer(w1[b], 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
     off += 256ull * 256;
+    if (rc == R2L_OK) rc = pack_bias(b2[b], 256, static_cast<float>(res_scale), dst + off, m->bf16, st);
+    off += 256ull * 16;
     if (rc == R2L_OK)
       rc = pack_layer(w2[b], 256, 256, 256, 256, nullptr, static_cast<float>(res_scale), dst + off, m->bf16, st,
                       scratch);
     off += 256ull * 256;
   }
   if (rc != R2L_OK) return cleanup(rc);
-  float* a_bhead = m->aux;
-  float* a_b1 = m->aux + 256;
-  float* a_cb = a_b1 + static_cast<size_t>(n_blocks) * 256;
-  float* a_wt = a_cb + static_cast<size_t>(n_blocks) * 256;
-  cudaError_t e = cudaMemcpyAsync(a_bhead, head_b, 256 * 4, cudaMemcpyDeviceToDevice, st);
-  for (int b = 0; b < n_blocks && e == cudaSuccess; ++b)
-    e = cudaMemcpyAsync(a_b1 + static_cast<size_t>(b) * 256, b1[b], 256 * 4, cudaMemcpyDeviceToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(a_wt, tail_w, 768 * 4, cudaMemcpyDeviceToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_b2, b2, sizeof(float*) * n_blocks, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    cumulative_bias_kernel<<<1, 256, 0, st>>>(d_b2, n_blocks, 256, res_scale, a_cb);
-    e = cudaGetLastError();
-  }
+  cudaError_t e = cudaMemcpyAsync(m->aux, tail_w, 768 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->b_tail, tail_b, 12, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cleanup(fail(R2L_ERR_CUDA, "r2l_resmlp_create: %s", cudaGetErrorString(e)));
@@ -519,10 +558,7 @@ static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_
                       float* dbg_x0 = nullptr, void* dbg_a = nullptr, long long* prof = nullptr) {
   R2lParams p{};
   p.wstream = m->wstream;
-  p.b_head = m->aux;
-  p.b1 = m->aux + 256;
-  p.cb = p.b1 + static_cast<size_t>(m->n_blocks) * 256;
-  p.w_tail = p.cb + static_cast<size_t>(m->n_blocks) * 256;
+  p.w_tail = m->aux;
   for (int i = 0; i < 3; ++i) p.b_tail[i] = m->b_tail[i];
   p.n_blocks = m->n_blocks;
   p.n_points = m->n_points;

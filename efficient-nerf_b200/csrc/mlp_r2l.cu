@@ -2,176 +2,241 @@
 // Reference math: NeRF_v3_2.forward model/nerf_raybased.py:539-544, ResMLP.forward :461-465,
 // PositionalEmbedder.__call__ :198-208 on PointSampler points :94-126.
 //
-// One tile = 128 RAYS.  Per tile:
-//   head : x0 = relu(W_h enc(pts) + b_h); K = 64 per 3-D point (63 features + pad, weights
-//          permuted at pack time), encoded by the epilogue warps straight into the shared-memory
-//          A buffers in chunks of 4 points (K = 256) that ping-pong between the two buffers.
-//   body : 43 x [ h = relu(W1 x + b1) ;  x = x + res_scale*(W2 h + b2) ]
-//          The residual stream lives in TMEM columns [256,512) in fp32 for the whole body:
-//          the head accumulates there, x0 = relu(.) is stored back in place (tcgen05.st) and every W2
-//          layer ACCUMULATES onto it
-//          (tcgen05.mma with the accumulate flag), so the residual add costs nothing and is
-//          exact fp32.  The biases b2 are folded into a per-block cumulative bias cb_b that is
-//          added when x is read back (x_{b+1} = D2 + cb_b); W1 layers use TMEM columns [0,256).
-//   tail : rgb = sigmoid(W_t (x_43 + x0) + b_t)   (outer skip, use_residual) on CUDA cores in
-//          fp32: W_t x0 is accumulated at the head epilogue, W_t x_43 at the last epilogue.
-// Weight stream per tile: (P/4)*8 + 43*16 stages of 16 KiB (P = 16: 720 stages, 11.8 MB, L2 resident).
+// One tile = 128 RAYS.  Per tile (see mlp_tc.cuh for the execution model):
+//   head : x0 = relu(W_h enc(pts) + b_h); K = 64 per 3-D point (63 features + pad, weights permuted at
+//          pack time), encoded by the epilogue warps straight into the shared-memory A buffer in chunks
+//          of 4 points (K = 256); block j of the next chunk is written as soon as the MMAs have consumed
+//          block j of the current one.  The head accumulates in TMEM columns [256,512) ("D2").
+//   body : 43 x [ h = relu(W1 x + b1)  (accumulator D1 = columns [0,256)) ;
+//                 x = x + res_scale*(W2 h + b2)  (ACCUMULATED onto D2) ]
+//          The residual stream lives in D2 in fp32 for the whole body: x0 is stored back there once
+//          (tcgen05.st) and every W2 layer accumulates onto it (tcgen05.mma accumulate flag), so the
+//          residual add is free and exact fp32; b1/b2 ride along as the folded bias step.
+//   tail : rgb = sigmoid(W_t (x_43 + x0) + b_t)   (outer skip, use_residual) on CUDA cores in fp32:
+//          W_t x0 is accumulated at the head epilogue, W_t x_43 at the last epilogue.
+// Weight stream per tile: 1 + (P/4)*8 + 43*2*9 stages (P = 16: 807 stages, 12.4 MB, L2 resident).
 #include "common.cuh"
 #include "mlp_params.cuh"
 #include "mlp_tc.cuh"
 
 namespace r2l {
 
-constexpr int kR2lRing = 5;
-constexpr int kR2lOffA0 = 0;
-constexpr int kR2lOffA1 = kR2lOffA0 + kABufBytes;
-constexpr int kR2lOffRing = kR2lOffA1 + kABufBytes;
-constexpr int kR2lOffPart = kR2lOffRing + kR2lRing * kStageBytes;   // 128*3 floats
+constexpr int kR2lThreads = 320;
+constexpr int kR2lProducerWarp = 8;
+constexpr int kR2lMmaWarp = 9;
+constexpr int kR2lRing = 9;
+constexpr int kR2lOffA = 0;
+constexpr int kR2lOffOnes = kR2lOffA + kABufBytes;
+constexpr int kR2lOffRing = kR2lOffOnes + kOnesBytes;
+constexpr int kR2lOffWt = kR2lOffRing + kR2lRing * kStageBytes;     // 3*256 floats
+constexpr int kR2lOffPart = kR2lOffWt + 768 * 4;                    // 128*4 floats
 constexpr int kR2lOffBars = kR2lOffPart + 128 * 4 * 4;
-constexpr int kR2lNumBars = 2 * kR2lRing + 4 + 2 + 2;
+constexpr int kR2lNumBars = 2 * kR2lRing + 8 + 2 + 4 + 1;
 constexpr int kR2lOffTmem = kR2lOffBars + kR2lNumBars * 8;
 constexpr int kR2lSmemBytes = kR2lOffTmem + 16;
 static_assert(kR2lSmemBytes <= 227 * 1024, "R2L kernel shared memory exceeds 227 KiB");
+static_assert(kR2lOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
 
 template <bool BF16>
-__global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p) {
+__global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* const sA0 = smem + kR2lOffA0;   // A buffers are addressed as sA0 + buf*kABufBytes (no local arrays:
-                                            // dynamically indexed stack arrays were mis-overlapped by nvcc 12.9)
-  uint8_t* sRing = smem + kR2lOffRing;
-  float* sPart = reinterpret_cast<float*>(smem + kR2lOffPart);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kR2lOffBars);
-  uint64_t* w_full = bars;
-  uint64_t* w_empty = bars + kR2lRing;
-  uint64_t* a_ready = bars + 2 * kR2lRing;   // [buf*2 + half]
-  uint64_t* d_full = a_ready + 4;            // [0] = D1 (cols 0..255), [1] = D2 (cols 256..511)
-  uint64_t* a_free = d_full + 2;             // [buf]: head-chunk MMAs finished reading A[buf]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kR2lOffTmem);
+  uint8_t* const sA = smem + kR2lOffA;
+  uint8_t* const sOnes = smem + kR2lOffOnes;
+  uint8_t* const sRing = smem + kR2lOffRing;
+  float* const sWt = reinterpret_cast<float*>(smem + kR2lOffWt);
+  float* const sPart = reinterpret_cast<float*>(smem + kR2lOffPart);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kR2lOffBars);
+  uint64_t* const w_full = bars;
+  uint64_t* const w_empty = bars + kR2lRing;
+  uint64_t* const a_ready = bars + 2 * kR2lRing;   // [group 0..7]
+  uint64_t* const d_full = a_ready + 8;            // [0] = D1 (cols 0..255), [1] = D2 (cols 256..511)
+  uint64_t* const a_free = d_full + 2;             // [block 0..3]: head MMAs finished reading block j of A
+  uint64_t* const drained = a_free + 4;            // all 8 epilogue warps have read the tile's final accumulator (D2)
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + kR2lOffTmem);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_chunks = p.n_points / 4;
   const int nb = p.n_blocks;
 
+  // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < kR2lRing; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 128);
+    for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], 4);
     mbar_init(&d_full[0], 1);
     mbar_init(&d_full[1], 1);
-    mbar_init(&a_free[0], 1);
-    mbar_init(&a_free[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
+    mbar_init(drained, 8);
     mbar_fence_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
+  write_ones_block<BF16>(sOnes, threadIdx.x, kR2lThreads);
+  for (int i = threadIdx.x; i < 768; i += kR2lThreads) sWt[i] = p.w_tail[i];
+  fence_proxy_async_smem();
+  if (warp == kR2lMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kProducerWarp) {
+  if (warp == kR2lProducerWarp) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      const int stages_per_tile = n_chunks * 8 + nb * 16;
       uint32_t g = 0;
+      const uint8_t* src = nullptr;
+      auto push = [&](uint32_t bytes) {
+        const uint32_t slot = g % kR2lRing;
+        mbar_wait(&w_empty[slot], ((g / kR2lRing) & 1) ^ 1, p.dbg, 100 + slot);
+        mbar_expect_tx(&w_full[slot], bytes);
+        bulk_g2s(sRing + slot * kStageBytes, src, bytes, &w_full[slot]);
+        src += bytes;
+        ++g;
+      };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const uint8_t* src = p.wstream;
-        for (int st = 0; st < stages_per_tile; ++st) {
-          const uint32_t slot = g % kR2lRing;
-          mbar_wait(&w_empty[slot], ((g / kR2lRing) & 1) ^ 1, p.dbg, 100 + slot);
-          mbar_expect_tx(&w_full[slot], kStageBytes);
-          bulk_g2s(sRing + slot * kStageBytes, src, kStageBytes, &w_full[slot]);
-          src += kStageBytes;
-          ++g;
+        src = p.wstream;
+        push(kBiasStageBytes);
+        for (int i = 0; i < n_chunks * 8; ++i) push(kStageBytes);
+        for (int l = 0; l < 2 * nb; ++l) {
+          push(kBiasStageBytes);
+          for (int i = 0; i < 8; ++i) push(kStageBytes);
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kR2lMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(BF16, kTileM, 256);
-      const uint32_t aA0 = smem_u32(sA0);
+      const uint32_t aA = smem_u32(sA);
+      const uint32_t aOnes = smem_u32(sOnes);
       const uint32_t aRing = smem_u32(sRing);
       const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
       uint32_t g = 0;
-      uint32_t par_a = 0;   // bit (buf*2+half): parity of the next a_ready phase to wait for
+      uint32_t par_a = 0;   // parity of the a_ready phase the next layer / chunk waits for (all 8 groups in step)
       const bool prof = p.prof != nullptr;
-      long long t_a = 0, t_w = 0, t_start = prof ? clock64() : 0;
-      // 8 stages (K = 256) from A[buf] into d_tmem
-      auto run_k256 = [&](int buf, uint32_t d_tmem, bool fresh) {
+      long long t_a = 0, t_w = 0;
+      const long long t_start = prof ? clock64() : 0;
+      // the K=16 bias step of a layer (needs no activations)
+      auto bias_step = [&](uint32_t d_tmem, bool fresh) {
+        const uint32_t slot = g % kR2lRing;
+        const long long c0 = prof ? clock64() : 0;
+        mbar_wait(&w_full[slot], (g / kR2lRing) & 1, p.dbg, 240 + slot);
+        if (prof) t_w += clock64() - c0;
+        tc_fence_after_sync();
+        issue_bias_stage(d_tmem, aOnes, aRing + slot * kStageBytes, 256 * 16, idesc, fresh);
+        umma_commit(&w_empty[slot]);
+        ++g;
+      };
+      // 8 stages (K = 256) of A accumulated into d_tmem; `free_blocks`: release A blocks to the head encoders
+      auto run8 = [&](uint32_t d_tmem, bool free_blocks) {
         for (int st = 0; st < 8; ++st) {
-          if (st == 0 || st == 4) {
-            const int bi = buf * 2 + (st >> 2);
-            const long long c0 = prof ? clock64() : 0;
-            mbar_wait(&a_ready[bi], (par_a >> bi) & 1u, p.dbg, 210 + bi);
-            if (prof) t_a += clock64() - c0;
-            par_a ^= 1u << bi;
+          long long c0 = prof ? clock64() : 0;
+          mbar_wait(&a_ready[st], par_a, p.dbg, 210 + st);
+          if (prof) {
+            const long long c1 = clock64();
+            t_a += c1 - c0;
+            c0 = c1;
           }
           const uint32_t slot = g % kR2lRing;
-          const long long c1 = prof ? clock64() : 0;
           mbar_wait(&w_full[slot], (g / kR2lRing) & 1, p.dbg, 220 + slot);
-          if (prof) t_w += clock64() - c1;
+          if (prof) t_w += clock64() - c0;
           tc_fence_after_sync();
-          issue_stage(d_tmem, aA0 + buf * kABufBytes + st * 4 * kChunkBytes, aRing + slot * kStageBytes, 256 * 16, idesc,
-                      fresh && st == 0);
+          issue_stage(d_tmem, aA + st * kGroupBytes, aRing + slot * kStageBytes, 256 * 16, idesc, false);
           umma_commit(&w_empty[slot]);
+          if (free_blocks && (st & 1)) umma_commit(&a_free[st >> 1]);
           ++g;
         }
+        par_a ^= 1u;
       };
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        // head accumulates in D2: the next layer (W1 of block 0) writes D1 and may start on K-half 0 while
-        // WG1 is still reading the head accumulators (consecutive layers must never share a TMEM buffer)
-        for (int c = 0; c < n_chunks; ++c) {
-          run_k256(c & 1, d2, c == 0);
-          if (c + 2 < n_chunks) umma_commit(&a_free[c & 1]);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        // head accumulates in D2; W1 of block 0 then writes D1 (consecutive layers never share a TMEM buffer).
+        // The previous tile's last epilogue reads D2 without handing anything back through a_ready, so the
+        // first (overwriting) MMA of this tile waits until all epilogue warps have drained it.
+        if (it > 0) {
+          mbar_wait(drained, (it - 1) & 1u, p.dbg, 250);
+          tc_fence_after_sync();
         }
+        bias_step(d2, true);
+        for (int c = 0; c < n_chunks; ++c) run8(d2, c + 1 < n_chunks);
         umma_commit(&d_full[1]);
         for (int b = 0; b < nb; ++b) {
-          run_k256(0, d1, true);
+          bias_step(d1, true);
+          run8(d1, false);
           umma_commit(&d_full[0]);
-          run_k256(1, d2, false);   // accumulate onto the fp32 residual stream
+          bias_step(d2, false);   // accumulate onto the fp32 residual stream
+          run8(d2, false);
           umma_commit(&d_full[1]);
         }
       }
       if (prof) {
         long long* o = p.prof + blockIdx.x * 8;
         o[0] = clock64() - t_start;   // MMA thread: total
-        o[1] = t_a;                   // waiting for A (epilogues / encoders)
+        o[1] = t_a;                   // waiting for A groups (epilogues / encoders)
         o[2] = t_w;                   // waiting for weight stages
       }
     }
   } else {
     // ===================== epilogue / encoder warpgroups =====================
-    const int wg = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
+    const int wg = warp >> 2;                    // owns groups g = 2*gi + wg
+    const int row = (warp & 3) * 32 + lane;      // tile row == TMEM lane
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const int c0 = wg * 128;
     const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
-    long long t_d = 0, t_enc = 0, t_start = prof ? clock64() : 0;
+    long long t_d = 0, t_enc = 0;
+    const long long t_start = prof ? clock64() : 0;
     uint32_t par_d = 0;      // bit dbuf: parity of the next d_full phase
-    uint32_t par_free = 0;   // bit buf: parity of the next a_free phase
+    uint32_t par_free = 0;   // bit j: parity of the next a_free[j] phase
+    uint8_t* const a_row = sA + row * 16;
+    auto wait_d = [&](int db, uint32_t id) {
+      const long long cd = prof ? clock64() : 0;
+      mbar_wait(&d_full[db], (par_d >> db) & 1u, p.dbg, id);
+      if (prof) t_d += clock64() - cd;
+      par_d ^= 1u << db;
+      tc_fence_after_sync();
+    };
+    // One layer's epilogue for this warp's 4 groups, software pipelined: the TMEM load of group i+1 is in
+    // flight while group i is converted, stored and signalled.  f(g, v) consumes group g's 32 fp32 values.
+    auto for_groups = [&](uint32_t d_col0, auto&& f) {
+      uint32_t va[32], vb[32];
+      tmem_ld32(lane_taddr + d_col0 + 32 * wg, va);
+      tmem_ld_wait();
+      tmem_ld32(lane_taddr + d_col0 + 32 * (2 + wg), vb);
+      f(wg, va);
+      tmem_ld_wait();
+      tmem_ld32(lane_taddr + d_col0 + 32 * (4 + wg), va);
+      f(2 + wg, vb);
+      tmem_ld_wait();
+      tmem_ld32(lane_taddr + d_col0 + 32 * (6 + wg), vb);
+      f(4 + wg, va);
+      tmem_ld_wait();
+      f(6 + wg, vb);
+    };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long ray = static_cast<long long>(tile) * kTileM + row;
       const bool valid = ray < p.n_rays;
       const long long ray_c = valid ? ray : (p.n_rays - 1);
       const float* prow = (p.pts != nullptr) ? p.pts + ray_c * p.pts_stride : nullptr;
       const float* erow = (p.embedded != nullptr) ? p.embedded + ray_c * p.emb_stride : nullptr;
-      // ---- head: encode chunks of 4 points (K = 256); this WG owns points 2*wg, 2*wg+1 of each chunk
+      // ---- head: chunks of 4 points (K = 256); this WG encodes blocks j = wg and wg+2 of every chunk
       const long long ce = prof ? clock64() : 0;
       for (int c = 0; c < n_chunks; ++c) {
-        const int buf = c & 1;
-        if (c >= 2) {
-          mbar_wait(&a_free[buf], (par_free >> buf) & 1u, p.dbg, 400 + buf);
-          par_free ^= 1u << buf;
-        }
 #pragma unroll 1
-        for (int bl = 0; bl < 2; ++bl) {
-          const int pt = c * 4 + wg * 2 + bl;
-          uint8_t* blk = sA0 + buf * kABufBytes + (wg * 2 + bl) * 8 * kChunkBytes;
+        for (int bi = 0; bi < 2; ++bi) {
+          const int j = wg + 2 * bi;
+          const int pt = c * 4 + j;
+          float px = 0.f, py = 0.f, pz = 0.f;
           if (erow == nullptr) {
-            const float px = __ldg(prow + 3 * pt), py = __ldg(prow + 3 * pt + 1), pz = __ldg(prow + 3 * pt + 2);
+            px = __ldg(prow + 3 * pt);
+            py = __ldg(prow + 3 * pt + 1);
+            pz = __ldg(prow + 3 * pt + 2);
+          }
+          if (c > 0) {
+            mbar_wait(&a_free[j], (par_free >> j) & 1u, p.dbg, 400 + j);
+            par_free ^= 1u << j;
+          }
+          uint8_t* blk = sA + j * 8 * kChunkBytes;
+          if (erow == nullptr) {
             encode_point_block<BF16>(blk, row, px, py, pz);
           } else {
             // API path: gather the caller's embedding (reference order (3s+c)*21 + f') into block order
@@ -199,111 +264,71 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
               *reinterpret_cast<uint4*>(blk + ch * kChunkBytes + row * 16) = q;
             }
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&a_ready[2 * j]);
+            mbar_arrive(&a_ready[2 * j + 1]);
+          }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&a_ready[buf * 2 + wg]);
       }
       if (prof) t_enc += clock64() - ce;
+
       float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-      const float* wt = p.w_tail;
-      // ---- head epilogue: x0 = relu(D2 + b_h) -> residual stream (written back in place to D2), A[0], tail partials
-      {
-        const long long cd = prof ? clock64() : 0;
-        mbar_wait(&d_full[1], (par_d >> 1) & 1u, p.dbg, 300);
-        if (prof) t_d += clock64() - cd;
-      }
-      par_d ^= 2u;
-      tc_fence_after_sync();
-      {
-        uint8_t* a_dst = sA0 + row * 16;
-        const float* bias = p.b_head;
-        const bool skip = p.outer_skip != 0;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const int col0 = c0 + h * 64;
-          epilogue_cols64<BF16, true, true>(lane_taddr + 256 + col0, a_dst + (col0 >> 3) * kChunkBytes, col0,
-                                            lane_taddr + 256 + col0, [&](int n, float acc) {
-                                              const float v = fmaxf(acc + __ldg(bias + n), 0.0f);
-                                              if (p.dbg_head_acc != nullptr) {
-                                                const long long o = (static_cast<long long>(tile) * kTileM + row) * 256 + n;
-                                                p.dbg_head_acc[o] = acc;
-                                                p.dbg_head_x0[o] = v;
-                                              }
-                                              if (skip) {
-                                                t0 = fmaf(__ldg(wt + n), v, t0);
-                                                t1 = fmaf(__ldg(wt + 256 + n), v, t1);
-                                                t2 = fmaf(__ldg(wt + 512 + n), v, t2);
-                                              }
-                                              return v;
-                                            });
+      // ---- head epilogue: x0 = relu(D2) -> stored back in place (fp32 residual stream), A, tail partials
+      wait_d(1, 300);
+      for_groups(256, [&](int g, uint32_t (&v)[32]) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = fmaxf(__uint_as_float(v[i]), 0.0f);
+          if (p.dbg_head_acc != nullptr) {   // debug hook: raw accumulator (bias included) and x0
+            const long long o = (static_cast<long long>(tile) * kTileM + row) * 256 + 32 * g + i;
+            p.dbg_head_acc[o] = __uint_as_float(v[i]);
+            p.dbg_head_x0[o] = x;
+          }
+          v[i] = __float_as_uint(x);
+          if (p.outer_skip) {
+            t0 = fmaf(sWt[32 * g + i], x, t0);
+            t1 = fmaf(sWt[256 + 32 * g + i], x, t1);
+            t2 = fmaf(sWt[512 + 32 * g + i], x, t2);
+          }
         }
+        tmem_st32(lane_taddr + 256 + 32 * g, v);
+        store_group<BF16, false>(v, a_row + g * kGroupBytes);
         tmem_st_wait();
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        mbar_arrive(&a_ready[0 * 2 + wg]);
-      }
+        warp_arrive(&a_ready[g], lane);
+      });
       // ---- body
       for (int b = 0; b < nb; ++b) {
-        // W1: h = relu(D1 + b1) -> A[1]
-        {
-          const long long cd = prof ? clock64() : 0;
-          mbar_wait(&d_full[0], par_d & 1u, p.dbg, 310);
-          if (prof) t_d += clock64() - cd;
-        }
-        par_d ^= 1u;
-        tc_fence_after_sync();
-        {
-          uint8_t* a_dst = sA0 + kABufBytes + row * 16;
-          const float* bias = p.b1 + b * 256;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const int col0 = c0 + h * 64;
-            epilogue_cols64<BF16, true, false>(lane_taddr + col0, a_dst + (col0 >> 3) * kChunkBytes, col0, 0u,
-                                               [&](int n, float acc) { return fmaxf(acc + __ldg(bias + n), 0.0f); });
-          }
-          fence_proxy_async_smem();
+        // W1: h = relu(D1) -> A
+        wait_d(0, 310);
+        for_groups(0, [&](int g, uint32_t (&v)[32]) {
+          store_group<BF16, true>(v, a_row + g * kGroupBytes);
+          warp_arrive(&a_ready[g], lane);
+        });
+        // W2: x = D2 -> A   (last block: tail partials instead)
+        wait_d(1, 320);
+        if (b + 1 < nb) {
+          for_groups(256, [&](int g, uint32_t (&v)[32]) {
+            store_group<BF16, false>(v, a_row + g * kGroupBytes);
+            warp_arrive(&a_ready[g], lane);
+          });
+        } else {
+          for_groups(256, [&](int g, uint32_t (&v)[32]) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = __uint_as_float(v[i]);
+              t0 = fmaf(sWt[32 * g + i], x, t0);
+              t1 = fmaf(sWt[256 + 32 * g + i], x, t1);
+              t2 = fmaf(sWt[512 + 32 * g + i], x, t2);
+            }
+          });
           tc_fence_before_sync();
-          mbar_arrive(&a_ready[1 * 2 + wg]);
-        }
-        // W2: x = D2 + cb_b -> A[0]   (last block: tail partials instead)
-        {
-          const long long cd = prof ? clock64() : 0;
-          mbar_wait(&d_full[1], (par_d >> 1) & 1u, p.dbg, 320);
-          if (prof) t_d += clock64() - cd;
-        }
-        par_d ^= 2u;
-        tc_fence_after_sync();
-        {
-          uint8_t* a_dst = sA0 + row * 16;
-          const float* bias = p.cb + b * 256;
-          if (b + 1 < nb) {
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-              const int col0 = c0 + h * 64;
-              epilogue_cols64<BF16, true, false>(lane_taddr + 256 + col0, a_dst + (col0 >> 3) * kChunkBytes, col0,
-                                                 0u, [&](int n, float acc) { return acc + __ldg(bias + n); });
-            }
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            mbar_arrive(&a_ready[0 * 2 + wg]);
-          } else {
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-              const int col0 = c0 + h * 64;
-              epilogue_cols64<BF16, false, false>(lane_taddr + 256 + col0, nullptr, col0, 0u,
-                                                  [&](int n, float acc) {
-                                                    const float v = acc + __ldg(bias + n);
-                                                    t0 = fmaf(__ldg(wt + n), v, t0);
-                                                    t1 = fmaf(__ldg(wt + 256 + n), v, t1);
-                                                    t2 = fmaf(__ldg(wt + 512 + n), v, t2);
-                                                    return v;
-                                                  });
-            }
-            tc_fence_before_sync();
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(drained);
         }
       }
-      // ---- tail: combine the two column halves, bias, sigmoid
+      // ---- tail: combine the two column sets, bias, sigmoid
       if (wg == 1) {
         sPart[row * 4 + 0] = t0;
         sPart[row * 4 + 1] = t1;
@@ -336,9 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
     }
   }
 
+  // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kR2lMmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }
@@ -347,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) r2l_mlp_kernel(const R2lParams p)
 template <bool BF16>
 int launch_r2l(const R2lParams& p, int grid, cudaStream_t st) {
   R2L_CUDA(cudaFuncSetAttribute(r2l_mlp_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR2lSmemBytes));
-  r2l_mlp_kernel<BF16><<<grid, kThreads, kR2lSmemBytes, st>>>(p);
+  r2l_mlp_kernel<BF16><<<grid, kR2lThreads, kR2lSmemBytes, st>>>(p);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }

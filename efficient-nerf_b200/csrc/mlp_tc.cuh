@@ -1,23 +1,29 @@
 // Shared pieces of the persistent fused-MLP kernels (NeRF W256xD8 and R2L W256xD88).
 //
-// Execution model (one CTA per SM, 320 threads, all 512 TMEM columns):
-//   warps 0-3  "WG0": epilogue / encoder for output columns [0,128)   (TMEM lane quarter = warp%4)
-//   warps 4-7  "WG1": epilogue / encoder for output columns [128,256)
-//   warp  8    weight producer: streams pre-packed 16-bit weight stages global(L2) -> shared
-//              with 1-D bulk copies (TMA engine) through a ring of kRing stages
-//   warp  9    MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16) with both
-//              operands in shared memory and fp32 accumulators in TMEM
-// A 128-row tile of activations never leaves the SM: layer l's accumulators are read from
-// TMEM (tcgen05.ld), bias/activation is applied in fp32 registers, the result is rounded to
-// 16 bit and written to the *other* shared-memory A buffer, which layer l+1's MMAs read.
-// Accumulators alternate between TMEM columns [0,256) and [256,512).
+// Execution model (one CTA per SM, all 512 TMEM columns, warp-specialised):
+//   warps 0-3  "WG0": epilogue warps, own the even 32-column groups (0,2,4,6) of a layer's output
+//   warps 4-7  "WG1": epilogue warps, own the odd groups (1,3,5,7)              (TMEM lane quarter = warp%4)
+//   [NeRF only] warps 8-11 "WG2": encoder warps (ray -> point -> sin/cos features of the NEXT tile)
+//   producer warp: streams pre-packed 16-bit weight stages global(L2) -> shared with 1-D bulk copies
+//              (TMA engine, UBLKCP) through a ring of 16 KiB stages
+//   MMA warp:  one thread issues tcgen05.mma (M=128, N=256|128, K=16), both operands in shared memory,
+//              fp32 accumulators in TMEM
+// A 128-row tile of activations never leaves the SM.  There is ONE activation buffer A [128 x 256]
+// (16-bit, k-chunk major): layer l's accumulators are read from TMEM (tcgen05.ld) 32 columns at a time,
+// rounded (+ReLU) to 16 bit by one cvt.rn[.relu].f16x2 per pair and written IN PLACE over A (all of layer
+// l's MMAs have completed by then).  Each 32-column group has its own mbarrier, so layer l+1's MMA for
+// K-stage s starts as soon as group s is written: the tensor pipe "chases" the epilogue and is idle only
+// for the latency of the first group.  Accumulators alternate between TMEM columns [0,256) and [256,512),
+// so the next layer writes its accumulator while the previous one is still being read.
+// Biases are folded into the MMA: every layer STARTS with one K=16 step whose A operand is a constant
+// "ones" block (columns 0 and 1 = 1.0) and whose weights hold bias_hi / bias_lo (16-bit split, exact to
+// 2^-22 relative in fp16) — it needs no activations, so it also covers part of the epilogue latency, and
+// the epilogue has no bias add at all.
 //
-// Synchronisation is mbarrier-only on the critical path:
-//   w_full[s]/w_empty[s]   weight ring           (producer <-> MMA, tcgen05.commit frees a slot)
-//   a_ready[buf][half]     "K-half of A buffer written and my TMEM reads are done" (WG -> MMA)
-//   d_full[dbuf]           "accumulator complete" (MMA -> WGs, tcgen05.commit)
-// The MMA warp starts layer l+1 on K-half 0 as soon as WG0 has produced it, so WG1's
-// epilogue overlaps the first half of the next layer's MMAs.
+// Synchronisation (mbarrier only on the critical path):
+//   w_full[s]/w_empty[s]  weight ring (producer <-> MMA; tcgen05.commit frees a slot)
+//   a_ready[g]            "32-column group g of A is written" (4 warps of the owning WG -> MMA), one phase / layer
+//   d_full[dbuf]          "accumulator complete" (MMA -> WGs, tcgen05.commit)
 #pragma once
 #include "tc_common.cuh"
 
@@ -27,14 +33,75 @@ constexpr int kTileM = 128;              // rows (samples / rays) per tile = UMM
 constexpr int kWidth = 256;              // hidden width = UMMA N
 constexpr int kStageK = 32;              // K elements per weight stage (2 x UMMA K=16)
 constexpr int kStageBytes = kWidth * kStageK * 2;      // 16 KiB
+constexpr int kBiasStageBytes = kWidth * 16 * 2;       // 8 KiB: the K=16 bias step of a 256-wide layer
 constexpr int kChunkBytes = kTileM * 16;               // one 8-element K-chunk of an A operand (128 rows x 16 B)
+constexpr int kGroupBytes = 4 * kChunkBytes;           // one 32-column group (= one weight stage's worth of K)
 constexpr int kABufBytes = kTileM * kWidth * 2;        // 64 KiB: [128 x 256] 16-bit, k-chunk major
 constexpr int kPBlockBytes = kTileM * 64 * 2;          // 16 KiB: one encoded 3-D point block (63 features + pad)
-constexpr int kThreads = 320;
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
+constexpr int kVBlockBytes = kTileM * 32 * 2;          // 8 KiB: encoded view direction (27 features, 1, 1, pad)
+constexpr int kOnesBytes = 2 * kChunkBytes;            // 4 KiB: constant A operand of the bias step
 constexpr uint32_t kLboA = kChunkBytes;  // 2048
 constexpr uint32_t kSbo = 128;
+
+// pack two fp32 into 16-bit x2 (lo in the low half), optionally clamping negatives to zero in the same instruction
+template <bool BF16, bool RELU>
+__device__ __forceinline__ uint32_t cvt2(float lo, float hi) {
+  uint32_t r;
+  if (BF16) {
+    if (RELU)
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    if (RELU)
+      asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
+
+// Write 32 accumulator columns of this thread's row as one 32-column group of the A operand.
+//   a_grp = A base + group*kGroupBytes + row*16.  A warp stores 512 contiguous bytes per chunk: conflict free.
+template <bool BF16, bool RELU>
+__device__ __forceinline__ void store_group(const uint32_t (&v)[32], uint8_t* a_grp) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint4 q;
+    q.x = cvt2<BF16, RELU>(__uint_as_float(v[8 * ch + 0]), __uint_as_float(v[8 * ch + 1]));
+    q.y = cvt2<BF16, RELU>(__uint_as_float(v[8 * ch + 2]), __uint_as_float(v[8 * ch + 3]));
+    q.z = cvt2<BF16, RELU>(__uint_as_float(v[8 * ch + 4]), __uint_as_float(v[8 * ch + 5]));
+    q.w = cvt2<BF16, RELU>(__uint_as_float(v[8 * ch + 6]), __uint_as_float(v[8 * ch + 7]));
+    *reinterpret_cast<uint4*>(a_grp + ch * kChunkBytes) = q;
+  }
+}
+
+// "My warp's part of this operand group is written": make the generic-proxy stores visible to the async
+// proxy (UMMA reads shared memory through it), order this warp's TMEM accesses before the signal, then ONE
+// lane arrives (barrier count = number of warps, not threads).
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// sin/cos of (x, 2x, 4x, ..., 2^(L-1) x) for L <= 10: accurate sincosf at octaves 0 and 5, exact double-angle
+// recurrence in between (4 doublings amplify the ~1 ulp seed error to < 2e-6, far below the 16-bit operand
+// rounding).  The reference computes sin(x * 2^f) with the product exact in fp32 (helpers:41-56).
+template <int L>
+__device__ __forceinline__ void sincos_octaves(float x, float (&s)[L], float (&c)[L]) {
+#pragma unroll
+  for (int f = 0; f < L; ++f) {
+    if (f == 0 || f == 5) {
+      sincosf(x * static_cast<float>(1 << f), &s[f], &c[f]);
+    } else {
+      const float t = 2.0f * s[f - 1];
+      s[f] = t * c[f - 1];
+      c[f] = fmaf(-t, s[f - 1], 1.0f);
+    }
+  }
+}
 
 // Encode one 3-D point into the 64-wide "point block" of row `row`:
 //   k = 0..2 -> x,y,z ; k = 3+6f+c -> sin(2^f p_c) ; k = 3+6f+3+c -> cos(2^f p_c) ; k = 63 -> 0
@@ -47,19 +114,26 @@ __device__ __forceinline__ void encode_point_block(uint8_t* dst, int row, float 
   v[0] = px;
   v[1] = py;
   v[2] = pz;
+  {
+    float s[10], c[10];
+    sincos_octaves<10>(px, s, c);
 #pragma unroll
-  for (int f = 0; f < 10; ++f) {
-    const float sc = static_cast<float>(1 << f);
-    float s, c;
-    sincosf(px * sc, &s, &c);
-    v[3 + 6 * f + 0] = s;
-    v[3 + 6 * f + 3] = c;
-    sincosf(py * sc, &s, &c);
-    v[3 + 6 * f + 1] = s;
-    v[3 + 6 * f + 4] = c;
-    sincosf(pz * sc, &s, &c);
-    v[3 + 6 * f + 2] = s;
-    v[3 + 6 * f + 5] = c;
+    for (int f = 0; f < 10; ++f) {
+      v[3 + 6 * f + 0] = s[f];
+      v[3 + 6 * f + 3] = c[f];
+    }
+    sincos_octaves<10>(py, s, c);
+#pragma unroll
+    for (int f = 0; f < 10; ++f) {
+      v[3 + 6 * f + 1] = s[f];
+      v[3 + 6 * f + 4] = c[f];
+    }
+    sincos_octaves<10>(pz, s, c);
+#pragma unroll
+    for (int f = 0; f < 10; ++f) {
+      v[3 + 6 * f + 2] = s[f];
+      v[3 + 6 * f + 5] = c[f];
+    }
   }
   v[63] = 0.0f;
 #pragma unroll
@@ -73,60 +147,48 @@ __device__ __forceinline__ void encode_point_block(uint8_t* dst, int row, float 
   }
 }
 
-// Epilogue for 64 accumulator columns [col0, col0+64) of this thread's row:
-//   f(n, acc) -> value (bias, activation and any side computation happen in `f`);
-//   WRITE_A : round the values to 16 bit and store them as 8 chunks of the next A operand
-//   ST_TMEM : also store the fp32 values to TMEM columns st_taddr.. (R2L residual stream)
-//   d_taddr : TMEM address of (this warp's lane quarter, accumulator column col0)
-//   a_dst   : A buffer base + (first chunk index)*kChunkBytes + row*16
-template <bool BF16, bool WRITE_A, bool ST_TMEM, class F>
-__device__ __forceinline__ void epilogue_cols64(uint32_t d_taddr, uint8_t* a_dst, int col0, uint32_t st_taddr,
-                                                F&& f) {
-  uint32_t v0[32], v1[32];
-  tmem_ld32(d_taddr, v0);
-  tmem_ld32(d_taddr + 32, v1);
-  tmem_ld_wait();
+// Write 32 fp32 values as the 32-wide block (4 chunks) of row `row`.
+template <bool BF16>
+__device__ __forceinline__ void store_block32(uint8_t* dst, int row, const float (&v)[32]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(f(col0 + i, __uint_as_float(v0[i])));
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(f(col0 + 32 + i, __uint_as_float(v1[i])));
-  if (WRITE_A) {
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      uint4 q;
-      q.x = pack2<BF16>(__uint_as_float(v0[8 * ch + 0]), __uint_as_float(v0[8 * ch + 1]));
-      q.y = pack2<BF16>(__uint_as_float(v0[8 * ch + 2]), __uint_as_float(v0[8 * ch + 3]));
-      q.z = pack2<BF16>(__uint_as_float(v0[8 * ch + 4]), __uint_as_float(v0[8 * ch + 5]));
-      q.w = pack2<BF16>(__uint_as_float(v0[8 * ch + 6]), __uint_as_float(v0[8 * ch + 7]));
-      *reinterpret_cast<uint4*>(a_dst + ch * kChunkBytes) = q;
-    }
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      uint4 q;
-      q.x = pack2<BF16>(__uint_as_float(v1[8 * ch + 0]), __uint_as_float(v1[8 * ch + 1]));
-      q.y = pack2<BF16>(__uint_as_float(v1[8 * ch + 2]), __uint_as_float(v1[8 * ch + 3]));
-      q.z = pack2<BF16>(__uint_as_float(v1[8 * ch + 4]), __uint_as_float(v1[8 * ch + 5]));
-      q.w = pack2<BF16>(__uint_as_float(v1[8 * ch + 6]), __uint_as_float(v1[8 * ch + 7]));
-      *reinterpret_cast<uint4*>(a_dst + (4 + ch) * kChunkBytes) = q;
-    }
-  }
-  if (ST_TMEM) {
-    tmem_st32(st_taddr, v0);
-    tmem_st32(st_taddr + 32, v1);
+  for (int ch = 0; ch < 4; ++ch) {
+    uint4 q;
+    q.x = pack2<BF16>(v[8 * ch + 0], v[8 * ch + 1]);
+    q.y = pack2<BF16>(v[8 * ch + 2], v[8 * ch + 3]);
+    q.z = pack2<BF16>(v[8 * ch + 4], v[8 * ch + 5]);
+    q.w = pack2<BF16>(v[8 * ch + 6], v[8 * ch + 7]);
+    *reinterpret_cast<uint4*>(dst + ch * kChunkBytes + row * 16) = q;
   }
 }
 
-// Issue the two K=16 MMAs of one weight stage.
+// Constant A operand of the bias step: column 0 and 1 are 1.0, the other 14 columns 0.
+template <bool BF16>
+__device__ __forceinline__ void write_ones_block(uint8_t* ones, int tid, int nthreads) {
+  const uint32_t one2 = pack2<BF16>(1.0f, 1.0f);
+  for (int r = tid; r < kTileM; r += nthreads) {
+    *reinterpret_cast<uint4*>(ones + r * 16) = make_uint4(one2, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(ones + kChunkBytes + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// Issue the two K=16 MMAs of one 32-wide weight stage (one thread).
 //   a_addr : shared address of the A operand's first chunk for this stage (4 chunks are consumed)
 //   b_addr : shared address of the weight stage; lbo_b = N*16
 __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t lbo_b,
-                                            uint32_t idesc, bool first_of_layer) {
+                                            uint32_t idesc, bool fresh) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const uint64_t ad = make_smem_desc(a_addr + j * 2 * kLboA, kLboA, kSbo);
     const uint64_t bd = make_smem_desc(b_addr + j * 2 * lbo_b, lbo_b, kSbo);
-    umma_f16_ss(d_tmem, ad, bd, idesc, (first_of_layer && j == 0) ? 0u : 1u);
+    umma_f16_ss(d_tmem, ad, bd, idesc, (fresh && j == 0) ? 0u : 1u);
   }
+}
+// The single K=16 MMA of a bias stage (A = the constant ones block).
+__device__ __forceinline__ void issue_bias_stage(uint32_t d_tmem, uint32_t ones_addr, uint32_t b_addr, uint32_t lbo_b,
+                                                 uint32_t idesc, bool fresh) {
+  const uint64_t ad = make_smem_desc(ones_addr, kLboA, kSbo);
+  const uint64_t bd = make_smem_desc(b_addr, lbo_b, kSbo);
+  umma_f16_ss(d_tmem, ad, bd, idesc, fresh ? 0u : 1u);
 }
 
 }  // namespace r2l

@@ -207,11 +207,10 @@ class NeRF(nn.Module):
         h = self.packed_handle()
         ro, rd, vd = (_rows(t, dev) for t in (rays_o, rays_d, viewdirs))
         z = _lib.as_f32_cuda(z_vals, dev)
-        ws = torch.empty((N, 128), dtype=torch.float32, device=dev)
         raw = torch.empty((N, S, 4), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.call("r2l_nerf_forward", h.h, N, S, _lib.ptr(ro), ro.stride(0), _lib.ptr(rd), rd.stride(0),
-                      _lib.ptr(vd), vd.stride(0), _lib.ptr(z), _lib.ptr(ws), _lib.ptr(raw), _lib.stream_ptr(dev))
+                      _lib.ptr(vd), vd.stride(0), _lib.ptr(z), _lib.ptr(raw), _lib.stream_ptr(dev))
         return raw
 
     # -- nn.Module API ---------------------------------------------------------------------
@@ -223,11 +222,10 @@ class NeRF(nn.Module):
             x2 = x2.contiguous()
             M = x2.shape[0]
             h = self.packed_handle()
-            ws = torch.empty((M, 128), dtype=torch.float32, device=x2.device)
             out = torch.empty((M, 4), dtype=torch.float32, device=x2.device)
             with torch.cuda.device(x2.device):
-                _lib.call("r2l_nerf_forward_embedded", h.h, M, _lib.ptr(x2), x2.stride(0), _lib.ptr(ws),
-                          _lib.ptr(out), _lib.stream_ptr(x2.device))
+                _lib.call("r2l_nerf_forward_embedded", h.h, M, _lib.ptr(x2), x2.stride(0), _lib.ptr(out),
+                          _lib.stream_ptr(x2.device))
             return out.reshape(*lead, 4)
         return self._forward_fp32(x2).reshape(*lead, -1)
 

@@ -103,14 +103,19 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
                     void* stream);
 
 /* run_network + NeRF.forward fused (main.py:65-87, model/nerf_raybased.py:377-401):
- * raw[r,s,:] = NeRF(embed(o_r + d_r z_rs), embed(viewdir_r)).  view_bias_ws: n_rays*128 floats. */
+ * raw[r,s,:] = NeRF(embed(o_r + d_r z_rs), embed(viewdir_r)); raw [n_rays,S,4] = (rgb, sigma). */
 int r2l_nerf_forward(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
                      const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
-                     const float* z_vals, float* view_bias_ws, float* raw, void* stream);
+                     const float* z_vals, float* raw, void* stream);
 
-/* NeRF.forward(x [M, >=90]) -> [M,4]   (model/nerf_raybased.py:377-401).  view_bias_ws: M*128 floats. */
-int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long long ldx, float* view_bias_ws,
-                              float* out, void* stream);
+/* NeRF.forward(x [M, >=90]) -> [M,4]   (model/nerf_raybased.py:377-401). */
+int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long long ldx, float* out, void* stream);
+
+/* Profiling hook: r2l_nerf_forward + per-CTA cycle counters prof[n_CTAs][8] (device int64): MMA-thread total /
+ * wait-for-A / wait-for-weights, WG0 and WG1 wait-for-accumulator / epilogue work, MMA wait-for-encoder. */
+int r2l_nerf_profile(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
+                     const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
+                     const float* z_vals, float* raw, long long* prof, void* stream);
 
 /* Packed NeRF_v3_2 with ResMLP body (model/nerf_raybased.py:443-544): head Linear(n_points*63, 256),
  * n_blocks x ResMLP(256, n_learnable=2), tail Linear(256, 3) [+ Sigmoid]. */

@@ -267,18 +267,24 @@ def test_r2l_head_accumulators_and_packed_weights(E, O, n_points):
     torch.cuda.synchronize()
     x = O.embed_r2l(pts.cpu(), 10)
     W, b = net.head[0].weight.detach().cpu(), net.head[0].bias.detach().cpu()
-    acc_ref = torch.nn.functional.linear(x.half().double(), W.half().double()).float()
+    # the bias is folded into the MMA (hi/lo 16-bit split x 1.0), so the accumulators already include it
+    acc_ref = (torch.nn.functional.linear(x.half().double(), W.half().double()) + b.double()).float()
     assert maxabs(acc[:200], acc_ref) < 2e-3
-    assert maxabs(x0[:200], torch.relu(acc_ref + b)) < 2e-3
+    assert maxabs(x0[:200], torch.relu(acc_ref)) < 2e-3
     with torch.no_grad():
         assert maxabs(rgb, net._forward_fp32(x.cuda())) < 2e-3
     n = ctypes.c_ulonglong(0)
     L.call("r2l_mlp_debug_wstream", h.h, None, 0, ctypes.byref(n))
-    assert n.value == 2 * (256 * n_points * 64 + 2 * 2 * 256 * 256)
+    # stream = per layer [K=16 bias stage][K/32 weight stages]: head + 2 blocks x 2 layers
+    assert n.value == 2 * (256 * 16 + 256 * n_points * 64 + 2 * 2 * (256 * 16 + 256 * 256))
     buf = np.zeros(n.value // 2, dtype=np.float16)
     L.call("r2l_mlp_debug_wstream", h.h, buf.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n))
     K = n_points * 64
-    Wp = torch.from_numpy(buf[:256 * K]).float().reshape(K // 32, 4, 256, 8).permute(2, 0, 1, 3).reshape(256, K)
+    bias_stage = torch.from_numpy(buf[:256 * 16]).float().reshape(2, 256, 8)     # [k-chunk][n][k%8]
+    assert maxabs(bias_stage[0, :, 0] + bias_stage[0, :, 1], b) < 1e-6              # hi + lo == bias
+    assert float(bias_stage[0, :, 2:].abs().max()) == 0. and float(bias_stage[1].abs().max()) == 0.
+    Wp = torch.from_numpy(buf[256 * 16:256 * 16 + 256 * K]).float().reshape(K // 32, 4, 256, 8).permute(2, 0, 1, 3)
+    Wp = Wp.reshape(256, K)
     for s_ in range(n_points):          # block order: k = 64 s + i ; i<3 identity, then (sin, cos) per frequency
         for c in range(3):
             assert torch.equal(Wp[:, 64 * s_ + c], W[:, (3 * s_ + c) * 21 + 20].half().float())
