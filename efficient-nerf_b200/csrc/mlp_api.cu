@@ -44,8 +44,8 @@ int sm_count() {
 // ---------------------------------------------------------------------------------
 // W [N, *] fp32 row-major (row stride ldw)  ->  stage stream of 16-bit values.
 // Logical operand B[n][k], k in [0, Kpad): source column kmap[k] (or k when kmap == nullptr),
-// -1 / out-of-range -> 0.  Stage s holds k in [32s, 32s+32), k-chunk major:
-//   element offset = s*(N*32) + ((k%32)/8)*(N*8) + n*8 + (k%8)
+// -1 / out-of-range -> 0.  Stage s holds k in [64s, 64s+64) (kStageK), k-chunk major:
+//   element offset = s*(N*64) + ((k%64)/8)*(N*8) + n*8 + (k%8)
 __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, int N, int K_src, int Kpad,
                                   const int* __restrict__ kmap, float scale, uint16_t* __restrict__ dst, int bf16) {
   const long long total = static_cast<long long>(N) * Kpad;
@@ -60,8 +60,8 @@ __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, in
       bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
     else
       bits = __half_as_ushort(__float2half_rn(v));
-    const int s = k >> 5, kk = k & 31;
-    dst[static_cast<long long>(s) * N * 32 + (kk >> 3) * (N * 8) + n * 8 + (kk & 7)] = bits;
+    const int s = k / kStageK, kk = k % kStageK;
+    dst[static_cast<long long>(s) * N * kStageK + (kk >> 3) * (N * 8) + n * 8 + (kk & 7)] = bits;
   }
 }
 
@@ -201,20 +201,23 @@ gemm_probe_kernel(const float* __restrict__ A, int K, const uint16_t* __restrict
     const uint32_t bytes = static_cast<uint32_t>(N) * K * 2;
     mbar_expect_tx(&bars[0], bytes);
     // bulk copies are limited in size per instruction; move stage by stage
-    const uint32_t stage_bytes = static_cast<uint32_t>(N) * 64;
-    for (uint32_t off = 0; off < bytes; off += stage_bytes)
-      bulk_g2s(sB + off, reinterpret_cast<const uint8_t*>(Bpacked) + off, stage_bytes, &bars[0]);
+    // bulk copies in pieces of 32 K-columns (the packed stream is contiguous)
+    const uint32_t piece_bytes = static_cast<uint32_t>(N) * 64;
+    for (uint32_t off = 0; off < bytes; off += piece_bytes)
+      bulk_g2s(sB + off, reinterpret_cast<const uint8_t*>(Bpacked) + off, piece_bytes, &bars[0]);
     mbar_wait(&bars[0], 0, dbg, 1);
     tc_fence_after_sync();
     const uint32_t idesc = make_idesc_f16(BF16, kTileM, N);
     const uint32_t lbo_b = static_cast<uint32_t>(N) * 16;
-    for (int s = 0; s < K / 32; ++s) {
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t a_addr = smem_u32(sA) + (s * 4 + j * 2) * kChunkBytes;
-        const uint32_t b_addr = smem_u32(sB) + s * stage_bytes + j * 2 * lbo_b;
+    // K-step ks (16 columns) lives in stage ks/4 (a partial last stage holds K%64 columns, still k-chunk major)
+    for (int ks = 0; ks < K / 16; ++ks) {
+      {
+        const int s = ks / 4, j = ks % 4;
+        const uint32_t a_addr = smem_u32(sA) + ks * 2 * kChunkBytes;
+        const uint32_t b_addr = smem_u32(sB) + s * (static_cast<uint32_t>(N) * kStageK * 2) + j * 2 * lbo_b;
         const uint64_t ad = swap_lbo_sbo ? make_smem_desc(a_addr, kSbo, kLboA) : make_smem_desc(a_addr, kLboA, kSbo);
         const uint64_t bd = swap_lbo_sbo ? make_smem_desc(b_addr, kSbo, lbo_b) : make_smem_desc(b_addr, lbo_b, kSbo);
-        umma_f16_ss(tmem_base, ad, bd, idesc, (s | j) != 0 ? 1u : 0u);
+        umma_f16_ss(tmem_base, ad, bd, idesc, ks != 0 ? 1u : 0u);
       }
     }
     umma_commit(&bars[1]);

@@ -14,7 +14,8 @@
 //   9   : v = relu(Wv [V, f])                         N = 128, K = 32 + 256  (bias rides in V's ones columns)
 //         rgb = Wr v + br                             fp32 CUDA cores
 //   raw[g] = (rgb, sigma)
-// Weight stream per tile: 86 stages (9 bias stages of 8 KiB, 68 of 16 KiB, 9 of 8 KiB for the N = 128 layer).
+// Weight stream per tile: 9 bias stages + the view stage (8 KiB each, small ring), 34 K=64 stages of 32 KiB and
+// 4 of 16 KiB for the N = 128 layer (main ring).
 #include "common.cuh"
 #include "mlp_params.cuh"
 #include "mlp_tc.cuh"
@@ -24,18 +25,20 @@ namespace r2l {
 constexpr int kNerfThreads = 448;
 constexpr int kNerfProducerWarp = 12;
 constexpr int kNerfMmaWarp = 13;
-constexpr int kNerfRing = 6;
+constexpr int kNerfRing = 3;       // 32 KiB weight stages (K = 64)
+constexpr int kNerfBiasRing = 1;   // 8 KiB bias / view stages
 // shared memory map
 constexpr int kNerfOffA = 0;
 constexpr int kNerfOffP = kNerfOffA + kABufBytes;                     // 2 point blocks (double buffered)
 constexpr int kNerfOffV = kNerfOffP + 2 * kPBlockBytes;               // 2 view blocks
 constexpr int kNerfOffOnes = kNerfOffV + 2 * kVBlockBytes;
 constexpr int kNerfOffRing = kNerfOffOnes + kOnesBytes;
-constexpr int kNerfOffAlphaW = kNerfOffRing + kNerfRing * kStageBytes;   // 256 floats
+constexpr int kNerfOffBiasRing = kNerfOffRing + kNerfRing * kStageBytes;
+constexpr int kNerfOffAlphaW = kNerfOffBiasRing + kNerfBiasRing * kBiasStageBytes;   // 256 floats
 constexpr int kNerfOffRgbW = kNerfOffAlphaW + 256 * 4;                // 3*128 floats
 constexpr int kNerfOffPart = kNerfOffRgbW + 384 * 4;                  // 128 x float4
 constexpr int kNerfOffBars = kNerfOffPart + 128 * 16;
-constexpr int kNerfNumBars = 2 * kNerfRing + 8 + 2 + 2 + 2 + 1;
+constexpr int kNerfNumBars = 2 * kNerfRing + 2 * kNerfBiasRing + 4 + 2 + 2 + 2 + 1;
 constexpr int kNerfOffTmem = kNerfOffBars + kNerfNumBars * 8;
 constexpr int kNerfSmemBytes = kNerfOffTmem + 16;
 static_assert(kNerfSmemBytes <= 227 * 1024, "NeRF kernel shared memory exceeds 227 KiB");
@@ -49,14 +52,17 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
   uint8_t* const sV = smem + kNerfOffV;
   uint8_t* const sOnes = smem + kNerfOffOnes;
   uint8_t* const sRing = smem + kNerfOffRing;
+  uint8_t* const sBiasRing = smem + kNerfOffBiasRing;
   float* const sAlphaW = reinterpret_cast<float*>(smem + kNerfOffAlphaW);
   float* const sRgbW = reinterpret_cast<float*>(smem + kNerfOffRgbW);
   float4* const sPart = reinterpret_cast<float4*>(smem + kNerfOffPart);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kNerfOffBars);
   uint64_t* const w_full = bars;
   uint64_t* const w_empty = bars + kNerfRing;
-  uint64_t* const a_ready = bars + 2 * kNerfRing;   // [group 0..7]
-  uint64_t* const d_full = a_ready + 8;             // [dbuf]
+  uint64_t* const b_full = bars + 2 * kNerfRing;
+  uint64_t* const b_empty = b_full + kNerfBiasRing;
+  uint64_t* const a_ready = b_empty + kNerfBiasRing;   // [64-column group 0..3]
+  uint64_t* const d_full = a_ready + 4;             // [dbuf]
   uint64_t* const p_ready = d_full + 2;             // [buf]: P/V blocks of a tile are encoded
   uint64_t* const p_free = p_ready + 2;             // [buf]: all MMAs of the tile that used them have completed
   uint64_t* const drained = p_free + 2;             // all 8 epilogue warps have read the view-branch accumulator (D1)
@@ -74,7 +80,11 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], 4);
+    for (int i = 0; i < kNerfBiasRing; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 4);
     mbar_init(&d_full[0], 1);
     mbar_init(&d_full[1], 1);
     for (int i = 0; i < 2; ++i) {
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
   if (warp == kNerfProducerWarp) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      uint32_t g = 0;
+      uint32_t g = 0, gb = 0;
       const uint8_t* src = nullptr;
       auto push = [&](uint32_t bytes) {
         const uint32_t slot = g % kNerfRing;
@@ -104,14 +114,23 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
         src += bytes;
         ++g;
       };
+      auto push_bias = [&]() {
+        const uint32_t slot = gb % kNerfBiasRing;
+        mbar_wait(&b_empty[slot], ((gb / kNerfBiasRing) & 1) ^ 1, p.dbg, 120 + slot);
+        mbar_expect_tx(&b_full[slot], kBiasStageBytes);
+        bulk_g2s(sBiasRing + slot * kBiasStageBytes, src, kBiasStageBytes, &b_full[slot]);
+        src += kBiasStageBytes;
+        ++gb;
+      };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         src = p.wstream;
         for (int step = 0; step < 9; ++step) {
-          push(kBiasStageBytes);
-          const int n16 = (step == 0) ? 2 : (step == 5 ? 10 : 8);
-          for (int i = 0; i < n16; ++i) push(kStageBytes);
+          push_bias();
+          const int n = (step == 0) ? 1 : (step == 5 ? 5 : 4);
+          for (int i = 0; i < n; ++i) push(kStageBytes);
         }
-        for (int i = 0; i < 9; ++i) push(kStageBytes / 2);   // N = 128 layer: V stage + 8 stages
+        push_bias();                                          // view stage (N = 128, K = 32)
+        for (int i = 0; i < 4; ++i) push(kStageBytes / 2);    // N = 128 layer: 4 stages of 16 KiB
       }
     }
   } else if (warp == kNerfMmaWarp) {
@@ -122,46 +141,52 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
       const uint32_t aA = smem_u32(sA);
       const uint32_t aOnes = smem_u32(sOnes);
       const uint32_t aRing = smem_u32(sRing);
-      uint32_t g = 0;
-      uint32_t par_a = 0;   // parity of the a_ready phase the next layer waits for (all 8 groups in step)
+      const uint32_t aBiasRing = smem_u32(sBiasRing);
+      uint32_t g = 0, gb = 0;
+      uint32_t par_a = 0;   // parity of the a_ready phase the next layer waits for (all 4 groups in step)
       const bool prof = p.prof != nullptr;
       long long t_a = 0, t_w = 0, t_p = 0;
       const long long t_start = prof ? clock64() : 0;
-      // wait for the next weight stage; returns its shared address
-      auto next_w = [&]() -> uint32_t {
+      // wait for the next 8 KiB stage of the small ring (bias / view stage); returns its shared address
+      auto next_b = [&]() -> uint32_t {
+        const uint32_t slot = gb % kNerfBiasRing;
+        const long long c0 = prof ? clock64() : 0;
+        mbar_wait(&b_full[slot], (gb / kNerfBiasRing) & 1, p.dbg, 240 + slot);
+        if (prof) t_w += clock64() - c0;
+        tc_fence_after_sync();
+        return aBiasRing + slot * kBiasStageBytes;
+      };
+      auto release_b = [&]() {
+        umma_commit(&b_empty[gb % kNerfBiasRing]);
+        ++gb;
+      };
+      auto bias_step = [&](uint32_t d_tmem) {
+        const uint32_t b = next_b();
+        issue_bias_stage(d_tmem, aOnes, b, 256 * 16, idesc256, true);
+        release_b();
+      };
+      // one K=64 stage fed from the point block
+      auto run_p = [&](uint32_t d_tmem, uint32_t aP) {
         const uint32_t slot = g % kNerfRing;
         const long long c0 = prof ? clock64() : 0;
         mbar_wait(&w_full[slot], (g / kNerfRing) & 1, p.dbg, 220 + slot);
         if (prof) t_w += clock64() - c0;
         tc_fence_after_sync();
-        return aRing + slot * kStageBytes;
-      };
-      auto release_w = [&]() {
-        umma_commit(&w_empty[g % kNerfRing]);
+        issue_stage<4>(d_tmem, aP, aRing + slot * kStageBytes, 256 * 16, idesc256, false);
+        umma_commit(&w_empty[slot]);
         ++g;
       };
-      auto bias_step = [&](uint32_t d_tmem) {
-        const uint32_t b = next_w();
-        issue_bias_stage(d_tmem, aOnes, b, 256 * 16, idesc256, true);
-        release_w();
-      };
-      // two K=32 stages fed from the point block
-      auto run_p = [&](uint32_t d_tmem, uint32_t aP) {
-        for (int st = 0; st < 2; ++st) {
-          const uint32_t b = next_w();
-          issue_stage(d_tmem, aP + st * kGroupBytes, b, 256 * 16, idesc256, false);
-          release_w();
-        }
-      };
-      // eight K=32 stages fed from the activation buffer, chasing the previous layer's epilogue
-      auto run8 = [&](uint32_t d_tmem, uint32_t idesc, uint32_t lbo_b) {
-        for (int st = 0; st < 8; ++st) {
+      // four K=64 stages fed from the activation buffer, chasing the previous layer's epilogue
+      auto run4 = [&](uint32_t d_tmem, uint32_t idesc, uint32_t lbo_b) {
+        for (int st = 0; st < 4; ++st) {
+          const uint32_t slot = g % kNerfRing;
           const long long c0 = prof ? clock64() : 0;
-          mbar_wait(&a_ready[st], par_a, p.dbg, 210 + st);
+          mbar_wait2(&a_ready[st], par_a, &w_full[slot], (g / kNerfRing) & 1, p.dbg, 210 + st);
           if (prof) t_a += clock64() - c0;
-          const uint32_t b = next_w();
-          issue_stage(d_tmem, aA + st * kGroupBytes, b, lbo_b, idesc, false);
-          release_w();
+          tc_fence_after_sync();
+          issue_stage<4>(d_tmem, aA + st * kGroupBytes, aRing + slot * kStageBytes, lbo_b, idesc, false);
+          umma_commit(&w_empty[slot]);
+          ++g;
         }
         par_a ^= 1u;
       };
@@ -192,15 +217,15 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
           }
           bias_step(d);
           if (step == 5) run_p(d, aP);
-          run8(d, idesc256, 256 * 16);
+          run4(d, idesc256, 256 * 16);
           umma_commit(&d_full[step & 1]);
         }
         // step 9: view branch, N = 128
         {
-          const uint32_t b = next_w();
-          issue_stage(d1, aV, b, 128 * 16, idesc128, true);
-          release_w();
-          run8(d1, idesc128, 128 * 16);
+          const uint32_t b = next_b();
+          issue_stage<2>(d1, aV, b, 128 * 16, idesc128, true);
+          release_b();
+          run4(d1, idesc128, 128 * 16);
           umma_commit(&d_full[1]);
           umma_commit(&p_free[buf]);
         }
@@ -208,8 +233,8 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
       if (prof) {
         long long* o = p.prof + blockIdx.x * 8;
         o[0] = clock64() - t_start;   // MMA thread: total
-        o[1] = t_a;                   // waiting for A groups (epilogues)
-        o[2] = t_w;                   // waiting for weight stages
+        o[1] = t_a;                   // waiting for A groups + weight stages (joint wait)
+        o[2] = t_w;                   // waiting for bias / point-block weight stages
         o[7] = t_p;                   // waiting for the encoder
       }
     }
@@ -294,7 +319,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
     }
   } else {
     // ===================== epilogue warpgroups =====================
-    const int wg = warp >> 2;                       // owns groups g = 2*gi + wg
+    const int wg = warp >> 2;                       // owns the 64-column groups wg and wg+2
     const int row = (warp & 3) * 32 + lane;         // tile row == TMEM lane
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     uint8_t* const a_row = sA + row * 16;
@@ -309,22 +334,26 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
       par_d ^= 1u << db;
       tc_fence_after_sync();
     };
-    // One 256-wide layer's epilogue for this warp's 4 groups, software pipelined: the TMEM load of group i+1 is
-    // in flight while group i is converted, stored and signalled.
-    auto for_groups = [&](uint32_t d_col0, auto&& f) {
+    // One 256-wide layer's epilogue for this warp's two 64-column groups, as four 32-column pieces, software
+    // pipelined: the TMEM load of the next piece is in flight while the current one is converted and stored.
+    // f(col0, v) consumes 32 fp32 values starting at column col0; g_done(group) runs after both pieces of a group.
+    auto for_pieces = [&](uint32_t d_col0, auto&& f, auto&& g_done) {
       uint32_t va[32], vb[32];
-      tmem_ld32(lane_taddr + d_col0 + 32 * wg, va);
+      const uint32_t c0 = 64 * wg, c1 = 64 * (wg + 2);
+      tmem_ld32(lane_taddr + d_col0 + c0, va);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + 32 * (2 + wg), vb);
-      f(wg, va);
+      tmem_ld32(lane_taddr + d_col0 + c0 + 32, vb);
+      f(c0, va);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + 32 * (4 + wg), va);
-      f(2 + wg, vb);
+      tmem_ld32(lane_taddr + d_col0 + c1, va);
+      f(c0 + 32, vb);
+      g_done(wg);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + 32 * (6 + wg), vb);
-      f(4 + wg, va);
+      tmem_ld32(lane_taddr + d_col0 + c1 + 32, vb);
+      f(c1, va);
       tmem_ld_wait();
-      f(6 + wg, vb);
+      f(c1 + 32, vb);
+      g_done(wg + 2);
     };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long g_row = static_cast<long long>(tile) * kTileM + row;
@@ -333,40 +362,41 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
       for (int step = 0; step <= 8; ++step) {
         const int db = step & 1;
         wait_d(db, 300 + step);
+        auto signal = [&](int g) { warp_arrive(&a_ready[g], lane); };
         if (step == 7) {
-          for_groups(db * 256, [&](int g, uint32_t (&v)[32]) {
-            store_group<BF16, true>(v, a_row + g * kGroupBytes);
-            warp_arrive(&a_ready[g], lane);
+          for_pieces(
+              db * 256,
+              [&](uint32_t col0, uint32_t (&v)[32]) {
+                store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              sigma_part = fmaf(sAlphaW[32 * g + i], fmaxf(__uint_as_float(v[i]), 0.0f), sigma_part);
-          });
+                for (int i = 0; i < 32; ++i)
+                  sigma_part = fmaf(sAlphaW[col0 + i], fmaxf(__uint_as_float(v[i]), 0.0f), sigma_part);
+              },
+              signal);
         } else if (step == 8) {
-          for_groups(db * 256, [&](int g, uint32_t (&v)[32]) {
-            store_group<BF16, false>(v, a_row + g * kGroupBytes);
-            warp_arrive(&a_ready[g], lane);
-          });
+          for_pieces(
+              db * 256,
+              [&](uint32_t col0, uint32_t (&v)[32]) { store_sub<BF16, false>(v, a_row + (col0 >> 5) * kSubBytes); }, signal);
         } else {
-          for_groups(db * 256, [&](int g, uint32_t (&v)[32]) {
-            store_group<BF16, true>(v, a_row + g * kGroupBytes);
-            warp_arrive(&a_ready[g], lane);
-          });
+          for_pieces(
+              db * 256,
+              [&](uint32_t col0, uint32_t (&v)[32]) { store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes); }, signal);
         }
       }
-      // step 9: view branch (N = 128 -> D1 columns [256,384)); this WG owns groups wg and wg+2
+      // step 9: view branch (N = 128 -> D1 columns [256,384)); this WG owns the 64 columns [64*wg, 64*wg+64)
       wait_d(1, 309);
       float r = 0.f, gch = 0.f, b = 0.f;
       {
         uint32_t va[32], vb[32];
-        tmem_ld32(lane_taddr + 256 + 32 * wg, va);
-        tmem_ld32(lane_taddr + 256 + 32 * (2 + wg), vb);
+        tmem_ld32(lane_taddr + 256 + 64 * wg, va);
+        tmem_ld32(lane_taddr + 256 + 64 * wg + 32, vb);
         tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(drained);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int n = 32 * wg + i;
+          const int n = 64 * wg + i;
           const float x = fmaxf(__uint_as_float(va[i]), 0.0f);
           r = fmaf(sRgbW[n], x, r);
           gch = fmaf(sRgbW[128 + n], x, gch);
@@ -374,7 +404,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int n = 32 * (2 + wg) + i;
+          const int n = 64 * wg + 32 + i;
           const float x = fmaxf(__uint_as_float(vb[i]), 0.0f);
           r = fmaf(sRgbW[n], x, r);
           gch = fmaf(sRgbW[128 + n], x, gch);

@@ -14,7 +14,7 @@
 //          residual add is free and exact fp32; b1/b2 ride along as the folded bias step.
 //   tail : rgb = sigmoid(W_t (x_43 + x0) + b_t)   (outer skip, use_residual) on CUDA cores in fp32:
 //          W_t x0 is accumulated at the head epilogue, W_t x_43 at the last epilogue.
-// Weight stream per tile: 1 + (P/4)*8 + 43*2*9 stages (P = 16: 807 stages, 12.4 MB, L2 resident).
+// Weight stream per tile: per layer one 8 KiB bias stage + K/64 stages of 32 KiB (P = 16: 12.4 MB, L2 resident).
 #include "common.cuh"
 #include "mlp_params.cuh"
 #include "mlp_tc.cuh"
@@ -24,14 +24,16 @@ namespace r2l {
 constexpr int kR2lThreads = 320;
 constexpr int kR2lProducerWarp = 8;
 constexpr int kR2lMmaWarp = 9;
-constexpr int kR2lRing = 9;
+constexpr int kR2lRing = 4;       // 32 KiB weight stages (K = 64)
+constexpr int kR2lBiasRing = 2;   // 8 KiB bias stages
 constexpr int kR2lOffA = 0;
 constexpr int kR2lOffOnes = kR2lOffA + kABufBytes;
 constexpr int kR2lOffRing = kR2lOffOnes + kOnesBytes;
-constexpr int kR2lOffWt = kR2lOffRing + kR2lRing * kStageBytes;     // 3*256 floats
-constexpr int kR2lOffPart = kR2lOffWt + 768 * 4;                    // 128*4 floats
+constexpr int kR2lOffBiasRing = kR2lOffRing + kR2lRing * kStageBytes;
+constexpr int kR2lOffWt = kR2lOffBiasRing + kR2lBiasRing * kBiasStageBytes;   // 3*256 floats
+constexpr int kR2lOffPart = kR2lOffWt + 768 * 4;                              // 128*4 floats
 constexpr int kR2lOffBars = kR2lOffPart + 128 * 4 * 4;
-constexpr int kR2lNumBars = 2 * kR2lRing + 8 + 2 + 4 + 1;
+constexpr int kR2lNumBars = 2 * kR2lRing + 2 * kR2lBiasRing + 4 + 2 + 4 + 1;
 constexpr int kR2lOffTmem = kR2lOffBars + kR2lNumBars * 8;
 constexpr int kR2lSmemBytes = kR2lOffTmem + 16;
 static_assert(kR2lSmemBytes <= 227 * 1024, "R2L kernel shared memory exceeds 227 KiB");
@@ -43,13 +45,16 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
   uint8_t* const sA = smem + kR2lOffA;
   uint8_t* const sOnes = smem + kR2lOffOnes;
   uint8_t* const sRing = smem + kR2lOffRing;
+  uint8_t* const sBiasRing = smem + kR2lOffBiasRing;
   float* const sWt = reinterpret_cast<float*>(smem + kR2lOffWt);
   float* const sPart = reinterpret_cast<float*>(smem + kR2lOffPart);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kR2lOffBars);
   uint64_t* const w_full = bars;
   uint64_t* const w_empty = bars + kR2lRing;
-  uint64_t* const a_ready = bars + 2 * kR2lRing;   // [group 0..7]
-  uint64_t* const d_full = a_ready + 8;            // [0] = D1 (cols 0..255), [1] = D2 (cols 256..511)
+  uint64_t* const b_full = bars + 2 * kR2lRing;
+  uint64_t* const b_empty = b_full + kR2lBiasRing;
+  uint64_t* const a_ready = b_empty + kR2lBiasRing;   // [64-column group 0..3]
+  uint64_t* const d_full = a_ready + 4;            // [0] = D1 (cols 0..255), [1] = D2 (cols 256..511)
   uint64_t* const a_free = d_full + 2;             // [block 0..3]: head MMAs finished reading block j of A
   uint64_t* const drained = a_free + 4;            // all 8 epilogue warps have read the tile's final accumulator (D2)
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + kR2lOffTmem);
@@ -65,7 +70,11 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], 4);
+    for (int i = 0; i < kR2lBiasRing; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 4);
     mbar_init(&d_full[0], 1);
     mbar_init(&d_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
@@ -84,23 +93,31 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
   if (warp == kR2lProducerWarp) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      uint32_t g = 0;
+      uint32_t g = 0, gb = 0;
       const uint8_t* src = nullptr;
-      auto push = [&](uint32_t bytes) {
+      auto push = [&]() {
         const uint32_t slot = g % kR2lRing;
         mbar_wait(&w_empty[slot], ((g / kR2lRing) & 1) ^ 1, p.dbg, 100 + slot);
-        mbar_expect_tx(&w_full[slot], bytes);
-        bulk_g2s(sRing + slot * kStageBytes, src, bytes, &w_full[slot]);
-        src += bytes;
+        mbar_expect_tx(&w_full[slot], kStageBytes);
+        bulk_g2s(sRing + slot * kStageBytes, src, kStageBytes, &w_full[slot]);
+        src += kStageBytes;
         ++g;
+      };
+      auto push_bias = [&]() {
+        const uint32_t slot = gb % kR2lBiasRing;
+        mbar_wait(&b_empty[slot], ((gb / kR2lBiasRing) & 1) ^ 1, p.dbg, 120 + slot);
+        mbar_expect_tx(&b_full[slot], kBiasStageBytes);
+        bulk_g2s(sBiasRing + slot * kBiasStageBytes, src, kBiasStageBytes, &b_full[slot]);
+        src += kBiasStageBytes;
+        ++gb;
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         src = p.wstream;
-        push(kBiasStageBytes);
-        for (int i = 0; i < n_chunks * 8; ++i) push(kStageBytes);
+        push_bias();
+        for (int i = 0; i < n_chunks * 4; ++i) push();
         for (int l = 0; l < 2 * nb; ++l) {
-          push(kBiasStageBytes);
-          for (int i = 0; i < 8; ++i) push(kStageBytes);
+          push_bias();
+          for (int i = 0; i < 4; ++i) push();
         }
       }
     }
@@ -112,39 +129,34 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       const uint32_t aOnes = smem_u32(sOnes);
       const uint32_t aRing = smem_u32(sRing);
       const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
-      uint32_t g = 0;
-      uint32_t par_a = 0;   // parity of the a_ready phase the next layer / chunk waits for (all 8 groups in step)
+      const uint32_t aBiasRing = smem_u32(sBiasRing);
+      uint32_t g = 0, gb = 0;
+      uint32_t par_a = 0;   // parity of the a_ready phase the next layer / chunk waits for (all 4 groups in step)
       const bool prof = p.prof != nullptr;
       long long t_a = 0, t_w = 0;
       const long long t_start = prof ? clock64() : 0;
       // the K=16 bias step of a layer (needs no activations)
       auto bias_step = [&](uint32_t d_tmem, bool fresh) {
-        const uint32_t slot = g % kR2lRing;
+        const uint32_t slot = gb % kR2lBiasRing;
         const long long c0 = prof ? clock64() : 0;
-        mbar_wait(&w_full[slot], (g / kR2lRing) & 1, p.dbg, 240 + slot);
+        mbar_wait(&b_full[slot], (gb / kR2lBiasRing) & 1, p.dbg, 240 + slot);
         if (prof) t_w += clock64() - c0;
         tc_fence_after_sync();
-        issue_bias_stage(d_tmem, aOnes, aRing + slot * kStageBytes, 256 * 16, idesc, fresh);
-        umma_commit(&w_empty[slot]);
-        ++g;
+        issue_bias_stage(d_tmem, aOnes, aBiasRing + slot * kBiasStageBytes, 256 * 16, idesc, fresh);
+        umma_commit(&b_empty[slot]);
+        ++gb;
       };
-      // 8 stages (K = 256) of A accumulated into d_tmem; `free_blocks`: release A blocks to the head encoders
-      auto run8 = [&](uint32_t d_tmem, bool free_blocks) {
-        for (int st = 0; st < 8; ++st) {
-          long long c0 = prof ? clock64() : 0;
-          mbar_wait(&a_ready[st], par_a, p.dbg, 210 + st);
-          if (prof) {
-            const long long c1 = clock64();
-            t_a += c1 - c0;
-            c0 = c1;
-          }
+      // 4 stages (K = 256) of A accumulated into d_tmem; `free_blocks`: release A blocks to the head encoders
+      auto run4 = [&](uint32_t d_tmem, bool free_blocks) {
+        for (int st = 0; st < 4; ++st) {
           const uint32_t slot = g % kR2lRing;
-          mbar_wait(&w_full[slot], (g / kR2lRing) & 1, p.dbg, 220 + slot);
-          if (prof) t_w += clock64() - c0;
+          const long long c0 = prof ? clock64() : 0;
+          mbar_wait2(&a_ready[st], par_a, &w_full[slot], (g / kR2lRing) & 1, p.dbg, 210 + st);
+          if (prof) t_a += clock64() - c0;
           tc_fence_after_sync();
-          issue_stage(d_tmem, aA + st * kGroupBytes, aRing + slot * kStageBytes, 256 * 16, idesc, false);
+          issue_stage<4>(d_tmem, aA + st * kGroupBytes, aRing + slot * kStageBytes, 256 * 16, idesc, false);
           umma_commit(&w_empty[slot]);
-          if (free_blocks && (st & 1)) umma_commit(&a_free[st >> 1]);
+          if (free_blocks) umma_commit(&a_free[st]);
           ++g;
         }
         par_a ^= 1u;
@@ -159,27 +171,27 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           tc_fence_after_sync();
         }
         bias_step(d2, true);
-        for (int c = 0; c < n_chunks; ++c) run8(d2, c + 1 < n_chunks);
+        for (int c = 0; c < n_chunks; ++c) run4(d2, c + 1 < n_chunks);
         umma_commit(&d_full[1]);
         for (int b = 0; b < nb; ++b) {
           bias_step(d1, true);
-          run8(d1, false);
+          run4(d1, false);
           umma_commit(&d_full[0]);
           bias_step(d2, false);   // accumulate onto the fp32 residual stream
-          run8(d2, false);
+          run4(d2, false);
           umma_commit(&d_full[1]);
         }
       }
       if (prof) {
         long long* o = p.prof + blockIdx.x * 8;
         o[0] = clock64() - t_start;   // MMA thread: total
-        o[1] = t_a;                   // waiting for A groups (epilogues / encoders)
-        o[2] = t_w;                   // waiting for weight stages
+        o[1] = t_a;                   // waiting for A groups + weight stages (joint wait)
+        o[2] = t_w;                   // waiting for bias stages
       }
     }
   } else {
     // ===================== epilogue / encoder warpgroups =====================
-    const int wg = warp >> 2;                    // owns groups g = 2*gi + wg
+    const int wg = warp >> 2;                    // owns the 64-column groups wg and wg+2
     const int row = (warp & 3) * 32 + lane;      // tile row == TMEM lane
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
@@ -195,22 +207,27 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       par_d ^= 1u << db;
       tc_fence_after_sync();
     };
-    // One layer's epilogue for this warp's 4 groups, software pipelined: the TMEM load of group i+1 is in
-    // flight while group i is converted, stored and signalled.  f(g, v) consumes group g's 32 fp32 values.
-    auto for_groups = [&](uint32_t d_col0, auto&& f) {
+    // One layer's epilogue for this warp's two 64-column groups, as four 32-column pieces q (columns
+    // 64*(wg + 2*(q/2)) + 32*(q%2)), software pipelined: the TMEM load of piece q+1 is in flight while piece q is
+    // processed.  f(col0, v) consumes 32 fp32 values starting at column col0; g_done(group) runs after both
+    // pieces of a group.
+    auto for_pieces = [&](uint32_t d_col0, auto&& f, auto&& g_done) {
       uint32_t va[32], vb[32];
-      tmem_ld32(lane_taddr + d_col0 + 32 * wg, va);
+      const uint32_t c0 = 64 * wg, c1 = 64 * (wg + 2);
+      tmem_ld32(lane_taddr + d_col0 + c0, va);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + 32 * (2 + wg), vb);
-      f(wg, va);
+      tmem_ld32(lane_taddr + d_col0 + c0 + 32, vb);
+      f(c0, va);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + 32 * (4 + wg), va);
-      f(2 + wg, vb);
+      tmem_ld32(lane_taddr + d_col0 + c1, va);
+      f(c0 + 32, vb);
+      g_done(wg);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + 32 * (6 + wg), vb);
-      f(4 + wg, va);
+      tmem_ld32(lane_taddr + d_col0 + c1 + 32, vb);
+      f(c1, va);
       tmem_ld_wait();
-      f(6 + wg, vb);
+      f(c1 + 32, vb);
+      g_done(wg + 2);
     };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long ray = static_cast<long long>(tile) * kTileM + row;
@@ -266,10 +283,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&a_ready[2 * j]);
-            mbar_arrive(&a_ready[2 * j + 1]);
-          }
+          if (lane == 0) mbar_arrive(&a_ready[j]);
         }
       }
       if (prof) t_enc += clock64() - ce;
@@ -277,52 +291,57 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       float t0 = 0.f, t1 = 0.f, t2 = 0.f;
       // ---- head epilogue: x0 = relu(D2) -> stored back in place (fp32 residual stream), A, tail partials
       wait_d(1, 300);
-      for_groups(256, [&](int g, uint32_t (&v)[32]) {
+      for_pieces(
+          256,
+          [&](uint32_t col0, uint32_t (&v)[32]) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = fmaxf(__uint_as_float(v[i]), 0.0f);
-          if (p.dbg_head_acc != nullptr) {   // debug hook: raw accumulator (bias included) and x0
-            const long long o = (static_cast<long long>(tile) * kTileM + row) * 256 + 32 * g + i;
-            p.dbg_head_acc[o] = __uint_as_float(v[i]);
-            p.dbg_head_x0[o] = x;
-          }
-          v[i] = __float_as_uint(x);
-          if (p.outer_skip) {
-            t0 = fmaf(sWt[32 * g + i], x, t0);
-            t1 = fmaf(sWt[256 + 32 * g + i], x, t1);
-            t2 = fmaf(sWt[512 + 32 * g + i], x, t2);
-          }
-        }
-        tmem_st32(lane_taddr + 256 + 32 * g, v);
-        store_group<BF16, false>(v, a_row + g * kGroupBytes);
-        tmem_st_wait();
-        warp_arrive(&a_ready[g], lane);
-      });
+            for (int i = 0; i < 32; ++i) {
+              const float x = fmaxf(__uint_as_float(v[i]), 0.0f);
+              if (p.dbg_head_acc != nullptr) {   // debug hook: raw accumulator (bias included) and x0
+                const long long o = (static_cast<long long>(tile) * kTileM + row) * 256 + col0 + i;
+                p.dbg_head_acc[o] = __uint_as_float(v[i]);
+                p.dbg_head_x0[o] = x;
+              }
+              v[i] = __float_as_uint(x);
+              if (p.outer_skip) {
+                t0 = fmaf(sWt[col0 + i], x, t0);
+                t1 = fmaf(sWt[256 + col0 + i], x, t1);
+                t2 = fmaf(sWt[512 + col0 + i], x, t2);
+              }
+            }
+            tmem_st32(lane_taddr + 256 + col0, v);
+            store_sub<BF16, false>(v, a_row + (col0 >> 5) * kSubBytes);
+          },
+          [&](int g) {
+            tmem_st_wait();
+            warp_arrive(&a_ready[g], lane);
+          });
       // ---- body
       for (int b = 0; b < nb; ++b) {
         // W1: h = relu(D1) -> A
         wait_d(0, 310);
-        for_groups(0, [&](int g, uint32_t (&v)[32]) {
-          store_group<BF16, true>(v, a_row + g * kGroupBytes);
-          warp_arrive(&a_ready[g], lane);
-        });
+        for_pieces(
+            0, [&](uint32_t col0, uint32_t (&v)[32]) { store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes); },
+            [&](int g) { warp_arrive(&a_ready[g], lane); });
         // W2: x = D2 -> A   (last block: tail partials instead)
         wait_d(1, 320);
         if (b + 1 < nb) {
-          for_groups(256, [&](int g, uint32_t (&v)[32]) {
-            store_group<BF16, false>(v, a_row + g * kGroupBytes);
-            warp_arrive(&a_ready[g], lane);
-          });
+          for_pieces(
+              256, [&](uint32_t col0, uint32_t (&v)[32]) { store_sub<BF16, false>(v, a_row + (col0 >> 5) * kSubBytes); },
+              [&](int g) { warp_arrive(&a_ready[g], lane); });
         } else {
-          for_groups(256, [&](int g, uint32_t (&v)[32]) {
+          for_pieces(
+              256,
+              [&](uint32_t col0, uint32_t (&v)[32]) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = __uint_as_float(v[i]);
-              t0 = fmaf(sWt[32 * g + i], x, t0);
-              t1 = fmaf(sWt[256 + 32 * g + i], x, t1);
-              t2 = fmaf(sWt[512 + 32 * g + i], x, t2);
-            }
-          });
+                for (int i = 0; i < 32; ++i) {
+                  const float x = __uint_as_float(v[i]);
+                  t0 = fmaf(sWt[col0 + i], x, t0);
+                  t1 = fmaf(sWt[256 + col0 + i], x, t1);
+                  t2 = fmaf(sWt[512 + col0 + i], x, t2);
+                }
+              },
+              [&](int) {});
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(drained);

@@ -1,18 +1,20 @@
 // Shared pieces of the persistent fused-MLP kernels (NeRF W256xD8 and R2L W256xD88).
 //
 // Execution model (one CTA per SM, all 512 TMEM columns, warp-specialised):
-//   warps 0-3  "WG0": epilogue warps, own the even 32-column groups (0,2,4,6) of a layer's output
-//   warps 4-7  "WG1": epilogue warps, own the odd groups (1,3,5,7)              (TMEM lane quarter = warp%4)
+//   warps 0-3  "WG0": epilogue warps, own the even 64-column groups (0,2) of a layer's output
+//   warps 4-7  "WG1": epilogue warps, own the odd groups (1,3)                  (TMEM lane quarter = warp%4)
 //   [NeRF only] warps 8-11 "WG2": encoder warps (ray -> point -> sin/cos features of the NEXT tile)
 //   producer warp: streams pre-packed 16-bit weight stages global(L2) -> shared with 1-D bulk copies
-//              (TMA engine, UBLKCP) through a ring of 16 KiB stages
+//              (TMA engine, UBLKCP) through a ring of 32 KiB stages (K = 64) + a small ring of 8 KiB bias stages
 //   MMA warp:  one thread issues tcgen05.mma (M=128, N=256|128, K=16), both operands in shared memory,
-//              fp32 accumulators in TMEM
+//              fp32 accumulators in TMEM.  mbarrier operations cost ~100 cycles each on the issuing thread
+//              (measured, scratch/ubench), so a stage carries FOUR MMAs (512 tensor-pipe cycles) per pair of
+//              waits and the two waits of a stage are issued together.
 // A 128-row tile of activations never leaves the SM.  There is ONE activation buffer A [128 x 256]
 // (16-bit, k-chunk major): layer l's accumulators are read from TMEM (tcgen05.ld) 32 columns at a time,
 // rounded (+ReLU) to 16 bit by one cvt.rn[.relu].f16x2 per pair and written IN PLACE over A (all of layer
-// l's MMAs have completed by then).  Each 32-column group has its own mbarrier, so layer l+1's MMA for
-// K-stage s starts as soon as group s is written: the tensor pipe "chases" the epilogue and is idle only
+// l's MMAs have completed by then).  Each 64-column group has its own mbarrier, so layer l+1's MMAs for
+// K-stage s start as soon as group s is written: the tensor pipe "chases" the epilogue and is idle only
 // for the latency of the first group.  Accumulators alternate between TMEM columns [0,256) and [256,512),
 // so the next layer writes its accumulator while the previous one is still being read.
 // Biases are folded into the MMA: every layer STARTS with one K=16 step whose A operand is a constant
@@ -22,7 +24,7 @@
 //
 // Synchronisation (mbarrier only on the critical path):
 //   w_full[s]/w_empty[s]  weight ring (producer <-> MMA; tcgen05.commit frees a slot)
-//   a_ready[g]            "32-column group g of A is written" (4 warps of the owning WG -> MMA), one phase / layer
+//   a_ready[g]            "64-column group g of A is written" (4 warps of the owning WG -> MMA), one phase / layer
 //   d_full[dbuf]          "accumulator complete" (MMA -> WGs, tcgen05.commit)
 #pragma once
 #include "tc_common.cuh"
@@ -31,11 +33,12 @@ namespace r2l {
 
 constexpr int kTileM = 128;              // rows (samples / rays) per tile = UMMA M
 constexpr int kWidth = 256;              // hidden width = UMMA N
-constexpr int kStageK = 32;              // K elements per weight stage (2 x UMMA K=16)
-constexpr int kStageBytes = kWidth * kStageK * 2;      // 16 KiB
+constexpr int kStageK = 64;              // K elements per weight stage (4 x UMMA K=16)
+constexpr int kStageBytes = kWidth * kStageK * 2;      // 32 KiB
 constexpr int kBiasStageBytes = kWidth * 16 * 2;       // 8 KiB: the K=16 bias step of a 256-wide layer
 constexpr int kChunkBytes = kTileM * 16;               // one 8-element K-chunk of an A operand (128 rows x 16 B)
-constexpr int kGroupBytes = 4 * kChunkBytes;           // one 32-column group (= one weight stage's worth of K)
+constexpr int kSubBytes = 4 * kChunkBytes;             // 32 columns of A (one tcgen05.ld.x32 worth)
+constexpr int kGroupBytes = 8 * kChunkBytes;           // one 64-column group (= one weight stage's worth of K)
 constexpr int kABufBytes = kTileM * kWidth * 2;        // 64 KiB: [128 x 256] 16-bit, k-chunk major
 constexpr int kPBlockBytes = kTileM * 64 * 2;          // 16 KiB: one encoded 3-D point block (63 features + pad)
 constexpr int kVBlockBytes = kTileM * 32 * 2;          // 8 KiB: encoded view direction (27 features, 1, 1, pad)
@@ -61,10 +64,10 @@ __device__ __forceinline__ uint32_t cvt2(float lo, float hi) {
   return r;
 }
 
-// Write 32 accumulator columns of this thread's row as one 32-column group of the A operand.
-//   a_grp = A base + group*kGroupBytes + row*16.  A warp stores 512 contiguous bytes per chunk: conflict free.
+// Write 32 accumulator columns of this thread's row as 4 chunks of the A operand.
+//   a_sub = A base + (first column / 32)*kSubBytes + row*16.  A warp stores 512 contiguous bytes per chunk.
 template <bool BF16, bool RELU>
-__device__ __forceinline__ void store_group(const uint32_t (&v)[32], uint8_t* a_grp) {
+__device__ __forceinline__ void store_sub(const uint32_t (&v)[32], uint8_t* a_grp) {
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
     uint4 q;
@@ -171,13 +174,37 @@ __device__ __forceinline__ void write_ones_block(uint8_t* ones, int tid, int nth
   }
 }
 
-// Issue the two K=16 MMAs of one 32-wide weight stage (one thread).
-//   a_addr : shared address of the A operand's first chunk for this stage (4 chunks are consumed)
+// Wait for two barriers at once: both try_waits are in flight together, so the ~100-cycle latency of an
+// mbarrier operation is paid once per stage instead of twice.
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t par_a, uint64_t* bar_b, uint32_t par_b,
+                                           DebugBuf* dbg, uint32_t id) {
+  bool a = mbar_try_wait(bar_a, par_a);
+  bool b = mbar_try_wait(bar_b, par_b);
+  uint32_t spins = 0;
+  while (!(a && b)) {
+    if (!a) a = mbar_try_wait(bar_a, par_a);
+    if (!b) b = mbar_try_wait(bar_b, par_b);
+    if (++spins > R2L_WATCHDOG_SPINS) {
+      if (dbg != nullptr && atomicCAS(&dbg->flag, 0u, 1u) == 0u) {
+        dbg->block = blockIdx.x;
+        dbg->thread = threadIdx.x;
+        dbg->barrier_id = id + (a ? 1000u : 0u);
+        dbg->parity = par_a | (par_b << 1);
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
+// Issue the K=16 MMAs of one weight stage (one thread): N_MMA = 4 for a full K=64 stage, 2 for a K=32 stage.
+//   a_addr : shared address of the A operand's first chunk for this stage (2*N_MMA chunks are consumed)
 //   b_addr : shared address of the weight stage; lbo_b = N*16
+template <int N_MMA = 4>
 __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t lbo_b,
                                             uint32_t idesc, bool fresh) {
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < N_MMA; ++j) {
     const uint64_t ad = make_smem_desc(a_addr + j * 2 * kLboA, kLboA, kSbo);
     const uint64_t bd = make_smem_desc(b_addr + j * 2 * lbo_b, lbo_b, kSbo);
     umma_f16_ss(d_tmem, ad, bd, idesc, (fresh && j == 0) ? 0u : 1u);

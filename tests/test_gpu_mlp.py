@@ -283,7 +283,7 @@ def test_r2l_head_accumulators_and_packed_weights(E, O, n_points):
     bias_stage = torch.from_numpy(buf[:256 * 16]).float().reshape(2, 256, 8)     # [k-chunk][n][k%8]
     assert maxabs(bias_stage[0, :, 0] + bias_stage[0, :, 1], b) < 1e-6              # hi + lo == bias
     assert float(bias_stage[0, :, 2:].abs().max()) == 0. and float(bias_stage[1].abs().max()) == 0.
-    Wp = torch.from_numpy(buf[256 * 16:256 * 16 + 256 * K]).float().reshape(K // 32, 4, 256, 8).permute(2, 0, 1, 3)
+    Wp = torch.from_numpy(buf[256 * 16:256 * 16 + 256 * K]).float().reshape(K // 64, 8, 256, 8).permute(2, 0, 1, 3)
     Wp = Wp.reshape(256, K)
     for s_ in range(n_points):          # block order: k = 64 s + i ; i<3 identity, then (sin, cos) per frequency
         for c in range(3):
