@@ -66,16 +66,25 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.n0 = 0
 
     def start(self):
+        """Start sampling (before the warm-up: nvidia-smi needs ~0.5 s to deliver its first line)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """The timed region starts now: only samples taken from here on are reported."""
+        self.n0 = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -91,7 +100,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.n0:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -231,7 +240,7 @@ WORKLOAD_DESC = {
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", choices=["r2l", "nerf"], default="r2l")
     ap.add_argument("--precision", choices=["fp16", "bf16"], default="fp16")
@@ -269,16 +278,17 @@ def main():
 
     # ---------------- device-resident timing
     with torch.no_grad():
-        for i in range(warmup):
-            wl.step(poses_dev[i])
-        barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for i in range(warmup):
+            wl.step(poses_dev[i])
+        barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         mev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         launches0 = E._lib.launch_count
         barrier()
+        sampler.mark()
         t_wall0 = time.perf_counter()
         for i in range(steps):
             flush.zero_()                              # L2 flush, outside the event bracket

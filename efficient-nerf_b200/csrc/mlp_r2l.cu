@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8);
     mbar_init(&d_full[0], 1);
     mbar_init(&d_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
     }
   } else {
     // ===================== epilogue / encoder warpgroups =====================
-    const int wg = warp >> 2;                    // owns the 64-column groups wg and wg+2
+    const int wg = warp >> 2;                    // owns the 32-column pieces wg, wg+2, wg+4, wg+6
     const int row = (warp & 3) * 32 + lane;      // tile row == TMEM lane
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
@@ -207,27 +207,30 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       par_d ^= 1u << db;
       tc_fence_after_sync();
     };
-    // One layer's epilogue for this warp's two 64-column groups, as four 32-column pieces q (columns
-    // 64*(wg + 2*(q/2)) + 32*(q%2)), software pipelined: the TMEM load of piece q+1 is in flight while piece q is
-    // processed.  f(col0, v) consumes 32 fp32 values starting at column col0; g_done(group) runs after both
-    // pieces of a group.
-    auto for_pieces = [&](uint32_t d_col0, auto&& f, auto&& g_done) {
+    // One 256-wide layer's epilogue: this warp converts the 32-column pieces q = wg, wg+2, wg+4, wg+6 (columns
+    // 32q) of its 32 rows, software pipelined (the TMEM load of the next piece is in flight while the current one
+    // is processed).  The two warpgroups interleave, so the 64-column K-groups complete in consumption order
+    // (group q/2 after ONE piece time each) and the first MMA of the next layer waits for a single piece.
+    // f(col0, v) consumes 32 fp32 values starting at column col0; done(group) signals the piece's group.
+    auto for_pieces = [&](uint32_t d_col0, auto&& f, auto&& done) {
       uint32_t va[32], vb[32];
-      const uint32_t c0 = 64 * wg, c1 = 64 * (wg + 2);
+      const uint32_t c0 = 32 * wg;
       tmem_ld32(lane_taddr + d_col0 + c0, va);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + c0 + 32, vb);
+      tmem_ld32(lane_taddr + d_col0 + c0 + 64, vb);
       f(c0, va);
+      done(0);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + c1, va);
-      f(c0 + 32, vb);
-      g_done(wg);
+      tmem_ld32(lane_taddr + d_col0 + c0 + 128, va);
+      f(c0 + 64, vb);
+      done(1);
       tmem_ld_wait();
-      tmem_ld32(lane_taddr + d_col0 + c1 + 32, vb);
-      f(c1, va);
+      tmem_ld32(lane_taddr + d_col0 + c0 + 192, vb);
+      f(c0 + 128, va);
+      done(2);
       tmem_ld_wait();
-      f(c1 + 32, vb);
-      g_done(wg + 2);
+      f(c0 + 192, vb);
+      done(3);
     };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long ray = static_cast<long long>(tile) * kTileM + row;
@@ -283,7 +286,10 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[j]);
+          if (lane == 0) {   // a_ready counts 8 warp arrivals per phase; an encoded block comes from 4 warps
+            mbar_arrive(&a_ready[j]);
+            mbar_arrive(&a_ready[j]);
+          }
         }
       }
       if (prof) t_enc += clock64() - ce;
