@@ -190,7 +190,39 @@ merge_sort_kernel(long long n_rays, int na, int nbv, const float* __restrict__ z
       }
       if (lane == 0) z_std[ray] = static_cast<float>(sqrt(ss / nbv));
     }
-    // bitonic sort of P elements
+    // Fast path (every deterministic render, and stratified z_a): both inputs already ascending -> stable merge
+    // by rank: rank(a_i) = i + #{b < a_i}, rank(b_j) = j + #{a <= b_j} (binary searches in shared memory).
+    // The result of a values-only sort does not depend on the algorithm, so this is bit-identical to the
+    // general path below.
+    bool sorted = true;
+    for (int j = lane; j + 1 < na; j += 32) sorted = sorted && (s[j] <= s[j + 1]);
+    for (int j = lane; j + 1 < nbv; j += 32) sorted = sorted && (s[na + j] <= s[na + j + 1]);
+    if (__all_sync(0xffffffffu, sorted)) {
+      const float* a = s;
+      const float* b = s + na;
+      float* out = z_out + ray * n;
+      for (int i = lane; i < na; i += 32) {
+        const float v = a[i];
+        int lo = 0, hi = nbv;   // first index with b[idx] >= v
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (b[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        out[i + lo] = v;
+      }
+      for (int j = lane; j < nbv; j += 32) {
+        const float v = b[j];
+        int lo = 0, hi = na;    // first index with a[idx] > v
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (a[mid] <= v) lo = mid + 1; else hi = mid;
+        }
+        out[j + lo] = v;
+      }
+      __syncwarp();
+      continue;
+    }
+    // general path: bitonic sort of P elements
     for (int k = 2; k <= P; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = lane; i < P; i += 32) {

@@ -237,3 +237,12 @@ def test_merge_sorted(E):
         out, std = E.merge_sorted(a.cuda(), b.cuda(), want_std=True)
         exact(out, torch.sort(torch.cat([a, b], -1), -1)[0], f"merge {na}+{nbv}")
         close(std, torch.std(b, dim=-1, unbiased=False), 1e-6, "z_std")
+        # both inputs ascending (every deterministic render): the rank-merge fast path; with heavy ties
+        bs = torch.sort(b, -1)[0]
+        out, std = E.merge_sorted(a.cuda(), bs.cuda(), want_std=True)
+        exact(out, torch.sort(torch.cat([a, bs], -1), -1)[0], f"sorted merge {na}+{nbv}")
+        close(std, torch.std(bs, dim=-1, unbiased=False), 1e-6, "z_std sorted")
+        aq = torch.sort(torch.round(a * 4) / 4, -1)[0]
+        bq = torch.sort(torch.round(b * 4) / 4, -1)[0]
+        out, _ = E.merge_sorted(aq.cuda(), bq.cuda(), want_std=True)
+        exact(out, torch.sort(torch.cat([aq, bq], -1), -1)[0], f"tied merge {na}+{nbv}")
