@@ -5,6 +5,7 @@ Mirrors the reference's call surface:
                                 raw2outputs, sample_pdf)
   nerf_raybased              <- model/nerf_raybased.py (NeRF, ResMLP, NeRF_v3_2, PointSampler, PositionalEmbedder)
   render                     <- main.py / utils/create_data.py render glue (render, render_rays, batchify_rays, ...)
+  create_data                <- utils/create_data.py `--create_data rand` (pseudo-data shards, sharded over ranks)
 All compute goes through the C-ABI CUDA library (include/r2l_b200.h); there is no CPU fallback.
 """
 from . import _lib
@@ -12,6 +13,7 @@ from . import run_nerf_raybased_helpers
 from . import nerf_raybased
 from . import render
 from . import sharding
+from . import create_data
 from .run_nerf_raybased_helpers import (get_rays, ndc_rays, Embedder, get_embedder, raw2outputs, sample_pdf,
                                         normalize_dirs, merge_sorted)
 from .nerf_raybased import NeRF, ResMLP, NeRF_v3_2, PointSampler, PositionalEmbedder, LazyEmbedding, get_activation

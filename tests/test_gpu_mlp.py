@@ -325,3 +325,62 @@ def test_nerf_full_frame_properties(E, O):
     assert tuple(rgb.shape) == (400, 400, 3) and tuple(extras["z_std"].shape) == (400, 400)
     assert bool(torch.isfinite(rgb).all()) and float(rgb.min()) >= -1e-6 and float(rgb.max()) <= 1. + 1e-5
     assert float(acc.max()) <= 1. + 1e-5
+
+
+# ------------------------------------------------------------------ stress / larger configs
+def test_fused_kernels_are_deterministic_under_repetition(E, O):
+    """The persistent kernels synchronise through ~40 mbarriers; a protocol race would show up as run-to-run
+    differences.  Full-size launches repeated back to back must be bit-identical."""
+    sd = O.r2l_state_dict(0)
+    net = load_r2l(E, O, sd, "fp16")
+    ps = E.PointSampler(400, 400, O.LEGO["focal"], 16, 2., 6.)
+    pts = ps.sample_test(O.pose_spherical(33., -30., 4.)[:3, :4].cuda())
+    sdc, _ = O.nerf_state_dicts(0)
+    nerf = load_nerf(E, sdc, "fp16")
+    ro, rd = E.get_rays(400, 400, O.LEGO["focal"], O.pose_spherical(33., -30., 4.)[:3, :4].cuda())
+    ro, rd = ro.reshape(-1, 3)[:40000].contiguous(), rd.reshape(-1, 3)[:40000].contiguous()
+    vd = E.normalize_dirs(rd)
+    torch.manual_seed(5)
+    z = torch.sort(torch.rand(40000, 192, device="cuda") * 4 + 2, -1)[0]
+    with torch.no_grad():
+        ref = net.forward_points(pts)
+        for _ in range(30):
+            assert torch.equal(net.forward_points(pts), ref)
+        raw = nerf.forward_samples(ro, rd, vd, z)
+        for _ in range(6):
+            assert torch.equal(nerf.forward_samples(ro, rd, vd, z), raw)
+    assert bool(torch.isfinite(raw).all())
+
+
+def test_r2l_800x800_frame(E, O):
+    """BASELINE configs[3]: lego_noview_800x800 — 640 000 rays in one un-chunked forward."""
+    sd = O.r2l_state_dict(0)
+    net = load_r2l(E, O, sd, "fp16")
+    cam = O.LEGO_800
+    c2w = O.pose_spherical(120., -30., 4.)[:3, :4]
+    ps = E.PointSampler(cam["H"], cam["W"], cam["focal"], 16, 2., 6.)
+    rows = torch.arange(0, 640000, 6397)
+    with torch.no_grad():
+        rgb = E.render_r2l(net, ps, c2w.cuda())
+        ref = O.render_r2l(sd, cam["H"], cam["W"], cam["focal"], 2., 6., c2w, rows=rows)
+    assert tuple(rgb.shape) == (640000, 3) and bool(torch.isfinite(rgb).all())
+    assert maxabs(rgb[rows.cuda()], ref) <= RGB_TOL
+
+
+def test_nerf_800x800_rays_vs_oracle(E, O):
+    """BASELINE configs[3]: lego_800x800 NeRF — a strided subset of the 800x800 frame against the oracle, and the
+    whole frame for finiteness / range (640 000 rays x 192 samples in one launch)."""
+    sdc, sdf = O.nerf_state_dicts(0)
+    coarse, fine = load_nerf(E, sdc, "fp16"), load_nerf(E, sdf, "fp16")
+    cam = O.LEGO_800
+    c2w = O.pose_spherical(-60., -30., 4.)[:3, :4]
+    kw = dict(network_query_fn=None, perturb=0., N_importance=128, network_fine=fine, N_samples=64, network_fn=coarse,
+              use_viewdirs=True, white_bkgd=True, raw_noise_std=0., ndc=False, near=2., far=6.)
+    ro, rd = O.get_rays(cam["H"], cam["W"], cam["focal"], c2w)
+    idx = torch.arange(0, 640000, 10007)
+    batch = O.pack_rays(ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx], 2., 6.)
+    with torch.no_grad():
+        ref = O.render_rays(batch, sdc, sdf, 64, 128, white_bkgd=True)
+        rgb, disp, acc, extras = E.render_image(cam["H"], cam["W"], cam["focal"], chunk=32768, c2w=c2w.cuda(), **kw)
+    assert tuple(rgb.shape) == (800, 800, 3) and bool(torch.isfinite(rgb).all())
+    assert maxabs(rgb.reshape(-1, 3)[idx.cuda()], ref["rgb_map"]) <= RGB_TOL
