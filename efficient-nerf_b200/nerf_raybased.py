@@ -168,6 +168,12 @@ class NeRF(nn.Module):
         d['_packed'] = {}   # C handles are process-local; they are rebuilt on demand after unpickling
         return d
 
+    def __setstate__(self, state):
+        # also reached when a module pickled by the REFERENCE class is loaded through compat's aliases
+        self.__dict__.update(state)
+        self.__dict__.setdefault('precision', DEFAULT_PRECISION)
+        self.__dict__['_packed'] = {}
+
     # -- tensor-core path -------------------------------------------------------------------
     def supports_tensor_core_path(self):
         return (self.D == 8 and self.W == 256 and self.input_ch == 63 and self.input_ch_views == 27
@@ -383,6 +389,14 @@ class NeRF_v3_2(nn.Module):
         d = self.__dict__.copy()
         d['_packed'] = {}   # C handles are process-local; they are rebuilt on demand after unpickling
         return d
+
+    def __setstate__(self, state):
+        # also reached when a module pickled by the REFERENCE class (main.py:1534-1536) is loaded through compat
+        self.__dict__.update(state)
+        self.__dict__.setdefault('precision', DEFAULT_PRECISION)
+        self.__dict__['_packed'] = {}
+        if 'input_dim' not in self.__dict__:
+            self.__dict__['input_dim'] = self.head[0].in_features
 
     # -- tensor-core path -------------------------------------------------------------------
     def _tc_config(self):
