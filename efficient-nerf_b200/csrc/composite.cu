@@ -39,6 +39,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// CH > 0: S <= 32*CH and ALL of a ray's loads (raw as float4, z, noise) are issued before the first scan step,
+// so a warp keeps CH*640 bytes in flight instead of one 32-sample chunk; CH == 0: any S, chunk-by-chunk loads.
+template <int CH>
 __global__ void __launch_bounds__(kCompWarps * 32)
 raw2outputs_kernel(long long n_rays, int S, const float4* __restrict__ raw, const float* __restrict__ z_vals,
                    const float* __restrict__ rays_d, long long d_stride, const float* __restrict__ noise,
@@ -47,20 +50,46 @@ raw2outputs_kernel(long long n_rays, int S, const float4* __restrict__ raw, cons
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * kCompWarps + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * kCompWarps;
-  const int chunks = (S + 31) / 32;
+  const int chunks = (CH > 0) ? CH : (S + 31) / 32;
+  constexpr int NR = (CH > 0) ? CH : 1;
   for (long long ray = warp0; ray < n_rays; ray += nwarps) {
-    const float dx = rays_d[ray * d_stride], dy = rays_d[ray * d_stride + 1], dz = rays_d[ray * d_stride + 2];
-    const float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     const float4* rraw = raw + ray * S;
     const float* rz = z_vals + ray * S;
+    float4 rv_[NR];
+    float zi_[NR], nz_[NR];
+    if (CH > 0) {
+#pragma unroll
+      for (int c = 0; c < NR; ++c) {
+        const int i = c * 32 + lane;
+        rv_[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        zi_[c] = 0.f;
+        nz_[c] = 0.f;
+        if (i < S) {
+          rv_[c] = __ldg(rraw + i);
+          zi_[c] = __ldg(rz + i);
+          if (noise != nullptr) nz_[c] = __ldg(noise + ray * S + i);
+        }
+      }
+    }
+    const float dx = rays_d[ray * d_stride], dy = rays_d[ray * d_stride + 1], dz = rays_d[ray * d_stride + 2];
+    const float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     double carry = 1.0;
     float ar = 0.f, ag = 0.f, ab = 0.f, adepth = 0.f, aacc = 0.f;
+#pragma unroll
     for (int c = 0; c < chunks; ++c) {
       const int i = c * 32 + lane;
       const bool valid = i < S;
       float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
       float zi = 0.f, zn = 0.f, nz = 0.f;
-      if (valid) {
+      if (CH > 0) {
+        rv = rv_[c % NR];
+        zi = zi_[c % NR];
+        nz = nz_[c % NR];
+        // z of the next sample: the next lane's value; lane 31 takes lane 0 of the next chunk
+        zn = __shfl_down_sync(0xffffffffu, zi, 1);
+        const float z_first_next = __shfl_sync(0xffffffffu, (c + 1 < NR) ? zi_[(c + 1) % NR] : 0.f, 0);
+        if (lane == 31) zn = z_first_next;
+      } else if (valid) {
         rv = __ldg(rraw + i);
         zi = __ldg(rz + i);
         if (i + 1 < S) zn = __ldg(rz + i + 1);
@@ -142,9 +171,20 @@ int r2l_raw2outputs(long long n_rays, int S, const float* raw, const float* z_va
   long long blocks = (n_rays + kCompWarps - 1) / kCompWarps;
   const long long cap = static_cast<long long>(sm_count()) * 8;  // 8 resident 256-thread CTAs per SM
   if (blocks > cap) blocks = cap;
-  raw2outputs_kernel<<<static_cast<int>(blocks), kCompWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      n_rays, S, reinterpret_cast<const float4*>(raw), z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map,
-      disp_map, acc_map, weights, depth_map);
+  auto st = static_cast<cudaStream_t>(stream);
+  const float4* raw4 = reinterpret_cast<const float4*>(raw);
+#define R2L_LAUNCH_COMP(CH)                                                                                         \
+  raw2outputs_kernel<CH><<<static_cast<int>(blocks), kCompWarps * 32, 0, st>>>(                                     \
+      n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map, disp_map, acc_map, weights, depth_map)
+  if (S <= 64)
+    R2L_LAUNCH_COMP(2);
+  else if (S <= 128)
+    R2L_LAUNCH_COMP(4);
+  else if (S <= 192)
+    R2L_LAUNCH_COMP(6);
+  else
+    R2L_LAUNCH_COMP(0);
+#undef R2L_LAUNCH_COMP
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }
