@@ -53,6 +53,7 @@ SIGNATURES = {
     "r2l_mlp_destroy": [_c_vp],
     "r2l_mlp_status": [_c_vp, _c_vp],
     "r2l_tc_gemm_probe": [_c_int, _c_int, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_int, _c_vp],
+    "r2l_tc_gemm_probe_pair": [_c_int, _c_int, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_vp],
 }
 _RESTYPES = {"r2l_last_error": ctypes.c_char_p}
 

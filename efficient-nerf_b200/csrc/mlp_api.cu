@@ -46,8 +46,11 @@ int sm_count() {
 // Logical operand B[n][k], k in [0, Kpad): source column kmap[k] (or k when kmap == nullptr),
 // -1 / out-of-range -> 0.  Stage s holds k in [64s, 64s+64) (kStageK), k-chunk major:
 //   element offset = s*(N*64) + ((k%64)/8)*(N*8) + n*8 + (k%8)
+// pair != 0: CTA-pair layout — every stage is split into two N-halves (rows [0,N/2) for the leader CTA, then rows
+// [N/2,N) for its peer), each half k-chunk major with N/2 rows, so each CTA bulk-copies one contiguous half stage.
 __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, int N, int K_src, int Kpad,
-                                  const int* __restrict__ kmap, float scale, uint16_t* __restrict__ dst, int bf16) {
+                                  const int* __restrict__ kmap, float scale, uint16_t* __restrict__ dst, int bf16,
+                                  int pair) {
   const long long total = static_cast<long long>(N) * Kpad;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -61,7 +64,14 @@ __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, in
     else
       bits = __half_as_ushort(__float2half_rn(v));
     const int s = k / kStageK, kk = k % kStageK;
-    dst[static_cast<long long>(s) * N * kStageK + (kk >> 3) * (N * 8) + n * 8 + (kk & 7)] = bits;
+    const int kst = (Kpad - s * kStageK < kStageK) ? (Kpad - s * kStageK) : kStageK;   // K columns in this stage
+    if (pair) {
+      const int Nh = N / 2, h = n / Nh, nn = n % Nh;
+      dst[static_cast<long long>(s) * N * kStageK + static_cast<long long>(h) * Nh * kst + (kk >> 3) * (Nh * 8) + nn * 8 +
+          (kk & 7)] = bits;
+    } else {
+      dst[static_cast<long long>(s) * N * kStageK + (kk >> 3) * (N * 8) + n * 8 + (kk & 7)] = bits;
+    }
   }
 }
 
@@ -127,7 +137,8 @@ static int alloc_debug(Mlp* m) {
 }
 
 static int pack_layer(const float* W, long long ldw, int N, int K_src, int Kpad, const std::vector<int>* kmap,
-                      float scale, uint16_t* dst, bool bf16, cudaStream_t st, std::vector<int*>& scratch) {
+                      float scale, uint16_t* dst, bool bf16, cudaStream_t st, std::vector<int*>& scratch,
+                      bool pair = false) {
   int* d_kmap = nullptr;
   if (kmap != nullptr) {
     R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_kmap), sizeof(int) * Kpad));
@@ -136,7 +147,7 @@ static int pack_layer(const float* W, long long ldw, int N, int K_src, int Kpad,
   }
   const long long total = static_cast<long long>(N) * Kpad;
   const int blocks = static_cast<int>((total + 255) / 256);
-  pack_layer_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K_src, Kpad, d_kmap, scale, dst, bf16 ? 1 : 0);
+  pack_layer_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K_src, Kpad, d_kmap, scale, dst, bf16 ? 1 : 0, pair ? 1 : 0);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }
@@ -242,6 +253,98 @@ gemm_probe_kernel(const float* __restrict__ A, int K, const uint16_t* __restrict
   (void)lane;
 }
 
+// CTA-pair probe: D[256, N] = A[256, K] * B[N, K]^T with tcgen05.mma.cta_group::2.  Two CTAs (one cluster): CTA r
+// holds A rows [128r, 128r+128) and the N-half r of B; the leader issues the MMAs, both read their own 128 D rows.
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+gemm_probe_pair_kernel(const float* __restrict__ A, int K, const uint16_t* __restrict__ Bpacked, int N,
+                       float* __restrict__ D, DebugBuf* dbg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int Nh = N / 2;
+  uint8_t* sA = smem;                                  // 128 x K 16-bit, chunk major
+  uint8_t* sB = smem + kTileM * K * 2;                 // Nh x K 16-bit: this CTA's half of every stage
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Nh * K * 2);   // [0] B landed (local), [1] done, [2] peer ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int row = threadIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc_pair(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  for (int ch = 0; ch < K / 8; ++ch) {
+    const float* a = A + (static_cast<long long>(rank) * kTileM + row) * K + ch * 8;
+    uint4 q;
+    q.x = pack2<BF16>(a[0], a[1]);
+    q.y = pack2<BF16>(a[2], a[3]);
+    q.z = pack2<BF16>(a[4], a[5]);
+    q.w = pack2<BF16>(a[6], a[7]);
+    *reinterpret_cast<uint4*>(sA + ch * kChunkBytes + row * 16) = q;
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  const int n_stages = (K + kStageK - 1) / kStageK;
+  if (threadIdx.x == 0) {
+    // this CTA's half of every stage (a partial last stage holds K % 64 columns)
+    mbar_expect_tx(&bars[0], static_cast<uint32_t>(Nh) * K * 2);
+    for (int s = 0; s < n_stages; ++s) {
+      const int kst = (K - s * kStageK < kStageK) ? (K - s * kStageK) : kStageK;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(Bpacked) + static_cast<size_t>(s) * N * kStageK * 2 +
+                           static_cast<size_t>(rank) * Nh * kst * 2;
+      bulk_g2s(sB + static_cast<size_t>(s) * Nh * kStageK * 2, src, static_cast<uint32_t>(Nh) * kst * 2, &bars[0]);
+    }
+    mbar_wait(&bars[0], 0, dbg, 1);
+    if (rank == 1) {
+      mbar_arrive_cluster(mapa_u32(&bars[2], 0));      // tell the leader: my A and B halves are in place
+    } else {
+      while (!mbar_try_wait_cluster(&bars[2], 0)) {}
+      tc_fence_after_sync();
+      const uint32_t idesc = make_idesc_f16(BF16, 2 * kTileM, N);
+      const uint32_t lbo_b = static_cast<uint32_t>(Nh) * 16;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const int s = ks / 4, j = ks % 4;
+        const uint32_t a_addr = smem_u32(sA) + ks * 2 * kChunkBytes;
+        const uint32_t b_addr = smem_u32(sB) + s * (static_cast<uint32_t>(Nh) * kStageK * 2) + j * 2 * lbo_b;
+        umma_f16_ss_pair(tmem_base, make_smem_desc(a_addr, kLboA, kSbo), make_smem_desc(b_addr, lbo_b, kSbo), idesc,
+                         ks != 0 ? 1u : 0u);
+      }
+      umma_commit_pair(&bars[1]);
+    }
+  }
+  __syncwarp();
+  {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(&bars[1], 0)) {
+      if (++spins > R2L_WATCHDOG_SPINS) __trap();
+    }
+  }
+  tc_fence_after_sync();
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c = 0; c < N; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(lane_taddr + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      D[(static_cast<long long>(rank) * kTileM + row) * N + c + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem_base, 256);
+  }
+}
+
 }  // namespace r2l
 
 using namespace r2l;
@@ -290,6 +393,48 @@ int r2l_tc_gemm_probe(int dtype, int N, int K, const float* A, const float* W, f
       rc = fail(R2L_ERR_CUDA, "r2l_tc_gemm_probe: %s (watchdog flag=%u barrier=%u)", cudaGetErrorString(e),
                 dbg_host ? dbg_host->flag : 0u, dbg_host ? dbg_host->barrier_id : 0u);
     }
+  }
+  if (dbg_host) cudaFreeHost(dbg_host);
+  cudaFree(packed);
+  return rc;
+}
+
+// CTA-pair variant of the probe: D [256, N] = A [256, K] x W [N, K]^T on tcgen05.mma.cta_group::2 (one cluster of two
+// CTAs).  K multiple of 32, <= 256; N multiple of 64, 64..256.
+int r2l_tc_gemm_probe_pair(int dtype, int N, int K, const float* A, const float* W, float* D, void* stream) {
+  R2L_CHECK_ARG(dtype == 0 || dtype == 1, "r2l_tc_gemm_probe_pair: dtype must be 0 (fp16) or 1 (bf16)");
+  R2L_CHECK_ARG(N >= 64 && N <= 256 && N % 64 == 0, "r2l_tc_gemm_probe_pair: N must be a multiple of 64 in [64,256]");
+  R2L_CHECK_ARG(K >= 32 && K <= 256 && K % 32 == 0, "r2l_tc_gemm_probe_pair: bad K");
+  R2L_CHECK_ARG(A && W && D, "r2l_tc_gemm_probe_pair: null pointer");
+  auto st = static_cast<cudaStream_t>(stream);
+  uint16_t* packed = nullptr;
+  R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&packed), static_cast<size_t>(N) * K * 2));
+  std::vector<int*> scratch;
+  int rc = pack_layer(W, K, N, K, K, nullptr, 1.0f, packed, dtype == 1, st, scratch, /*pair=*/true);
+  DebugBuf* dbg_host = nullptr;
+  DebugBuf* dbg_dev = nullptr;
+  if (rc == R2L_OK) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&dbg_host), sizeof(DebugBuf), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&dbg_dev), dbg_host, 0) != cudaSuccess)
+      rc = fail(R2L_ERR_CUDA, "r2l_tc_gemm_probe_pair: debug buffer allocation failed");
+    else
+      memset(dbg_host, 0, sizeof(DebugBuf));
+  }
+  if (rc == R2L_OK) {
+    const int smem = kTileM * K * 2 + (N / 2) * K * 2 + 64;
+    cudaError_t e;
+    if (dtype == 1) {
+      e = cudaFuncSetAttribute(gemm_probe_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) gemm_probe_pair_kernel<true><<<2, 128, smem, st>>>(A, K, packed, N, D, dbg_dev);
+    } else {
+      e = cudaFuncSetAttribute(gemm_probe_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) gemm_probe_pair_kernel<false><<<2, 128, smem, st>>>(A, K, packed, N, D, dbg_dev);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+      rc = fail(R2L_ERR_CUDA, "r2l_tc_gemm_probe_pair: %s (watchdog flag=%u barrier=%u)", cudaGetErrorString(e),
+                dbg_host ? dbg_host->flag : 0u, dbg_host ? dbg_host->barrier_id : 0u);
   }
   if (dbg_host) cudaFreeHost(dbg_host);
   cudaFree(packed);

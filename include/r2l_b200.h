@@ -154,6 +154,9 @@ int r2l_mlp_status(void* handle, unsigned int* out8);
 int r2l_tc_gemm_probe(int dtype, int N, int K, const float* A, const float* W, float* D, int swap_lbo_sbo,
                       void* stream);
 
+/* Unit-test probe of the CTA-pair path: D [256,N] = A [256,K] x W [N,K]^T on tcgen05.mma.cta_group::2. */
+int r2l_tc_gemm_probe_pair(int dtype, int N, int K, const float* A, const float* W, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

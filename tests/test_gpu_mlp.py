@@ -49,6 +49,22 @@ def test_tcgen05_gemm_probe(E, dtype, N, K):
     assert err < 1e-3 * K**0.5, f"probe N={N} K={K} dtype={dtype}: max err {err}"
 
 
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (128, 256), (128, 32), (64, 96)])
+def test_tcgen05_gemm_probe_cta_pair(E, dtype, N, K):
+    """tcgen05.mma.cta_group::2: M = 256 over two CTAs, each supplying its A rows and one N-half of B."""
+    torch.manual_seed(N * 3 + K)
+    A = torch.randn(256, K, device="cuda")
+    W = torch.randn(N, K, device="cuda")
+    D = torch.full((256, N), float("nan"), device="cuda")
+    E._lib.call("r2l_tc_gemm_probe_pair", dtype, N, K, E._lib.ptr(A), E._lib.ptr(W), E._lib.ptr(D), E._lib.stream_ptr())
+    torch.cuda.synchronize()
+    cast = torch.bfloat16 if dtype == 1 else torch.float16
+    ref = A.to(cast).double() @ W.to(cast).double().t()
+    err = float((D.double() - ref).abs().max())
+    assert err < 1e-3 * K**0.5, f"pair probe N={N} K={K} dtype={dtype}: max err {err}"
+
+
 def test_linear_fp32(E):
     from efficient_nerf_b200.nerf_raybased import _linear_fp32
     torch.manual_seed(0)
