@@ -2,6 +2,7 @@
 // 16-bit K-chunk-major stage stream), model handles, forward entry points and a minimal
 // tcgen05 GEMM probe used by the GPU unit tests.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -89,12 +90,17 @@ __device__ __forceinline__ uint16_t bias_part(float b, int part, int bf16) {
 // Bias step of a layer: one K=16 stage [N x 16] whose k=0 / k=1 columns hold the hi / lo split of scale*bias
 // (the matching A operand is the constant ones block), all other columns zero.
 __global__ void pack_bias_kernel(const float* __restrict__ bias, int N, float scale, uint16_t* __restrict__ dst,
-                                 int bf16) {
+                                 int bf16, int pair) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * 16) return;
   const int n = idx / 16, k = idx % 16;
   const uint16_t bits = (k < 2) ? bias_part(bias[n] * scale, k, bf16) : static_cast<uint16_t>(0);
-  dst[(k >> 3) * (N * 8) + n * 8 + (k & 7)] = bits;
+  if (pair) {   // two N-halves, each k-chunk major with N/2 rows (see pack_layer_kernel)
+    const int Nh = N / 2, h = n / Nh, nn = n % Nh;
+    dst[h * (Nh * 16) + (k >> 3) * (Nh * 8) + nn * 8 + (k & 7)] = bits;
+  } else {
+    dst[(k >> 3) * (N * 8) + n * 8 + (k & 7)] = bits;
+  }
 }
 
 // View stage of the NeRF view branch: [128 x 32], k < 27 -> views_w[n][256 + k] (embedded view direction),
@@ -117,6 +123,7 @@ __global__ void pack_view_stage_kernel(const float* __restrict__ views_w, long l
 struct Mlp {
   int kind = 0;  // 0 = NeRF, 1 = R2L ResMLP
   bool bf16 = false;
+  bool pair = false;   // weights packed for / kernels launched in CTA-pair mode (tcgen05.mma.cta_group::2)
   uint8_t* wstream = nullptr;
   size_t wbytes = 0;
   float* aux = nullptr;
@@ -128,6 +135,15 @@ struct Mlp {
   int n_points = 0, n_blocks = 0, sigmoid_out = 1, outer_skip = 1;
   float b_tail[3] = {0.f, 0.f, 0.f};
 };
+
+// R2L_PAIR=1 selects the CTA-pair kernel (tcgen05.mma.cta_group::2, half the L2 -> shared-memory weight traffic);
+// measured equal in throughput to the single-CTA kernel under the power cap (1.677 ms vs 1.678 ms per R2L frame,
+// 1.74 GHz vs 1.65 GHz), so the single-CTA kernel stays the default until the pair kernel's spare shared memory is
+// used to overlap the epilogue.
+static bool pair_mode_default() {
+  const char* e = getenv("R2L_PAIR");
+  return e != nullptr && e[0] == '1';
+}
 
 static int alloc_debug(Mlp* m) {
   R2L_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->dbg_host), sizeof(DebugBuf), cudaHostAllocMapped));
@@ -152,8 +168,9 @@ static int pack_layer(const float* W, long long ldw, int N, int K_src, int Kpad,
   return R2L_OK;
 }
 
-static int pack_bias(const float* bias, int N, float scale, uint16_t* dst, bool bf16, cudaStream_t st) {
-  pack_bias_kernel<<<(N * 16 + 255) / 256, 256, 0, st>>>(bias, N, scale, dst, bf16 ? 1 : 0);
+static int pack_bias(const float* bias, int N, float scale, uint16_t* dst, bool bf16, cudaStream_t st,
+                     bool pair = false) {
+  pack_bias_kernel<<<(N * 16 + 255) / 256, 256, 0, st>>>(bias, N, scale, dst, bf16 ? 1 : 0, pair ? 1 : 0);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }
@@ -633,6 +650,7 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
   Mlp* m = new Mlp();
   m->kind = 1;
   m->bf16 = dtype == 1;
+  m->pair = pair_mode_default();
   m->n_points = n_points;
   m->n_blocks = n_blocks;
   m->sigmoid_out = sigmoid_out;
@@ -670,26 +688,27 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
   }
   uint16_t* dst = reinterpret_cast<uint16_t*>(m->wstream);
   size_t off = 0;
-  rc = pack_bias(head_b, 256, 1.0f, dst + off, m->bf16, st);
+  const bool pr = m->pair;
+  rc = pack_bias(head_b, 256, 1.0f, dst + off, m->bf16, st, pr);
   off += 256ull * 16;
   if (rc == R2L_OK)
     rc = pack_layer(head_w, static_cast<long long>(n_points) * 63, 256, n_points * 63, K_head, &kmap, 1.0f, dst + off,
-                    m->bf16, st, scratch);
+                    m->bf16, st, scratch, pr);
   off += 256ull * K_head;
   for (int b = 0; b < n_blocks && rc == R2L_OK; ++b) {
     if (!(w1[b] && b1[b] && w2[b] && b2[b])) {
       rc = fail(R2L_ERR_INVALID, "r2l_resmlp_create: null block %d", b);
       break;
     }
-    rc = pack_bias(b1[b], 256, 1.0f, dst + off, m->bf16, st);
+    rc = pack_bias(b1[b], 256, 1.0f, dst + off, m->bf16, st, pr);
     off += 256ull * 16;
-    if (rc == R2L_OK) rc = pack_layer(w1[b], 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch);
+    if (rc == R2L_OK) rc = pack_layer(w1[b], 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch, pr);
     off += 256ull * 256;
-    if (rc == R2L_OK) rc = pack_bias(b2[b], 256, static_cast<float>(res_scale), dst + off, m->bf16, st);
+    if (rc == R2L_OK) rc = pack_bias(b2[b], 256, static_cast<float>(res_scale), dst + off, m->bf16, st, pr);
     off += 256ull * 16;
     if (rc == R2L_OK)
       rc = pack_layer(w2[b], 256, 256, 256, 256, nullptr, static_cast<float>(res_scale), dst + off, m->bf16, st,
-                      scratch);
+                      scratch, pr);
     off += 256ull * 256;
   }
   if (rc != R2L_OK) return cleanup(rc);
@@ -726,8 +745,15 @@ static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_
   p.dbg_head_x0 = dbg_x0;
   (void)dbg_a;
   p.prof = prof;
-  const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  return r2l_mlp_launch(m->bf16, p, grid, st);
+  int grid;
+  if (m->pair) {
+    const long long n_units = (n_tiles + 1) / 2;
+    const long long max_pairs = sm_count() / 2;
+    grid = static_cast<int>(2 * (n_units < max_pairs ? n_units : max_pairs));
+  } else {
+    grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  }
+  return r2l_mlp_launch(m->bf16, m->pair, p, grid, st);
 }
 
 // Fused PositionalEmbedder + NeRF_v3_2 on sampled points: pts [n_rays, n_points*3] -> rgb [n_rays, 3].

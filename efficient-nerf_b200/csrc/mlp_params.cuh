@@ -50,6 +50,6 @@ struct R2lParams {
 };
 
 int nerf_mlp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st);
-int r2l_mlp_launch(bool bf16, const R2lParams& p, int grid, cudaStream_t st);
+int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, int grid, cudaStream_t st);
 
 }  // namespace r2l

@@ -24,23 +24,35 @@ namespace r2l {
 constexpr int kR2lThreads = 320;
 constexpr int kR2lProducerWarp = 8;
 constexpr int kR2lMmaWarp = 9;
-constexpr int kR2lRing = 4;       // 32 KiB weight stages (K = 64)
-constexpr int kR2lBiasRing = 2;   // 8 KiB bias stages
+// The weight ring holds 128 KiB: 4 stages of 32 KiB, or (CTA pair: each CTA keeps its N-half) 8 half stages of 16 KiB.
+constexpr int kR2lRingBytes = 4 * kStageBytes;
+constexpr int kR2lBiasRingBytes = 2 * kBiasStageBytes;   // 2 bias stages of 8 KiB, or 4 halves of 4 KiB
+constexpr int kR2lMaxRing = 8, kR2lMaxBiasRing = 4;
 constexpr int kR2lOffA = 0;
 constexpr int kR2lOffOnes = kR2lOffA + kABufBytes;
 constexpr int kR2lOffRing = kR2lOffOnes + kOnesBytes;
-constexpr int kR2lOffBiasRing = kR2lOffRing + kR2lRing * kStageBytes;
-constexpr int kR2lOffWt = kR2lOffBiasRing + kR2lBiasRing * kBiasStageBytes;   // 3*256 floats
-constexpr int kR2lOffPart = kR2lOffWt + 768 * 4;                              // 128*4 floats
+constexpr int kR2lOffBiasRing = kR2lOffRing + kR2lRingBytes;
+constexpr int kR2lOffWt = kR2lOffBiasRing + kR2lBiasRingBytes;   // 3*256 floats
+constexpr int kR2lOffPart = kR2lOffWt + 768 * 4;                 // 128*4 floats
 constexpr int kR2lOffBars = kR2lOffPart + 128 * 4 * 4;
-constexpr int kR2lNumBars = 2 * kR2lRing + 2 * kR2lBiasRing + 4 + 2 + 4 + 1;
+constexpr int kR2lNumBars = 2 * kR2lMaxRing + 2 * kR2lMaxBiasRing + 4 + 2 + 4 + 1;
 constexpr int kR2lOffTmem = kR2lOffBars + kR2lNumBars * 8;
 constexpr int kR2lSmemBytes = kR2lOffTmem + 16;
 static_assert(kR2lSmemBytes <= 227 * 1024, "R2L kernel shared memory exceeds 227 KiB");
 static_assert(kR2lOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
 
-template <bool BF16>
+// PAIR = true: two CTAs of one cluster (a TPC's SM pair) work on two 128-ray tiles with tcgen05.mma.cta_group::2
+// (M = 256): each CTA streams only ITS N-half of every weight stage (half the L2 -> shared-memory traffic and half
+// the B-operand shared-memory reads per SM), the leader CTA's MMA thread issues for both, and all "operand ready"
+// barriers live in the leader and collect the warps of both CTAs; MMA completion is multicast to both.
+template <bool BF16, bool PAIR>
 __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams p) {
+  constexpr int kRing = PAIR ? 8 : 4;
+  constexpr int kBiasRing = PAIR ? 4 : 2;
+  constexpr uint32_t kStageB = PAIR ? kStageBytes / 2 : kStageBytes;          // bytes of a stage held by THIS CTA
+  constexpr uint32_t kBiasB = PAIR ? kBiasStageBytes / 2 : kBiasStageBytes;
+  constexpr uint32_t kLboB = (PAIR ? 128 : 256) * 16;
+  constexpr int kCtas = PAIR ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const sA = smem + kR2lOffA;
   uint8_t* const sOnes = smem + kR2lOffOnes;
@@ -50,10 +62,10 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
   float* const sPart = reinterpret_cast<float*>(smem + kR2lOffPart);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kR2lOffBars);
   uint64_t* const w_full = bars;
-  uint64_t* const w_empty = bars + kR2lRing;
-  uint64_t* const b_full = bars + 2 * kR2lRing;
-  uint64_t* const b_empty = b_full + kR2lBiasRing;
-  uint64_t* const a_ready = b_empty + kR2lBiasRing;   // [64-column group 0..3]
+  uint64_t* const w_empty = bars + kR2lMaxRing;
+  uint64_t* const b_full = bars + 2 * kR2lMaxRing;
+  uint64_t* const b_empty = b_full + kR2lMaxBiasRing;
+  uint64_t* const a_ready = b_empty + kR2lMaxBiasRing;   // [64-column group 0..3]
   uint64_t* const d_full = a_ready + 4;            // [0] = D1 (cols 0..255), [1] = D2 (cols 256..511)
   uint64_t* const a_free = d_full + 2;             // [block 0..3]: head MMAs finished reading block j of A
   uint64_t* const drained = a_free + 4;            // all 8 epilogue warps have read the tile's final accumulator (D2)
@@ -63,55 +75,66 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
   const int lane = threadIdx.x & 31;
   const int n_chunks = p.n_points / 4;
   const int nb = p.n_blocks;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs)
+  // work units: one tile per CTA; a pair takes tiles 2u and 2u+1 of unit u
+  const int n_units = PAIR ? (p.n_tiles + 1) / 2 : p.n_tiles;
+  const int unit0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kR2lRing; ++i) {
-      mbar_init(&w_full[i], 1);
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&w_full[i], (PAIR && rank == 0) ? 2 : 1);   // leader: own producer + the peer's relay
       mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < kR2lBiasRing; ++i) {
-      mbar_init(&b_full[i], 1);
+    for (int i = 0; i < kBiasRing; ++i) {
+      mbar_init(&b_full[i], (PAIR && rank == 0) ? 2 : 1);
       mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8 * kCtas);
     mbar_init(&d_full[0], 1);
     mbar_init(&d_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
-    mbar_init(drained, 8);
+    mbar_init(drained, 8 * kCtas);
     mbar_fence_init();
   }
   write_ones_block<BF16>(sOnes, threadIdx.x, kR2lThreads);
   for (int i = threadIdx.x; i < 768; i += kR2lThreads) sWt[i] = p.w_tail[i];
   fence_proxy_async_smem();
-  if (warp == kR2lMmaWarp) tmem_alloc(tmem_slot, 512);
+  if (warp == kR2lMmaWarp) {
+    if (PAIR)
+      tmem_alloc_pair(tmem_slot, 512);
+    else
+      tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before_sync();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anybody signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kR2lProducerWarp) {
-    // ===================== weight producer =====================
+    // ===================== weight producer (every CTA streams its own half in PAIR mode) =====================
     if (lane == 0) {
       uint32_t g = 0, gb = 0;
       const uint8_t* src = nullptr;
       auto push = [&]() {
-        const uint32_t slot = g % kR2lRing;
-        mbar_wait(&w_empty[slot], ((g / kR2lRing) & 1) ^ 1, p.dbg, 100 + slot);
-        mbar_expect_tx(&w_full[slot], kStageBytes);
-        bulk_g2s(sRing + slot * kStageBytes, src, kStageBytes, &w_full[slot]);
+        const uint32_t slot = g % kRing;
+        mbar_wait_x<PAIR>(&w_empty[slot], ((g / kRing) & 1) ^ 1, p.dbg, 100 + slot);
+        mbar_expect_tx(&w_full[slot], kStageB);
+        bulk_g2s(sRing + slot * kStageB, src + rank * kStageB, kStageB, &w_full[slot]);
         src += kStageBytes;
         ++g;
       };
       auto push_bias = [&]() {
-        const uint32_t slot = gb % kR2lBiasRing;
-        mbar_wait(&b_empty[slot], ((gb / kR2lBiasRing) & 1) ^ 1, p.dbg, 120 + slot);
-        mbar_expect_tx(&b_full[slot], kBiasStageBytes);
-        bulk_g2s(sBiasRing + slot * kBiasStageBytes, src, kBiasStageBytes, &b_full[slot]);
+        const uint32_t slot = gb % kBiasRing;
+        mbar_wait_x<PAIR>(&b_empty[slot], ((gb / kBiasRing) & 1) ^ 1, p.dbg, 120 + slot);
+        mbar_expect_tx(&b_full[slot], kBiasB);
+        bulk_g2s(sBiasRing + slot * kBiasB, src + rank * kBiasB, kBiasB, &b_full[slot]);
         src += kBiasStageBytes;
         ++gb;
       };
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
         src = p.wstream;
         push_bias();
         for (int i = 0; i < n_chunks * 4; ++i) push();
@@ -122,9 +145,35 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       }
     }
   } else if (warp == kR2lMmaWarp) {
-    // ===================== MMA issuer =====================
+    if (PAIR && rank != 0) {
+      // ===================== peer CTA: relay "my half stage has landed" to the leader's barriers =====================
+      if (lane == 0) {
+        uint32_t g = 0, gb = 0;
+        auto relay = [&]() {
+          const uint32_t slot = g % kRing;
+          mbar_wait(&w_full[slot], (g / kRing) & 1, p.dbg, 150 + slot);
+          mbar_arrive_cluster(mapa_u32(&w_full[slot], 0));
+          ++g;
+        };
+        auto relay_bias = [&]() {
+          const uint32_t slot = gb % kBiasRing;
+          mbar_wait(&b_full[slot], (gb / kBiasRing) & 1, p.dbg, 170 + slot);
+          mbar_arrive_cluster(mapa_u32(&b_full[slot], 0));
+          ++gb;
+        };
+        for (int unit = unit0; unit < n_units; unit += unit_step) {
+          relay_bias();
+          for (int i = 0; i < n_chunks * 4; ++i) relay();
+          for (int l = 0; l < 2 * nb; ++l) {
+            relay_bias();
+            for (int i = 0; i < 4; ++i) relay();
+          }
+        }
+      }
+    } else
+    // ===================== MMA issuer (leader CTA) =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(BF16, kTileM, 256);
+      const uint32_t idesc = make_idesc_f16(BF16, kCtas * kTileM, 256);
       const uint32_t aA = smem_u32(sA);
       const uint32_t aOnes = smem_u32(sOnes);
       const uint32_t aRing = smem_u32(sRing);
@@ -137,49 +186,49 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       const long long t_start = prof ? clock64() : 0;
       // the K=16 bias step of a layer (needs no activations)
       auto bias_step = [&](uint32_t d_tmem, bool fresh) {
-        const uint32_t slot = gb % kR2lBiasRing;
+        const uint32_t slot = gb % kBiasRing;
         const long long c0 = prof ? clock64() : 0;
-        mbar_wait(&b_full[slot], (gb / kR2lBiasRing) & 1, p.dbg, 240 + slot);
+        mbar_wait_x<PAIR>(&b_full[slot], (gb / kBiasRing) & 1, p.dbg, 240 + slot);
         if (prof) t_w += clock64() - c0;
         tc_fence_after_sync();
-        issue_bias_stage(d_tmem, aOnes, aBiasRing + slot * kBiasStageBytes, 256 * 16, idesc, fresh);
-        umma_commit(&b_empty[slot]);
+        issue_bias_stage<PAIR>(d_tmem, aOnes, aBiasRing + slot * kBiasB, kLboB, idesc, fresh);
+        umma_commit_x<PAIR>(&b_empty[slot]);
         ++gb;
       };
       // 4 stages (K = 256) of A accumulated into d_tmem; `free_blocks`: release A blocks to the head encoders
       auto run4 = [&](uint32_t d_tmem, bool free_blocks) {
         for (int st = 0; st < 4; ++st) {
-          const uint32_t slot = g % kR2lRing;
+          const uint32_t slot = g % kRing;
           const long long c0 = prof ? clock64() : 0;
-          mbar_wait2(&a_ready[st], par_a, &w_full[slot], (g / kR2lRing) & 1, p.dbg, 210 + st);
+          mbar_wait2<PAIR>(&a_ready[st], par_a, &w_full[slot], (g / kRing) & 1, p.dbg, 210 + st);
           if (prof) t_a += clock64() - c0;
           tc_fence_after_sync();
-          issue_stage<4>(d_tmem, aA + st * kGroupBytes, aRing + slot * kStageBytes, 256 * 16, idesc, false);
-          umma_commit(&w_empty[slot]);
-          if (free_blocks) umma_commit(&a_free[st]);
+          issue_stage<4, PAIR>(d_tmem, aA + st * kGroupBytes, aRing + slot * kStageB, kLboB, idesc, false);
+          umma_commit_x<PAIR>(&w_empty[slot]);
+          if (free_blocks) umma_commit_x<PAIR>(&a_free[st]);
           ++g;
         }
         par_a ^= 1u;
       };
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
         // head accumulates in D2; W1 of block 0 then writes D1 (consecutive layers never share a TMEM buffer).
         // The previous tile's last epilogue reads D2 without handing anything back through a_ready, so the
         // first (overwriting) MMA of this tile waits until all epilogue warps have drained it.
         if (it > 0) {
-          mbar_wait(drained, (it - 1) & 1u, p.dbg, 250);
+          mbar_wait_x<PAIR>(drained, (it - 1) & 1u, p.dbg, 250);
           tc_fence_after_sync();
         }
         bias_step(d2, true);
         for (int c = 0; c < n_chunks; ++c) run4(d2, c + 1 < n_chunks);
-        umma_commit(&d_full[1]);
+        umma_commit_x<PAIR>(&d_full[1]);
         for (int b = 0; b < nb; ++b) {
           bias_step(d1, true);
           run4(d1, false);
-          umma_commit(&d_full[0]);
+          umma_commit_x<PAIR>(&d_full[0]);
           bias_step(d2, false);   // accumulate onto the fp32 residual stream
           run4(d2, false);
-          umma_commit(&d_full[1]);
+          umma_commit_x<PAIR>(&d_full[1]);
         }
       }
       if (prof) {
@@ -202,7 +251,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
     uint8_t* const a_row = sA + row * 16;
     auto wait_d = [&](int db, uint32_t id) {
       const long long cd = prof ? clock64() : 0;
-      mbar_wait(&d_full[db], (par_d >> db) & 1u, p.dbg, id);
+      mbar_wait_x<PAIR>(&d_full[db], (par_d >> db) & 1u, p.dbg, id);
       if (prof) t_d += clock64() - cd;
       par_d ^= 1u << db;
       tc_fence_after_sync();
@@ -232,7 +281,8 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       f(c0 + 192, vb);
       done(3);
     };
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int tile = PAIR ? (2 * unit + static_cast<int>(rank)) : unit;   // may be == n_tiles for the peer: rows clamp
       const long long ray = static_cast<long long>(tile) * kTileM + row;
       const bool valid = ray < p.n_rays;
       const long long ray_c = valid ? ray : (p.n_rays - 1);
@@ -252,7 +302,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
             pz = __ldg(prow + 3 * pt + 2);
           }
           if (c > 0) {
-            mbar_wait(&a_free[j], (par_free >> j) & 1u, p.dbg, 400 + j);
+            mbar_wait_x<PAIR>(&a_free[j], (par_free >> j) & 1u, p.dbg, 400 + j);
             par_free ^= 1u << j;
           }
           uint8_t* blk = sA + j * 8 * kChunkBytes;
@@ -286,10 +336,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {   // a_ready counts 8 warp arrivals per phase; an encoded block comes from 4 warps
-            mbar_arrive(&a_ready[j]);
-            mbar_arrive(&a_ready[j]);
-          }
+          if (lane == 0) lane_arrive<PAIR>(&a_ready[j], 2);   // 8 arrivals per CTA and phase; a block comes from 4 warps
         }
       }
       if (prof) t_enc += clock64() - ce;
@@ -320,7 +367,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           },
           [&](int g) {
             tmem_st_wait();
-            warp_arrive(&a_ready[g], lane);
+            warp_arrive<PAIR>(&a_ready[g], lane);
           });
       // ---- body
       for (int b = 0; b < nb; ++b) {
@@ -328,13 +375,13 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
         wait_d(0, 310);
         for_pieces(
             0, [&](uint32_t col0, uint32_t (&v)[32]) { store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes); },
-            [&](int g) { warp_arrive(&a_ready[g], lane); });
+            [&](int g) { warp_arrive<PAIR>(&a_ready[g], lane); });
         // W2: x = D2 -> A   (last block: tail partials instead)
         wait_d(1, 320);
         if (b + 1 < nb) {
           for_pieces(
               256, [&](uint32_t col0, uint32_t (&v)[32]) { store_sub<BF16, false>(v, a_row + (col0 >> 5) * kSubBytes); },
-              [&](int g) { warp_arrive(&a_ready[g], lane); });
+              [&](int g) { warp_arrive<PAIR>(&a_ready[g], lane); });
         } else {
           for_pieces(
               256,
@@ -350,7 +397,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
               [&](int) {});
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(drained);
+          if (lane == 0) lane_arrive<PAIR>(drained);
         }
       }
       // ---- tail: combine the two column sets, bias, sigmoid
@@ -389,22 +436,40 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
   // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs are done with their TMEM and with each other's barriers
   if (warp == kR2lMmaWarp) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR)
+      tmem_dealloc_pair(tmem_base, 512);
+    else
+      tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <bool BF16>
+template <bool BF16, bool PAIR>
 int launch_r2l(const R2lParams& p, int grid, cudaStream_t st) {
-  R2L_CUDA(cudaFuncSetAttribute(r2l_mlp_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR2lSmemBytes));
-  r2l_mlp_kernel<BF16><<<grid, kR2lThreads, kR2lSmemBytes, st>>>(p);
-  R2L_LAUNCH_CHECK();
+  R2L_CUDA(cudaFuncSetAttribute(r2l_mlp_kernel<BF16, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kR2lSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kR2lThreads);
+  cfg.dynamicSmemBytes = kR2lSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, r2l_mlp_kernel<BF16, PAIR>, p));
   return R2L_OK;
 }
 
-int r2l_mlp_launch(bool bf16, const R2lParams& p, int grid, cudaStream_t st) {
-  return bf16 ? launch_r2l<true>(p, grid, st) : launch_r2l<false>(p, grid, st);
+// pair: CTA-pair mode (the weights must have been packed in the pair layout); grid is then a multiple of 2
+int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, int grid, cudaStream_t st) {
+  if (pair) return bf16 ? launch_r2l<true, true>(p, grid, st) : launch_r2l<false, true>(p, grid, st);
+  return bf16 ? launch_r2l<true, false>(p, grid, st) : launch_r2l<false, false>(p, grid, st);
 }
 
 }  // namespace r2l

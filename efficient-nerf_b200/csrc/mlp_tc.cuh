@@ -82,11 +82,34 @@ __device__ __forceinline__ void store_sub(const uint32_t (&v)[32], uint8_t* a_gr
 // "My warp's part of this operand group is written": make the generic-proxy stores visible to the async
 // proxy (UMMA reads shared memory through it), order this warp's TMEM accesses before the signal, then ONE
 // lane arrives (barrier count = number of warps, not threads).
+// PAIR: the barrier lives in the LEADER CTA of the pair (rank 0) and collects the warps of both CTAs.
+template <bool PAIR = false>
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
+  if (lane == 0) {
+    if (PAIR && cluster_ctarank() != 0)
+      mbar_arrive_cluster(mapa_u32(bar, 0));
+    else
+      mbar_arrive(bar);
+  }
+}
+// plain (no fences) one-lane arrival, `times` arrivals
+template <bool PAIR = false>
+__device__ __forceinline__ void lane_arrive(uint64_t* bar, int times = 1) {
+  if (PAIR && cluster_ctarank() != 0) {
+    const uint32_t a = mapa_u32(bar, 0);
+    for (int i = 0; i < times; ++i) mbar_arrive_cluster(a);
+  } else {
+    for (int i = 0; i < times; ++i) mbar_arrive(bar);
+  }
+}
+
+// mbarrier wait (same instruction in both modes: cta-scope acquire, see mbar_arrive_cluster)
+template <bool PAIR = false>
+__device__ __forceinline__ void mbar_wait_x(uint64_t* bar, uint32_t parity, DebugBuf* dbg, uint32_t id) {
+  mbar_wait(bar, parity, dbg, id);
 }
 
 // sin/cos of (x, 2x, 4x, ..., 2^(L-1) x) for L <= 10: accurate sincosf at octaves 0 and 5, exact double-angle
@@ -176,14 +199,16 @@ __device__ __forceinline__ void write_ones_block(uint8_t* ones, int tid, int nth
 
 // Wait for two barriers at once: both try_waits are in flight together, so the ~100-cycle latency of an
 // mbarrier operation is paid once per stage instead of twice.
+template <bool PAIR = false>
 __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t par_a, uint64_t* bar_b, uint32_t par_b,
                                            DebugBuf* dbg, uint32_t id) {
-  bool a = mbar_try_wait(bar_a, par_a);
-  bool b = mbar_try_wait(bar_b, par_b);
+  auto tw = [](uint64_t* bar, uint32_t par) { return mbar_try_wait(bar, par); };
+  bool a = tw(bar_a, par_a);
+  bool b = tw(bar_b, par_b);
   uint32_t spins = 0;
   while (!(a && b)) {
-    if (!a) a = mbar_try_wait(bar_a, par_a);
-    if (!b) b = mbar_try_wait(bar_b, par_b);
+    if (!a) a = tw(bar_a, par_a);
+    if (!b) b = tw(bar_b, par_b);
     if (++spins > R2L_WATCHDOG_SPINS) {
       if (dbg != nullptr && atomicCAS(&dbg->flag, 0u, 1u) == 0u) {
         dbg->block = blockIdx.x;
@@ -200,22 +225,38 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t par_a, uint
 // Issue the K=16 MMAs of one weight stage (one thread): N_MMA = 4 for a full K=64 stage, 2 for a K=32 stage.
 //   a_addr : shared address of the A operand's first chunk for this stage (2*N_MMA chunks are consumed)
 //   b_addr : shared address of the weight stage; lbo_b = N*16
-template <int N_MMA = 4>
+// PAIR: tcgen05.mma.cta_group::2 — b_addr / lbo_b describe THIS CTA's N-half of the stage (N/2 rows).
+template <int N_MMA = 4, bool PAIR = false>
 __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t lbo_b,
                                             uint32_t idesc, bool fresh) {
 #pragma unroll
   for (int j = 0; j < N_MMA; ++j) {
     const uint64_t ad = make_smem_desc(a_addr + j * 2 * kLboA, kLboA, kSbo);
     const uint64_t bd = make_smem_desc(b_addr + j * 2 * lbo_b, lbo_b, kSbo);
-    umma_f16_ss(d_tmem, ad, bd, idesc, (fresh && j == 0) ? 0u : 1u);
+    if (PAIR)
+      umma_f16_ss_pair(d_tmem, ad, bd, idesc, (fresh && j == 0) ? 0u : 1u);
+    else
+      umma_f16_ss(d_tmem, ad, bd, idesc, (fresh && j == 0) ? 0u : 1u);
   }
 }
 // The single K=16 MMA of a bias stage (A = the constant ones block).
+template <bool PAIR = false>
 __device__ __forceinline__ void issue_bias_stage(uint32_t d_tmem, uint32_t ones_addr, uint32_t b_addr, uint32_t lbo_b,
                                                  uint32_t idesc, bool fresh) {
   const uint64_t ad = make_smem_desc(ones_addr, kLboA, kSbo);
   const uint64_t bd = make_smem_desc(b_addr, lbo_b, kSbo);
-  umma_f16_ss(d_tmem, ad, bd, idesc, fresh ? 0u : 1u);
+  if (PAIR)
+    umma_f16_ss_pair(d_tmem, ad, bd, idesc, fresh ? 0u : 1u);
+  else
+    umma_f16_ss(d_tmem, ad, bd, idesc, fresh ? 0u : 1u);
+}
+// tcgen05.commit to this CTA's barrier (PAIR: to the barrier at the same offset in both CTAs of the pair)
+template <bool PAIR = false>
+__device__ __forceinline__ void umma_commit_x(uint64_t* bar) {
+  if (PAIR)
+    umma_commit_pair(bar);
+  else
+    umma_commit(bar);
 }
 
 }  // namespace r2l

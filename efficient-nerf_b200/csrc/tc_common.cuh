@@ -104,9 +104,13 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
-// arrive on an mbarrier of any CTA of the cluster (address from mapa_u32), release at cluster scope
+// Arrive on an mbarrier of any CTA of the cluster (address from mapa_u32).  Default (.release.cta) semantics, as
+// CUTLASS's ClusterBarrier::arrive does: a .release.cluster arrive costs a cluster-scope memory barrier (several
+// hundred cycles, measured) on every signal, and what these signals order — this CTA's shared-memory operand
+// writes (made visible to the async proxy by fence.proxy.async) and its TMEM reads (tcgen05.fence) — is consumed by
+// this SM's own tensor core.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
