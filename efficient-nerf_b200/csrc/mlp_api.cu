@@ -66,7 +66,12 @@ __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, in
       bits = __half_as_ushort(__float2half_rn(v));
     const int s = k / kStageK, kk = k % kStageK;
     const int kst = (Kpad - s * kStageK < kStageK) ? (Kpad - s * kStageK) : kStageK;   // K columns in this stage
-    if (pair) {
+    if (pair == 2) {
+      // v3 layout (CTA pair + N-half split): 64-row blocks ordered (CTA r, half h), n = 128h + 64r + i
+      const int h = n / 128, r = (n % 128) / 64, i = n % 64, nh = N / 128;
+      dst[static_cast<long long>(s) * N * kStageK + (static_cast<long long>(r) * nh + h) * 64 * kst + (kk >> 3) * 512 +
+          i * 8 + (kk & 7)] = bits;
+    } else if (pair) {
       const int Nh = N / 2, h = n / Nh, nn = n % Nh;
       dst[static_cast<long long>(s) * N * kStageK + static_cast<long long>(h) * Nh * kst + (kk >> 3) * (Nh * 8) + nn * 8 +
           (kk & 7)] = bits;
@@ -95,7 +100,10 @@ __global__ void pack_bias_kernel(const float* __restrict__ bias, int N, float sc
   if (idx >= N * 16) return;
   const int n = idx / 16, k = idx % 16;
   const uint16_t bits = (k < 2) ? bias_part(bias[n] * scale, k, bf16) : static_cast<uint16_t>(0);
-  if (pair) {   // two N-halves, each k-chunk major with N/2 rows (see pack_layer_kernel)
+  if (pair == 2) {   // v3: 64-row blocks ordered (CTA r, half h), n = 128h + 64r + i
+    const int h = n / 128, r = (n % 128) / 64, i = n % 64, nh = N / 128;
+    dst[(r * nh + h) * 64 * 16 + (k >> 3) * 512 + i * 8 + (k & 7)] = bits;
+  } else if (pair) {   // two N-halves, each k-chunk major with N/2 rows (see pack_layer_kernel)
     const int Nh = N / 2, h = n / Nh, nn = n % Nh;
     dst[h * (Nh * 16) + (k >> 3) * (Nh * 8) + nn * 8 + (k & 7)] = bits;
   } else {
@@ -123,7 +131,7 @@ __global__ void pack_view_stage_kernel(const float* __restrict__ views_w, long l
 struct Mlp {
   int kind = 0;  // 0 = NeRF, 1 = R2L ResMLP
   bool bf16 = false;
-  bool pair = false;   // weights packed for / kernels launched in CTA-pair mode (tcgen05.mma.cta_group::2)
+  int pair = 0;   // weight layout / kernel: 0 single CTA, 1 CTA pair (cta_group::2), 2 "v3" (pair + N-half split)
   uint8_t* wstream = nullptr;
   size_t wbytes = 0;
   float* aux = nullptr;
@@ -140,9 +148,9 @@ struct Mlp {
 // measured equal in throughput to the single-CTA kernel under the power cap (1.677 ms vs 1.678 ms per R2L frame,
 // 1.74 GHz vs 1.65 GHz), so the single-CTA kernel stays the default until the pair kernel's spare shared memory is
 // used to overlap the epilogue.
-static bool pair_mode_default() {
+static int pair_mode_default() {
   const char* e = getenv("R2L_PAIR");
-  return e != nullptr && e[0] == '1';
+  return (e != nullptr && e[0] == '1') ? 1 : 0;
 }
 
 static int alloc_debug(Mlp* m) {
@@ -154,7 +162,7 @@ static int alloc_debug(Mlp* m) {
 
 static int pack_layer(const float* W, long long ldw, int N, int K_src, int Kpad, const std::vector<int>* kmap,
                       float scale, uint16_t* dst, bool bf16, cudaStream_t st, std::vector<int*>& scratch,
-                      bool pair = false) {
+                      int pair = 0) {
   int* d_kmap = nullptr;
   if (kmap != nullptr) {
     R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_kmap), sizeof(int) * Kpad));
@@ -163,14 +171,14 @@ static int pack_layer(const float* W, long long ldw, int N, int K_src, int Kpad,
   }
   const long long total = static_cast<long long>(N) * Kpad;
   const int blocks = static_cast<int>((total + 255) / 256);
-  pack_layer_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K_src, Kpad, d_kmap, scale, dst, bf16 ? 1 : 0, pair ? 1 : 0);
+  pack_layer_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K_src, Kpad, d_kmap, scale, dst, bf16 ? 1 : 0, pair);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }
 
 static int pack_bias(const float* bias, int N, float scale, uint16_t* dst, bool bf16, cudaStream_t st,
-                     bool pair = false) {
-  pack_bias_kernel<<<(N * 16 + 255) / 256, 256, 0, st>>>(bias, N, scale, dst, bf16 ? 1 : 0, pair ? 1 : 0);
+                     int pair = 0) {
+  pack_bias_kernel<<<(N * 16 + 255) / 256, 256, 0, st>>>(bias, N, scale, dst, bf16 ? 1 : 0, pair);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }
@@ -427,7 +435,7 @@ int r2l_tc_gemm_probe_pair(int dtype, int N, int K, const float* A, const float*
   uint16_t* packed = nullptr;
   R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&packed), static_cast<size_t>(N) * K * 2));
   std::vector<int*> scratch;
-  int rc = pack_layer(W, K, N, K, K, nullptr, 1.0f, packed, dtype == 1, st, scratch, /*pair=*/true);
+  int rc = pack_layer(W, K, N, K, K, nullptr, 1.0f, packed, dtype == 1, st, scratch, /*pair=*/1);
   DebugBuf* dbg_host = nullptr;
   DebugBuf* dbg_dev = nullptr;
   if (rc == R2L_OK) {
@@ -688,7 +696,7 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
   }
   uint16_t* dst = reinterpret_cast<uint16_t*>(m->wstream);
   size_t off = 0;
-  const bool pr = m->pair;
+  const int pr = m->pair;
   rc = pack_bias(head_b, 256, 1.0f, dst + off, m->bf16, st, pr);
   off += 256ull * 16;
   if (rc == R2L_OK)
@@ -753,7 +761,7 @@ static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_
   } else {
     grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   }
-  return r2l_mlp_launch(m->bf16, m->pair, p, grid, st);
+  return r2l_mlp_launch(m->bf16, m->pair == 1, p, grid, st);
 }
 
 // Fused PositionalEmbedder + NeRF_v3_2 on sampled points: pts [n_rays, n_points*3] -> rgb [n_rays, 3].

@@ -225,14 +225,32 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t par_a, uint
 // Issue the K=16 MMAs of one weight stage (one thread): N_MMA = 4 for a full K=64 stage, 2 for a K=32 stage.
 //   a_addr : shared address of the A operand's first chunk for this stage (2*N_MMA chunks are consumed)
 //   b_addr : shared address of the weight stage; lbo_b = N*16
+// The MMA-issuing thread is a single thread: every instruction between two tcgen05.mma costs >= 4 cycles of
+// dependent issue, and rebuilding both 64-bit descriptors per MMA (~15 instructions) made the issue rate ~74 cycles
+// per MMA (measured) — slower than an N = 128 MMA executes.  So descriptors are assembled from a constant high word
+// and a low word that advances by a constant per K-step: (lbo >> 4) << 16 | (addr >> 4); addresses stay below 256 KiB,
+// so the 14-bit address field never carries.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((lbo_bytes >> 4) << 16) | ((smem_addr >> 4) & 0x3FFFu);
+}
+constexpr uint32_t kDescHi = ((kSbo >> 4) & 0x3FFFu) | (1u << 14);   // SBO >> 4 at bits [32,46), version 1 at bit 46
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi));
+  return d;
+}
+
 // PAIR: tcgen05.mma.cta_group::2 — b_addr / lbo_b describe THIS CTA's N-half of the stage (N/2 rows).
 template <int N_MMA = 4, bool PAIR = false>
 __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t lbo_b,
                                             uint32_t idesc, bool fresh) {
+  const uint32_t a_lo = desc_lo(a_addr, kLboA);
+  const uint32_t b_lo = desc_lo(b_addr, lbo_b);
+  const uint32_t b_step = (2 * lbo_b) >> 4;
 #pragma unroll
   for (int j = 0; j < N_MMA; ++j) {
-    const uint64_t ad = make_smem_desc(a_addr + j * 2 * kLboA, kLboA, kSbo);
-    const uint64_t bd = make_smem_desc(b_addr + j * 2 * lbo_b, lbo_b, kSbo);
+    const uint64_t ad = desc_pack(a_lo + j * ((2 * kLboA) >> 4));
+    const uint64_t bd = desc_pack(b_lo + j * b_step);
     if (PAIR)
       umma_f16_ss_pair(d_tmem, ad, bd, idesc, (fresh && j == 0) ? 0u : 1u);
     else
@@ -243,8 +261,8 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a_addr, ui
 template <bool PAIR = false>
 __device__ __forceinline__ void issue_bias_stage(uint32_t d_tmem, uint32_t ones_addr, uint32_t b_addr, uint32_t lbo_b,
                                                  uint32_t idesc, bool fresh) {
-  const uint64_t ad = make_smem_desc(ones_addr, kLboA, kSbo);
-  const uint64_t bd = make_smem_desc(b_addr, lbo_b, kSbo);
+  const uint64_t ad = desc_pack(desc_lo(ones_addr, kLboA));
+  const uint64_t bd = desc_pack(desc_lo(b_addr, lbo_b));
   if (PAIR)
     umma_f16_ss_pair(d_tmem, ad, bd, idesc, fresh ? 0u : 1u);
   else

@@ -72,10 +72,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Wait for the phase with the given parity to complete.  `id` only feeds the watchdog.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugBuf* dbg, uint32_t id) {
+// `patience` multiplies the watchdog limit: producers wait with more patience than consumers, so that the record
+// names the consumer that is really stuck rather than the producer starved behind it.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugBuf* dbg, uint32_t id,
+                                          uint32_t patience = 1) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > R2L_WATCHDOG_SPINS) {
+    if (++spins > R2L_WATCHDOG_SPINS * patience) {
       if (dbg != nullptr && atomicCAS(&dbg->flag, 0u, 1u) == 0u) {
         dbg->block = blockIdx.x;
         dbg->thread = threadIdx.x;
