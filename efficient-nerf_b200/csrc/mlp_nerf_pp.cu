@@ -1,0 +1,554 @@
+// NeRF MLP (W256 x D8 + heads), "ping-pong" schedule on a CTA pair.  Same math as mlp_nerf.cu
+// (model/nerf_raybased.py:377-401, main.py:65-87); what changes is how the epilogue latency is hidden.
+//
+// mlp_nerf.cu runs ONE 128-sample tile per CTA and lets layer l+1's MMAs chase layer l's epilogue: the tensor pipe
+// still idles ~900 cycles per layer (accumulator commit -> warps wake -> tcgen05.ld -> cvt/st -> fences -> arrive ->
+// issuer wakes), 30 % of the time.  Here every CTA owns TWO tiles T0, T1, each with its own activation buffer and
+// ONE 256-column TMEM accumulator, and the tensor pipe alternates:  T0.L0, T1.L0, T0.L1, T1.L1, ...  While tile
+// T1's layer executes (2176 tensor cycles), tile T0's epilogue converts its accumulator in place into T0's
+// activations, so the next T0 layer finds its operands ready and the pipe never waits for an epilogue.
+//
+// What makes it fit:
+//   * CTA pair (tcgen05.mma.cta_group::2, M = 256 = one tile of each CTA): every CTA streams only its N-half of a
+//     weight stage (16 KiB), so two activation buffers (128 KiB) + two point blocks (32 KiB) + a 3-slot weight ring
+//     (48 KiB) fit in 227 KiB.  A layer's weights are streamed once per tile (T0, then T1): 32 B/cycle/SM from L2.
+//   * TWO issuer threads, one per tile, passing a token: a thread needs ~56 cycles per tcgen05.mma and ~80 per
+//     tcgen05.commit / mbarrier wait (scratch/ubench/mmaissue.cu), i.e. ~2000 cycles per tile-layer — too close to
+//     the 2176 tensor cycles for one thread, comfortable for two that alternate.
+//   * The view branch is a per-ray fp32 bias vb (computed by nerf_view_bias_kernel into a caller workspace) added in
+//     the last epilogue instead of an extra K-stage: it needs no shared memory.
+//   * No per-group chasing barriers: a tile-layer starts when the tile's previous epilogue has signalled a_done[t]
+//     (one barrier, 16 warp arrivals), which also closes every TMEM / shared-memory write-after-read hazard.
+// Per tile: 10 steps (see mlp_nerf.cu): 0 = W0 P, 1-4, 5 = W5 [P, h], 6, 7 (+sigma), 8 = feature, 9 = views (N 128).
+#include "common.cuh"
+#include "mlp_params.cuh"
+#include "mlp_tc.cuh"
+
+namespace r2l {
+
+constexpr int kPpThreads = 480;
+constexpr int kPpProducerWarp = 12;
+constexpr int kPpMmaWarp0 = 13;   // leader: issuer of tile T0; peer: relays weight arrivals to the leader
+constexpr int kPpMmaWarp1 = 14;   // leader: issuer of tile T1
+constexpr int kPpRing = 3;
+constexpr int kPpBiasRing = 2;
+constexpr uint32_t kPpStageB = kStageBytes / 2;       // 16 KiB: this CTA's N-half of a K=64 stage
+constexpr uint32_t kPpBiasB = kBiasStageBytes / 2;    // 4 KiB
+constexpr uint32_t kPpLbo256 = 128 * 16;              // 128 B-rows per CTA (N = 256)
+constexpr uint32_t kPpLbo128 = 64 * 16;               // 64 B-rows per CTA (N = 128)
+// shared memory map
+constexpr int kPpOffA = 0;                                            // A[tile]
+constexpr int kPpOffP = kPpOffA + 2 * kABufBytes;                     // P[tile]
+constexpr int kPpOffOnes = kPpOffP + 2 * kPBlockBytes;
+constexpr int kPpOffRing = kPpOffOnes + kOnesBytes;
+constexpr int kPpOffBiasRing = kPpOffRing + kPpRing * kPpStageB;
+constexpr int kPpOffAlphaW = kPpOffBiasRing + kPpBiasRing * kPpBiasB;   // 256 floats
+constexpr int kPpOffRgbW = kPpOffAlphaW + 256 * 4;                    // 3*128 floats
+constexpr int kPpOffPart = kPpOffRgbW + 384 * 4;                      // 128 x float4
+constexpr int kPpOffBars = kPpOffPart + 128 * 16;
+constexpr int kPpNumBars = 2 * kPpRing + 2 * kPpBiasRing + 2 + 2 + 2 + 2 + 2;
+constexpr int kPpOffTmem = kPpOffBars + kPpNumBars * 8;
+constexpr int kPpSmemBytes = kPpOffTmem + 16;
+static_assert(kPpSmemBytes <= 227 * 1024, "NeRF ping-pong kernel shared memory exceeds 227 KiB");
+static_assert(kPpOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
+
+__device__ __forceinline__ int pp_main_stages(int step) { return step == 0 ? 1 : (step == 5 ? 5 : 4); }
+
+template <bool BF16>
+__global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* const sA = smem + kPpOffA;
+  uint8_t* const sP = smem + kPpOffP;
+  uint8_t* const sOnes = smem + kPpOffOnes;
+  uint8_t* const sRing = smem + kPpOffRing;
+  uint8_t* const sBiasRing = smem + kPpOffBiasRing;
+  float* const sAlphaW = reinterpret_cast<float*>(smem + kPpOffAlphaW);
+  float* const sRgbW = reinterpret_cast<float*>(smem + kPpOffRgbW);
+  float4* const sPart = reinterpret_cast<float4*>(smem + kPpOffPart);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kPpOffBars);
+  uint64_t* const w_full = bars;                    // leader: own producer + the peer's relay
+  uint64_t* const w_empty = w_full + kPpRing;
+  uint64_t* const b_full = w_empty + kPpRing;
+  uint64_t* const b_empty = b_full + kPpBiasRing;
+  uint64_t* const d_full = b_empty + kPpBiasRing;   // [tile]: accumulator complete (commit, both CTAs)
+  uint64_t* const a_done = d_full + 2;              // [tile]: leader; 16 epilogue warps are done with the tile's layer
+  uint64_t* const p_ready = a_done + 2;             // [tile]: leader; 8 encoder warps have written P[tile]
+  uint64_t* const p_free = p_ready + 2;             // [tile]: step 5's MMAs have read P[tile] (commit, both CTAs)
+  uint64_t* const turn = p_free + 2;                // [tile]: leader; the other issuer has issued its tile-layer
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + kPpOffTmem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+  // a unit = 4 tiles: tile(unit, t, rank) = 4*unit + 2*t + rank
+  const int n_units = (p.n_tiles + 3) / 4;
+  const int unit0 = static_cast<int>(blockIdx.x >> 1);
+  const int unit_step = static_cast<int>(gridDim.x >> 1);
+
+  // ---- one-time setup ----
+  for (int i = threadIdx.x; i < 256; i += kPpThreads) sAlphaW[i] = p.alpha_w[i];
+  for (int i = threadIdx.x; i < 384; i += kPpThreads) sRgbW[i] = p.rgb_w[i];
+  write_ones_block<BF16>(sOnes, threadIdx.x, kPpThreads);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPpRing; ++i) {
+      mbar_init(&w_full[i], rank == 0 ? 2 : 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < kPpBiasRing; ++i) {
+      mbar_init(&b_full[i], rank == 0 ? 2 : 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d_full[i], 1);
+      mbar_init(&a_done[i], 16);
+      mbar_init(&p_ready[i], 8);
+      mbar_init(&p_free[i], 1);
+      mbar_init(&turn[i], 1);
+    }
+    mbar_fence_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == kPpMmaWarp0) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anybody signals them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ===================== MMA issuer of tile t (leader CTA; one thread per tile) =====================
+  auto mma_issuer = [&](const int t) {
+    const uint32_t idesc256 = make_idesc_f16(BF16, 2 * kTileM, 256);
+    const uint32_t idesc128 = make_idesc_f16(BF16, 2 * kTileM, 128);
+    const uint32_t aA = smem_u32(sA) + t * kABufBytes;
+    const uint32_t aP = smem_u32(sP) + t * kPBlockBytes;
+    const uint32_t aOnes = smem_u32(sOnes);
+    const uint32_t aRing = smem_u32(sRing);
+    const uint32_t aBiasRing = smem_u32(sBiasRing);
+    const uint32_t d = tmem_base + 256u * t;
+    uint32_t g = 0, gb = 0;        // position in the shared weight / bias stage streams
+    uint32_t n_turn = 0;           // turns taken so far (parity of the next turn[t] phase)
+    uint32_t par_done = 0;         // parity of the next a_done[t] phase
+    const bool prof = p.prof != nullptr && t == 0;
+    long long t_a = 0, t_w = 0, t_p = 0;
+    const long long t_start = prof ? clock64() : 0;
+    auto next_w = [&]() -> uint32_t {
+      const uint32_t slot = g % kPpRing;
+      const long long c0 = prof ? clock64() : 0;
+      mbar_wait(&w_full[slot], (g / kPpRing) & 1, p.dbg, 220 + slot + 30 * t);
+      if (prof) t_w += clock64() - c0;
+      tc_fence_after_sync();
+      return slot;
+    };
+    uint32_t it = 0;
+    for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
+      for (int step = 0; step < 10; ++step) {
+        const int nm = pp_main_stages(step);
+        const int nbias = step < 9 ? 1 : 0;
+        if (t == 1) {   // tile 0's stages of this step come first in the streams
+          g += nm;
+          gb += nbias;
+        }
+        // my turn: the other issuer has issued its tile-layer (keeps the T0, T1, T0, ... order on the tensor pipe)
+        if (!(t == 0 && n_turn == 0)) {
+          mbar_wait(&turn[t], (t == 0 ? n_turn - 1 : n_turn) & 1u, p.dbg, 270 + t);
+        }
+        ++n_turn;
+        // the tile's previous epilogue is done: A[t] holds this layer's input and D[t] may be overwritten
+        if (!(it == 0 && step == 0)) {
+          const long long c0 = prof ? clock64() : 0;
+          mbar_wait(&a_done[t], par_done, p.dbg, 210 + t);
+          if (prof) t_a += clock64() - c0;
+          par_done ^= 1u;
+        }
+        if (step == 0) {
+          const long long c0 = prof ? clock64() : 0;
+          mbar_wait(&p_ready[t], it & 1u, p.dbg, 200 + t);
+          if (prof) t_p += clock64() - c0;
+        }
+        tc_fence_after_sync();
+        if (step < 9) {
+          // ---- bias step (fresh accumulator), [point-block stage], 4 activation stages
+          {
+            const uint32_t slot = gb % kPpBiasRing;
+            const long long c0 = prof ? clock64() : 0;
+            mbar_wait(&b_full[slot], (gb / kPpBiasRing) & 1, p.dbg, 240 + slot + 30 * t);
+            if (prof) t_w += clock64() - c0;
+            tc_fence_after_sync();
+            issue_bias_stage<true>(d, aOnes, aBiasRing + slot * kPpBiasB, kPpLbo256, idesc256, true);
+            umma_commit_pair(&b_empty[slot]);
+            ++gb;
+          }
+          if (step == 0 || step == 5) {
+            const uint32_t slot = next_w();
+            issue_stage<4, true>(d, aP, aRing + slot * kPpStageB, kPpLbo256, idesc256, false);
+            umma_commit_pair(&w_empty[slot]);
+            ++g;
+          }
+          if (step > 0) {
+            for (int st = 0; st < 4; ++st) {
+              const uint32_t slot = next_w();
+              issue_stage<4, true>(d, aA + st * kGroupBytes, aRing + slot * kPpStageB, kPpLbo256, idesc256, false);
+              umma_commit_pair(&w_empty[slot]);
+              ++g;
+            }
+          }
+          if (step == 5) umma_commit_pair(&p_free[t]);
+        } else {
+          // ---- step 9: view branch, N = 128 (per-ray bias added by the epilogue)
+          for (int st = 0; st < 4; ++st) {
+            const uint32_t slot = next_w();
+            issue_stage<4, true>(d, aA + st * kGroupBytes, aRing + slot * kPpStageB, kPpLbo128, idesc128, st == 0);
+            umma_commit_pair(&w_empty[slot]);
+            ++g;
+          }
+        }
+        umma_commit_pair(&d_full[t]);
+        mbar_arrive(&turn[1 - t]);
+        if (t == 0) {   // tile 1's stages of this step follow
+          g += nm;
+          gb += nbias;
+        }
+      }
+    }
+    if (prof) {
+      long long* o = p.prof + blockIdx.x * 8;
+      o[0] = clock64() - t_start;   // issuer T0: total
+      o[1] = t_a;                   // waiting for the tile's previous epilogue
+      o[2] = t_w;                   // waiting for weight / bias stages
+      o[7] = t_p;                   // waiting for the encoder
+    }
+  };
+
+  if (warp == kPpProducerWarp) {
+    // ===================== weight producer: this CTA's N-half of every stage, once per tile =====================
+    if (lane == 0) {
+      uint32_t g = 0, gb = 0;
+      auto push = [&](const uint8_t* src, uint32_t full_bytes) {
+        const uint32_t half = full_bytes / 2;
+        const uint32_t slot = g % kPpRing;
+        mbar_wait(&w_empty[slot], ((g / kPpRing) & 1) ^ 1, p.dbg, 100 + slot, 8);
+        mbar_expect_tx(&w_full[slot], half);
+        bulk_g2s(sRing + slot * kPpStageB, src + rank * half, half, &w_full[slot]);
+        ++g;
+      };
+      auto push_bias = [&](const uint8_t* src) {
+        const uint32_t slot = gb % kPpBiasRing;
+        mbar_wait(&b_empty[slot], ((gb / kPpBiasRing) & 1) ^ 1, p.dbg, 120 + slot, 8);
+        mbar_expect_tx(&b_full[slot], kPpBiasB);
+        bulk_g2s(sBiasRing + slot * kPpBiasB, src + rank * kPpBiasB, kPpBiasB, &b_full[slot]);
+        ++gb;
+      };
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        const uint8_t* src = p.wstream;
+        for (int step = 0; step < 10; ++step) {
+          const int nm = pp_main_stages(step);
+          const uint32_t sb = step < 9 ? kStageBytes : kStageBytes / 2;
+          for (int t = 0; t < 2; ++t) {
+            const uint8_t* s = src;
+            if (step < 9) {
+              push_bias(s);
+              s += kBiasStageBytes;
+            }
+            for (int i = 0; i < nm; ++i) {
+              push(s, sb);
+              s += sb;
+            }
+          }
+          src += (step < 9 ? kBiasStageBytes : 0) + nm * sb;
+        }
+      }
+    }
+  } else if (warp == kPpMmaWarp0) {
+    if (rank != 0) {
+      // ===================== peer CTA: relay "my half stage has landed" to the leader's barriers =====================
+      if (lane == 0) {
+        uint32_t g = 0, gb = 0;
+        for (int unit = unit0; unit < n_units; unit += unit_step) {
+          for (int step = 0; step < 10; ++step) {
+            const int nm = pp_main_stages(step);
+            for (int t = 0; t < 2; ++t) {
+              if (step < 9) {
+                const uint32_t slot = gb % kPpBiasRing;
+                mbar_wait(&b_full[slot], (gb / kPpBiasRing) & 1, p.dbg, 170 + slot, 8);
+                mbar_arrive_cluster(mapa_u32(&b_full[slot], 0));
+                ++gb;
+              }
+              for (int i = 0; i < nm; ++i) {
+                const uint32_t slot = g % kPpRing;
+                mbar_wait(&w_full[slot], (g / kPpRing) & 1, p.dbg, 150 + slot, 8);
+                mbar_arrive_cluster(mapa_u32(&w_full[slot], 0));
+                ++g;
+              }
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
+      mma_issuer(0);
+    }
+  } else if (warp == kPpMmaWarp1) {
+    if (rank == 0 && lane == 0) mma_issuer(1);
+  } else if (warp >= 8) {
+    // ===================== encoder warpgroup: P[t] of the NEXT unit as soon as step 5 has released it =====================
+    const int row = (warp & 3) * 32 + lane;
+    uint32_t it = 0;
+    for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
+      for (int t = 0; t < 2; ++t) {
+        const long long tile = 4LL * unit + 2 * t + rank;
+        long long gr = tile * kTileM + row;
+        if (gr >= p.n_rows) gr = p.n_rows - 1;
+        uint8_t* const dP = sP + t * kPBlockBytes;
+        if (p.embedded != nullptr) {
+          // API path: the caller already embedded the points (63 features per row)
+          const float* x = p.embedded + gr * p.emb_stride;
+          float e[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) e[i] = (i < 63) ? __ldg(x + i) : 0.0f;
+          if (it > 0) mbar_wait(&p_free[t], (it - 1) & 1u, p.dbg, 500 + t, 4);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4 q;
+            q.x = pack2<BF16>(e[8 * ch + 0], e[8 * ch + 1]);
+            q.y = pack2<BF16>(e[8 * ch + 2], e[8 * ch + 3]);
+            q.z = pack2<BF16>(e[8 * ch + 4], e[8 * ch + 5]);
+            q.w = pack2<BF16>(e[8 * ch + 6], e[8 * ch + 7]);
+            *reinterpret_cast<uint4*>(dP + ch * kChunkBytes + row * 16) = q;
+          }
+        } else {
+          const long long ray = gr / p.S;
+          const float z = __ldg(p.z_vals + gr);
+          const float* o = p.rays_o + ray * p.o_stride;
+          const float* dd = p.rays_d + ray * p.d_stride;
+          const float px = __fadd_rn(__ldg(o + 0), __fmul_rn(__ldg(dd + 0), z));
+          const float py = __fadd_rn(__ldg(o + 1), __fmul_rn(__ldg(dd + 1), z));
+          const float pz = __fadd_rn(__ldg(o + 2), __fmul_rn(__ldg(dd + 2), z));
+          if (it > 0) mbar_wait(&p_free[t], (it - 1) & 1u, p.dbg, 500 + t, 4);
+          encode_point_block<BF16>(dP, row, px, py, pz);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) lane_arrive<true>(&p_ready[t]);
+      }
+    }
+  } else {
+    // ===================== epilogue warpgroups (both tiles, alternating) =====================
+    const int wg = warp >> 2;                       // owns the 32-column pieces wg, wg+2, wg+4, wg+6
+    const int row = (warp & 3) * 32 + lane;         // tile row == TMEM lane
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
+    long long t_d = 0;
+    const long long t_start = prof ? clock64() : 0;
+    uint32_t par_d = 0;   // bit tile: parity of the next d_full phase
+    auto wait_d = [&](int t, uint32_t id) {
+      const long long cd = prof ? clock64() : 0;
+      mbar_wait(&d_full[t], (par_d >> t) & 1u, p.dbg, id, 4);
+      if (prof) t_d += clock64() - cd;
+      par_d ^= 1u << t;
+      tc_fence_after_sync();
+    };
+    // this warp's four 32-column pieces (columns 32*wg + 64*i) of accumulator D[t], software pipelined
+    auto for_pieces = [&](int t, auto&& f) {
+      uint32_t va[32], vb[32];
+      const uint32_t c0 = 32 * wg;
+      const uint32_t base = lane_taddr + 256 * t + c0;
+      tmem_ld32(base, va);
+      tmem_ld_wait();
+      tmem_ld32(base + 64, vb);
+      f(c0, va);
+      tmem_ld_wait();
+      tmem_ld32(base + 128, va);
+      f(c0 + 64, vb);
+      tmem_ld_wait();
+      tmem_ld32(base + 192, vb);
+      f(c0 + 128, va);
+      tmem_ld_wait();
+      f(c0 + 192, vb);
+    };
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      float sigma_part[2] = {0.0f, 0.0f};
+      for (int step = 0; step < 10; ++step) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          uint8_t* const a_row = sA + t * kABufBytes + row * 16;
+          wait_d(t, 300 + step * 2 + t);
+          if (step < 9) {
+            if (step == 7) {
+              float sp = 0.0f;
+              for_pieces(t, [&](uint32_t col0, uint32_t (&v)[32]) {
+                store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sp = fmaf(sAlphaW[col0 + i], fmaxf(__uint_as_float(v[i]), 0.0f), sp);
+              });
+              sigma_part[t] = sp;
+            } else if (step == 8) {
+              for_pieces(t, [&](uint32_t col0, uint32_t (&v)[32]) {
+                store_sub<BF16, false>(v, a_row + (col0 >> 5) * kSubBytes);
+              });
+            } else {
+              for_pieces(t, [&](uint32_t col0, uint32_t (&v)[32]) {
+                store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
+              });
+            }
+            warp_arrive<true>(&a_done[t], lane);
+          } else {
+            // step 9: view branch (N = 128 -> D[t] columns [0,128)); this warp owns columns 32*wg and 64 + 32*wg
+            const long long tile = 4LL * unit + 2 * t + rank;
+            const long long g_row = tile * kTileM + row;
+            const bool valid = g_row < p.n_rows;
+            const long long ray = (valid ? g_row : (p.n_rows - 1)) / p.S;
+            const float4* vb4 = reinterpret_cast<const float4*>(p.vb + ray * 128);
+            float r = 0.f, gch = 0.f, b = 0.f;
+            {
+              uint32_t va[32], vb[32];
+              tmem_ld32(lane_taddr + 256 * t + 32 * wg, va);
+              tmem_ld32(lane_taddr + 256 * t + 64 + 32 * wg, vb);
+              tmem_ld_wait();
+              warp_arrive<true>(&a_done[t], lane);   // D[t] is drained: the next unit's step 0 may overwrite it
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 bb = __ldg(vb4 + 8 * wg + i4);
+                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int n = 32 * wg + 4 * i4 + k;
+                  const float x = fmaxf(__uint_as_float(va[4 * i4 + k]) + bv[k], 0.0f);
+                  r = fmaf(sRgbW[n], x, r);
+                  gch = fmaf(sRgbW[128 + n], x, gch);
+                  b = fmaf(sRgbW[256 + n], x, b);
+                }
+              }
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 bb = __ldg(vb4 + 16 + 8 * wg + i4);
+                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int n = 64 + 32 * wg + 4 * i4 + k;
+                  const float x = fmaxf(__uint_as_float(vb[4 * i4 + k]) + bv[k], 0.0f);
+                  r = fmaf(sRgbW[n], x, r);
+                  gch = fmaf(sRgbW[128 + n], x, gch);
+                  b = fmaf(sRgbW[256 + n], x, b);
+                }
+              }
+            }
+            if (wg == 1) {
+              sPart[row] = make_float4(r, gch, b, sigma_part[t]);
+              named_bar_arrive(1, 256);
+              named_bar_sync(2, 256);   // WG0 has consumed sPart
+            } else {
+              named_bar_sync(1, 256);
+              const float4 o1 = sPart[row];
+              named_bar_arrive(2, 256);
+              if (valid) {
+                float4 o;
+                o.x = r + o1.x + p.rgb_b[0];
+                o.y = gch + o1.y + p.rgb_b[1];
+                o.z = b + o1.z + p.rgb_b[2];
+                o.w = sigma_part[t] + o1.w + p.alpha_b;
+                reinterpret_cast<float4*>(p.raw)[g_row] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (prof) {
+      long long* o = p.prof + blockIdx.x * 8 + 3 + wg * 2;
+      o[0] = t_d;                          // WG: waiting for accumulators
+      o[1] = (clock64() - t_start) - t_d;  // WG: epilogue work (everything else)
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs are done with their TMEM and with each other's barriers
+  if (warp == kPpMmaWarp0) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// Per-ray view-branch bias: vb[ray][n] = bv[n] + sum_j Wvd[n][j] * embed4(viewdir)[j]   (fp32)
+// embed4 = NeRF Embedder with L = 4 on the unit view direction (27 features, helpers:24-74); the view half of
+// views_linears[0] is constant along a ray, so it is evaluated once per ray (model/nerf_raybased.py:390-394).
+__global__ void __launch_bounds__(128)
+nerf_view_bias_kernel(long long n_rays, const float* __restrict__ viewdirs, long long v_stride, int pre_embedded,
+                      const float* __restrict__ wvd /*[128][27]*/, const float* __restrict__ bv, float* __restrict__ vb) {
+  __shared__ float s_w[128 * 27];
+  __shared__ float s_e[8][28];
+  for (int i = threadIdx.x; i < 128 * 27; i += 128) s_w[i] = wvd[i];
+  const int n = threadIdx.x;
+  const float b = bv[n];
+  for (long long r0 = static_cast<long long>(blockIdx.x) * 8; r0 < n_rays; r0 += static_cast<long long>(gridDim.x) * 8) {
+    __syncthreads();
+    if (pre_embedded) {
+      // rows already hold the 27 embedded view features
+      for (int it = threadIdx.x; it < 8 * 27; it += 128) {
+        const int rr = it / 27, j = it % 27;
+        const long long ray = r0 + rr;
+        if (ray < n_rays) s_e[rr][j] = viewdirs[ray * v_stride + j];
+      }
+    } else if (threadIdx.x < 24) {
+      // 8 rays x 3 coords: identity + 4 sincos each
+      const int rr = threadIdx.x / 3, c = threadIdx.x % 3;
+      const long long ray = r0 + rr;
+      if (ray < n_rays) {
+        const float v = viewdirs[ray * v_stride + c];
+        s_e[rr][c] = v;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          float s, co;
+          sincosf(v * static_cast<float>(1 << f), &s, &co);
+          s_e[rr][3 + 6 * f + c] = s;
+          s_e[rr][3 + 6 * f + 3 + c] = co;
+        }
+      }
+    }
+    __syncthreads();
+    for (int rr = 0; rr < 8; ++rr) {
+      const long long ray = r0 + rr;
+      if (ray >= n_rays) break;
+      float acc = b;
+#pragma unroll
+      for (int j = 0; j < 27; ++j) acc = fmaf(s_w[n * 27 + j], s_e[rr][j], acc);
+      vb[ray * 128 + n] = acc;
+    }
+  }
+}
+
+template <bool BF16>
+int launch_nerf_pp(const NerfParams& p, int grid, cudaStream_t st) {
+  R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kPpThreads);
+  cfg.dynamicSmemBytes = kPpSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16>, p));
+  return R2L_OK;
+}
+
+// grid must be even (CTA pairs); weights packed in the pair layout WITHOUT the view stage (mlp_api.cu)
+int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st) {
+  return bf16 ? launch_nerf_pp<true>(p, grid, st) : launch_nerf_pp<false>(p, grid, st);
+}
+
+int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,
+                          const float* wvd, const float* bv, float* vb, cudaStream_t st) {
+  long long blocks = (n_rays + 7) / 8;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  nerf_view_bias_kernel<<<static_cast<int>(blocks), 128, 0, st>>>(n_rays, viewdirs, v_stride, pre_embedded, wvd, bv, vb);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+}  // namespace r2l
