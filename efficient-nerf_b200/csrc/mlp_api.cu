@@ -139,6 +139,11 @@ struct Mlp {
   DebugBuf* dbg_dev = nullptr;
   // NeRF
   float alpha_b = 0.f, rgb_b[3] = {0.f, 0.f, 0.f};
+  int nerf_pp = 0;                 // 1: CTA-pair ping-pong kernel (mlp_nerf_pp.cu)
+  uint8_t* wstream_pp = nullptr;   // pair-layout stage stream without the view stage
+  float* view_tab = nullptr;       // [128][27] view half of views_linears[0].weight, then [128] its bias (fp32)
+  float* vb_ws = nullptr;          // workspace: per-ray view-branch bias [vb_cap rays][128]
+  long long vb_cap = 0;
   // R2L
   int n_points = 0, n_blocks = 0, sigmoid_out = 1, outer_skip = 1;
   float b_tail[3] = {0.f, 0.f, 0.f};
@@ -148,6 +153,11 @@ struct Mlp {
 // measured equal in throughput to the single-CTA kernel under the power cap (1.677 ms vs 1.678 ms per R2L frame,
 // 1.74 GHz vs 1.65 GHz), so the single-CTA kernel stays the default until the pair kernel's spare shared memory is
 // used to overlap the epilogue.
+// R2L_NERF_PP=0 selects the single-CTA chasing NeRF kernel (mlp_nerf.cu) instead of the CTA-pair ping-pong kernel.
+static int nerf_pp_default() {
+  const char* e = getenv("R2L_NERF_PP");
+  return (e != nullptr && e[0] == '1') ? 1 : 0;
+}
 static int pair_mode_default() {
   const char* e = getenv("R2L_PAIR");
   return (e != nullptr && e[0] == '1') ? 1 : 0;
@@ -186,6 +196,9 @@ static int pack_bias(const float* bias, int N, float scale, uint16_t* dst, bool 
 static void destroy(Mlp* m) {
   if (m == nullptr) return;
   if (m->wstream) cudaFree(m->wstream);
+  if (m->wstream_pp) cudaFree(m->wstream_pp);
+  if (m->view_tab) cudaFree(m->view_tab);
+  if (m->vb_ws) cudaFree(m->vb_ws);
   if (m->aux) cudaFree(m->aux);
   if (m->dbg_host) cudaFreeHost(m->dbg_host);
   delete m;
@@ -539,6 +552,50 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
   }
   if (rc != R2L_OK) return cleanup(rc);
   if (off != elems) return cleanup(fail(R2L_ERR_INVALID, "r2l_nerf_create: internal stream size mismatch"));
+  m->nerf_pp = nerf_pp_default();
+  if (m->nerf_pp) {
+    // second stream for the ping-pong kernel: CTA-pair layout (two N-halves per stage), no view stage — the view
+    // half of views_linears[0] becomes a per-ray fp32 bias (nerf_view_bias_kernel) from view_tab
+    const size_t elems_pp = elems - 128ull * 32;   // no view stage
+    if (cudaMalloc(reinterpret_cast<void**>(&m->wstream_pp), elems_pp * 2) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&m->view_tab), sizeof(float) * (128 * 27 + 128)) != cudaSuccess)
+      return cleanup(fail(R2L_ERR_CUDA, "r2l_nerf_create: cudaMalloc failed"));
+    uint16_t* d2 = reinterpret_cast<uint16_t*>(m->wstream_pp);
+    size_t o2 = 0;
+    for (int l = 0; l < 8 && rc == R2L_OK; ++l) {
+      rc = pack_bias(pts_b[l], 256, 1.0f, d2 + o2, m->bf16, st, 1);
+      o2 += 256ull * 16;
+      if (rc != R2L_OK) break;
+      if (l == 0) {
+        rc = pack_layer(pts_w[0], 63, 256, 63, 64, &kmap0, 1.0f, d2 + o2, m->bf16, st, scratch, 1);
+        o2 += 256ull * 64;
+      } else if (l == 5) {
+        rc = pack_layer(pts_w[5], 319, 256, 319, 320, &kmap5, 1.0f, d2 + o2, m->bf16, st, scratch, 1);
+        o2 += 256ull * 320;
+      } else {
+        rc = pack_layer(pts_w[l], 256, 256, 256, 256, nullptr, 1.0f, d2 + o2, m->bf16, st, scratch, 1);
+        o2 += 256ull * 256;
+      }
+    }
+    if (rc == R2L_OK) {
+      rc = pack_bias(feature_b, 256, 1.0f, d2 + o2, m->bf16, st, 1);
+      o2 += 256ull * 16;
+    }
+    if (rc == R2L_OK) {
+      rc = pack_layer(feature_w, 256, 256, 256, 256, nullptr, 1.0f, d2 + o2, m->bf16, st, scratch, 1);
+      o2 += 256ull * 256;
+    }
+    if (rc == R2L_OK) {
+      rc = pack_layer(views_w, 283, 128, 256, 256, nullptr, 1.0f, d2 + o2, m->bf16, st, scratch, 1);
+      o2 += 128ull * 256;
+    }
+    if (rc != R2L_OK) return cleanup(rc);
+    if (o2 != elems_pp) return cleanup(fail(R2L_ERR_INVALID, "r2l_nerf_create: internal pp stream size mismatch"));
+    cudaError_t e2 = cudaMemcpy2DAsync(m->view_tab, 27 * 4, views_w + 256, 283 * 4, 27 * 4, 128, cudaMemcpyDeviceToDevice, st);
+    if (e2 == cudaSuccess)
+      e2 = cudaMemcpyAsync(m->view_tab + 128 * 27, views_b, 128 * 4, cudaMemcpyDeviceToDevice, st);
+    if (e2 != cudaSuccess) return cleanup(fail(R2L_ERR_CUDA, "r2l_nerf_create: %s", cudaGetErrorString(e2)));
+  }
   cudaError_t e = cudaMemcpyAsync(m->aux + kNerfAuxAlphaW, alpha_w, 256 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxRgbW, rgb_w, 384 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&m->alpha_b, alpha_b, 4, cudaMemcpyDeviceToHost, st);
@@ -566,6 +623,30 @@ static int nerf_run(Mlp* m, NerfParams& p, cudaStream_t st) {
   R2L_CHECK_ARG(n_tiles < (1LL << 31), "r2l_nerf_forward: too many samples for one call");
   p.n_tiles = static_cast<int>(n_tiles);
   p.dbg = m->dbg_dev;
+  if (m->nerf_pp) {
+    { const char* e = getenv("R2L_PROF_MODE"); if (e != nullptr) p.prof_mode = atoi(e); }
+    // per-ray view bias into the handle's workspace (grown on demand: the only allocation a forward can make),
+    // then the ping-pong kernel: units of 4 tiles (2 per CTA of a pair)
+    const bool emb = p.embedded != nullptr;
+    const long long n_rays = emb ? p.n_rows : p.n_rows / p.S;
+    if (n_rays > m->vb_cap) {
+      R2L_CUDA(cudaStreamSynchronize(st));
+      if (m->vb_ws) cudaFree(m->vb_ws);
+      m->vb_ws = nullptr;
+      m->vb_cap = 0;
+      R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->vb_ws), sizeof(float) * 128 * static_cast<size_t>(n_rays)));
+      m->vb_cap = n_rays;
+    }
+    int rc = nerf_view_bias_launch(n_rays, emb ? p.embedded + 63 : p.viewdirs, emb ? p.emb_stride : p.v_stride,
+                                   emb ? 1 : 0, m->view_tab, m->view_tab + 128 * 27, m->vb_ws, st);
+    if (rc != R2L_OK) return rc;
+    p.vb = m->vb_ws;
+    p.wstream = m->wstream_pp;
+    const long long n_units = (n_tiles + 3) / 4;
+    const long long max_pairs = sm_count() / 2;
+    const int grid = static_cast<int>(2 * (n_units < max_pairs ? n_units : max_pairs));
+    return nerf_mlp_pp_launch(m->bf16, p, grid, st);
+  }
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   return nerf_mlp_launch(m->bf16, p, grid, st);
 }
@@ -638,6 +719,7 @@ int r2l_nerf_profile(void* handle, long long n_rays, int S, const float* rays_o,
   p.n_rows = n_rays * S;
   p.raw = raw;
   p.prof = prof;
+  { const char* e = getenv("R2L_PROF_MODE"); p.prof_mode = (e != nullptr) ? atoi(e) : 0; }
   return nerf_run(m, p, static_cast<cudaStream_t>(stream));
 }
 

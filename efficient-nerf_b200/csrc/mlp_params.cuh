@@ -26,6 +26,8 @@ struct NerfParams {
   const float* embedded;    // optional [n_rows][emb_stride]: 63 embedded-point + 27 embedded-view features
   long long emb_stride;
   long long* prof;          // optional [gridDim.x][8] cycle counters (see r2l_nerf_profile)
+  int prof_mode;            // ping-pong kernel: 1 = report ring turnaround instead of the wait split
+  const float* vb;          // ping-pong kernel only: per-ray view-branch bias [n_rays][128] (nerf_view_bias_kernel)
 };
 
 struct R2lParams {
@@ -51,5 +53,9 @@ struct R2lParams {
 
 int nerf_mlp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st);
 int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, int grid, cudaStream_t st);
+// CTA-pair "ping-pong" NeRF kernel (mlp_nerf_pp.cu): grid even, pair-layout stream without the view stage
+int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st);
+int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,
+                          const float* wvd, const float* bv, float* vb, cudaStream_t st);
 
 }  // namespace r2l
