@@ -144,6 +144,7 @@ struct Mlp {
   float* view_tab = nullptr;       // [128][27] view half of views_linears[0].weight, then [128] its bias (fp32)
   float* vb_ws = nullptr;          // workspace: per-ray view-branch bias [vb_cap rays][128]
   long long vb_cap = 0;
+  NerfPpMaps* pp_maps = nullptr;   // tensor maps over wstream_pp
   // R2L
   int n_points = 0, n_blocks = 0, sigmoid_out = 1, outer_skip = 1;
   float b_tail[3] = {0.f, 0.f, 0.f};
@@ -154,9 +155,35 @@ struct Mlp {
 // 1.74 GHz vs 1.65 GHz), so the single-CTA kernel stays the default until the pair kernel's spare shared memory is
 // used to overlap the epilogue.
 // R2L_NERF_PP=0 selects the single-CTA chasing NeRF kernel (mlp_nerf.cu) instead of the CTA-pair ping-pong kernel.
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static int encode_rows_map(CUtensorMap* out, void* base, size_t bytes, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    R2L_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+    if (sym == nullptr || q != cudaDriverEntryPointSuccess)
+      return fail(R2L_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  const cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(bytes / 512)};
+  const cuuint64_t strides[1] = {512};
+  const cuuint32_t box[2] = {256, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(R2L_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return R2L_OK;
+}
+
+// NeRF handles use the CTA-pair ping-pong kernel (mlp_nerf_pp.cu: 41.6 vs 44.8 ms per 400x400 frame on B200);
+// R2L_NERF_PP=0 selects the single-CTA chasing kernel (mlp_nerf.cu) instead.
 static int nerf_pp_default() {
   const char* e = getenv("R2L_NERF_PP");
-  return (e != nullptr && e[0] == '1') ? 1 : 0;
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
 }
 static int pair_mode_default() {
   const char* e = getenv("R2L_PAIR");
@@ -201,6 +228,7 @@ static void destroy(Mlp* m) {
   if (m->vb_ws) cudaFree(m->vb_ws);
   if (m->aux) cudaFree(m->aux);
   if (m->dbg_host) cudaFreeHost(m->dbg_host);
+  delete m->pp_maps;
   delete m;
 }
 
@@ -595,6 +623,11 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
     if (e2 == cudaSuccess)
       e2 = cudaMemcpyAsync(m->view_tab + 128 * 27, views_b, 128 * 4, cudaMemcpyDeviceToDevice, st);
     if (e2 != cudaSuccess) return cleanup(fail(R2L_ERR_CUDA, "r2l_nerf_create: %s", cudaGetErrorString(e2)));
+    m->pp_maps = new NerfPpMaps();
+    rc = encode_rows_map(&m->pp_maps->m16, m->wstream_pp, elems_pp * 2, 32);
+    if (rc == R2L_OK) rc = encode_rows_map(&m->pp_maps->m8, m->wstream_pp, elems_pp * 2, 16);
+    if (rc == R2L_OK) rc = encode_rows_map(&m->pp_maps->m4, m->wstream_pp, elems_pp * 2, 8);
+    if (rc != R2L_OK) return cleanup(rc);
   }
   cudaError_t e = cudaMemcpyAsync(m->aux + kNerfAuxAlphaW, alpha_w, 256 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxRgbW, rgb_w, 384 * 4, cudaMemcpyDeviceToDevice, st);
@@ -624,7 +657,6 @@ static int nerf_run(Mlp* m, NerfParams& p, cudaStream_t st) {
   p.n_tiles = static_cast<int>(n_tiles);
   p.dbg = m->dbg_dev;
   if (m->nerf_pp) {
-    { const char* e = getenv("R2L_PROF_MODE"); if (e != nullptr) p.prof_mode = atoi(e); }
     // per-ray view bias into the handle's workspace (grown on demand: the only allocation a forward can make),
     // then the ping-pong kernel: units of 4 tiles (2 per CTA of a pair)
     const bool emb = p.embedded != nullptr;
@@ -645,7 +677,7 @@ static int nerf_run(Mlp* m, NerfParams& p, cudaStream_t st) {
     const long long n_units = (n_tiles + 3) / 4;
     const long long max_pairs = sm_count() / 2;
     const int grid = static_cast<int>(2 * (n_units < max_pairs ? n_units : max_pairs));
-    return nerf_mlp_pp_launch(m->bf16, p, grid, st);
+    return nerf_mlp_pp_launch(m->bf16, p, *m->pp_maps, grid, st);
   }
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   return nerf_mlp_launch(m->bf16, p, grid, st);

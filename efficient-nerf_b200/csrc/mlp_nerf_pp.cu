@@ -20,6 +20,8 @@
 //   * TWO issuer threads, one per tile, running concurrently: a thread needs ~56 cycles per tcgen05.mma and ~100 per
 //     tcgen05.commit / mbarrier wait (scratch/ubench/mmaissue.cu), ~2600 cycles per tile-layer (measured) — more than
 //     the 2176 tensor cycles, so one thread cannot feed the pipe.  Both walk the SAME stage sequence, T1 behind T0.
+//   * The peer CTA's half stages arrive by cp.async.bulk.tensor...cta_group::2, which may signal the LEADER's
+//     mbarrier: the issuers see both halves of a stage on one barrier, no relay thread.
 //   * ONE point block P: the encoder warps re-encode a tile's points right before each of its two uses (steps 0 and
 //     5) — sin/cos of 128 points is ~2 k issue slots, the encoder warps are otherwise idle.
 //   * The view branch is a per-ray fp32 bias vb (computed by nerf_view_bias_kernel into a caller workspace) added in
@@ -39,6 +41,19 @@ constexpr int kPpMmaWarp0 = 13;   // leader: issuer of tile T0; peer: relays wei
 constexpr int kPpMmaWarp1 = 14;   // leader: issuer of tile T1
 constexpr int kPpRing = 4;
 constexpr int kPpBiasRing = 2;
+// The peer CTA's half stages are copied with cp.async.bulk.tensor...cta_group::2, whose completion may be signalled
+// on the LEADER's mbarrier (a plain cp.async.bulk with a remote barrier is a launch failure: tried), so the leader's
+// issuers see both halves on one barrier with no relay hop (~450 cycles off the refill latency).
+constexpr bool kPpDirect = true;
+#ifndef R2L_PP_TURNS
+#define R2L_PP_TURNS 0
+#endif
+// 1: the two issuers take turns, one tile-layer each (strict T0, T1, T0, ... alternation on the tensor pipe).  Measured
+// SLOWER (32.0 vs 29.8 ms per 160000x192 pass): with strict alternation a slot is refilled only ~2900 cycles after
+// the leading tile started its layer, and the refill latency (~2400 cycles) then paces the whole loop; left free, the
+// issuers settle ~1200 cycles apart, weights are prefetched a layer ahead and the tensor pipe idles only between
+// layers (~20 %, in-kernel timeline: scratch/prof_pp.py, R2L_PROF_MODE=5).
+constexpr bool kPpTurns = R2L_PP_TURNS != 0;
 constexpr uint32_t kPpStageB = kStageBytes / 2;       // 16 KiB: this CTA's N-half of a K=64 stage
 constexpr uint32_t kPpBiasB = kBiasStageBytes / 2;    // 4 KiB
 constexpr uint32_t kPpLbo256 = 128 * 16;              // 128 B-rows per CTA (N = 256)
@@ -53,7 +68,7 @@ constexpr int kPpOffAlphaW = kPpOffBiasRing + kPpBiasRing * kPpBiasB;   // 256 f
 constexpr int kPpOffRgbW = kPpOffAlphaW + 256 * 4;                    // 3*128 floats
 constexpr int kPpOffPart = kPpOffRgbW + 384 * 4;                      // 128 x float4
 constexpr int kPpOffBars = kPpOffPart + 128 * 16;
-constexpr int kPpNumBars = 2 * kPpRing + 2 * kPpBiasRing + 2 + 2 + 2 + 2;
+constexpr int kPpNumBars = 2 * kPpRing + 2 * kPpBiasRing + 2 + 2 + 2 + 2 + 2;
 constexpr int kPpOffTmem = kPpOffBars + kPpNumBars * 8;
 constexpr int kPpSmemBytes = kPpOffTmem + 16;
 static_assert(kPpSmemBytes <= 227 * 1024, "NeRF ping-pong kernel shared memory exceeds 227 KiB");
@@ -62,7 +77,8 @@ static_assert(kPpOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
 __device__ __forceinline__ int pp_main_stages(int step) { return step == 0 ? 1 : (step == 5 ? 5 : 4); }
 
 template <bool BF16>
-__global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfParams p) {
+__global__ void __launch_bounds__(kPpThreads, 1)
+nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const sA = smem + kPpOffA;
   uint8_t* const sP = smem + kPpOffP;
@@ -81,6 +97,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
   uint64_t* const a_done = d_full + 2;              // [tile]: leader; 16 epilogue warps are done with the tile's layer
   uint64_t* const p_ready = a_done + 2;             // [tile]: leader; 8 encoder warps have written P for tile t
   uint64_t* const p_free = p_ready + 2;             // [tile]: tile t's MMAs that read P have completed (commit, both CTAs)
+  uint64_t* const turn = p_free + 2;                // [tile]: leader; the other issuer has issued its tile-layer
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + kPpOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -97,11 +114,11 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
   write_ones_block<BF16>(sOnes, threadIdx.x, kPpThreads);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPpRing; ++i) {
-      mbar_init(&w_full[i], rank == 0 ? 2 : 1);
+      mbar_init(&w_full[i], (rank == 0 && !kPpDirect) ? 2 : 1);
       mbar_init(&w_empty[i], 2);
     }
     for (int i = 0; i < kPpBiasRing; ++i) {
-      mbar_init(&b_full[i], rank == 0 ? 2 : 1);
+      mbar_init(&b_full[i], (rank == 0 && !kPpDirect) ? 2 : 1);
       mbar_init(&b_empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
@@ -109,6 +126,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
       mbar_init(&a_done[i], 16);
       mbar_init(&p_ready[i], 8);
       mbar_init(&p_free[i], 1);
+      mbar_init(&turn[i], 1);
     }
     mbar_fence_init();
   }
@@ -119,6 +137,18 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
   cluster_sync_all();   // the peer's barriers are initialised before anybody signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // debug timeline (r2l_nerf_profile with R2L_PROF_MODE=5): CTA 0 records (tag, clock) pairs for its 4th unit
+  const bool tracing = p.prof != nullptr && p.prof_mode == 5 && blockIdx.x == 0;
+  // (the prof buffer must hold 3 x 400 + 8 int64 in this mode; each role appends to its own region, no atomics)
+  int n_trace = 0;
+  auto trace = [&](uint32_t it_, long long tag) {
+    if (tracing && it_ == 3 && n_trace < 200) {
+      const int role = (tag / 100000 >= 3) ? 2 : static_cast<int>((tag / 10000) % 10);
+      p.prof[8 + role * 400 + 2 * n_trace] = tag;
+      p.prof[9 + role * 400 + 2 * n_trace] = clock64();
+      ++n_trace;
+    }
+  };
 
   // ===================== MMA issuer of tile t (leader CTA; one thread per tile) =====================
   // Both issuers walk the same stage sequence (g, gb).  Every barrier wait below is unambiguous although only the
@@ -136,7 +166,8 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
     uint32_t g = 0, gb = 0;        // position in the weight / bias stage streams
     uint32_t par_done = 0;         // parity of the next a_done[t] phase
     uint32_t par_p = 0;            // parity of the next p_ready[t] phase
-    const bool prof = p.prof != nullptr;
+    uint32_t n_turn = 0;           // turns taken so far
+    const bool prof = p.prof != nullptr && p.prof_mode != 5;
     long long t_a = 0, t_w = 0, t_p = 0, t_b = 0;
     const long long t_start = prof ? clock64() : 0;
     auto next_w = [&]() -> uint32_t {
@@ -157,6 +188,26 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
     uint32_t it = 0;
     for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
       for (int step = 0; step < 10; ++step) {
+        // Everything that does not depend on the tile's previous epilogue is waited for FIRST (bias stage, first
+        // weight stage, point block): the issuer is idle until a_done anyway, and the ~100 cycles of each barrier wait
+        // then stay off the a_done -> first MMA path.
+        uint32_t bslot = 0;
+        if (step < 9) {
+          bslot = gb % kPpBiasRing;
+          const long long c0 = prof ? clock64() : 0;
+          mbar_wait(&b_full[bslot], (gb / kPpBiasRing) & 1, p.dbg, 240 + bslot + 30 * t);
+          if (prof) t_b += clock64() - c0;
+        }
+        if (step == 0 || step == 5) wait_p();
+        uint32_t slot = next_w();
+        if (kPpTurns && !(t == 0 && n_turn == 0)) {
+          // my turn: the other issuer has issued all MMAs of its tile-layer (keeps the two tiles' MMA phases apart on
+          // the in-order tensor pipe, so a tile's accumulator completes ~2176 cycles after its first MMA, not ~4000)
+          const long long c0 = prof ? clock64() : 0;
+          mbar_wait(&turn[t], (t == 0 ? n_turn - 1 : n_turn) & 1u, p.dbg, 270 + t);
+          if (prof) t_w += clock64() - c0;
+        }
+        ++n_turn;
         // the tile's previous epilogue is done: A[t] holds this layer's input and D[t] may be overwritten
         if (!(it == 0 && step == 0)) {
           const long long c0 = prof ? clock64() : 0;
@@ -164,31 +215,30 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
           if (prof) t_a += clock64() - c0;
           par_done ^= 1u;
         }
+        trace(it, 200000 + t * 10000 + step * 100);   // a_done seen: the step may start
         tc_fence_after_sync();
         if (step < 9) {
           // ---- bias step (fresh accumulator), [point-block stage], 4 activation stages
-          {
-            const uint32_t slot = gb % kPpBiasRing;
-            const long long c0 = prof ? clock64() : 0;
-            mbar_wait(&b_full[slot], (gb / kPpBiasRing) & 1, p.dbg, 240 + slot + 30 * t);
-            if (prof) t_b += clock64() - c0;
-            tc_fence_after_sync();
-            issue_bias_stage<true>(d, aOnes, aBiasRing + slot * kPpBiasB, kPpLbo256, idesc256, true);
-            umma_commit_pair(&b_empty[slot]);
-            ++gb;
-          }
+          issue_bias_stage<true>(d, aOnes, aBiasRing + bslot * kPpBiasB, kPpLbo256, idesc256, true);
+          umma_commit_pair(&b_empty[bslot]);
+          ++gb;
           if (step == 0 || step == 5) {
-            wait_p();
-            const uint32_t slot = next_w();
+            trace(it, 100000 + t * 10000 + step * 100 + 9);
             issue_stage<4, true>(d, aP, aRing + slot * kPpStageB, kPpLbo256, idesc256, false);
+            if (kPpTurns && step == 0) mbar_arrive(&turn[1 - t]);
             umma_commit_pair(&w_empty[slot]);
             umma_commit_pair(&p_free[t]);
             ++g;
+            if (step == 5) slot = next_w();
           }
           if (step > 0) {
             for (int st = 0; st < 4; ++st) {
-              const uint32_t slot = next_w();
+              if (st > 0) slot = next_w();
+              trace(it, 100000 + t * 10000 + step * 100 + st);
               issue_stage<4, true>(d, aA + st * kGroupBytes, aRing + slot * kPpStageB, kPpLbo256, idesc256, false);
+              // step 5 has 5 stages for a 4-slot ring: its last stage can only be loaded after the OTHER tile has
+              // used the first one, so the turn is passed one stage early there
+              if (kPpTurns && st == (step == 5 ? 2 : 3)) mbar_arrive(&turn[1 - t]);
               umma_commit_pair(&w_empty[slot]);
               ++g;
             }
@@ -196,8 +246,9 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
         } else {
           // ---- step 9: view branch, N = 128 (per-ray bias added by the epilogue)
           for (int st = 0; st < 4; ++st) {
-            const uint32_t slot = next_w();
+            if (st > 0) slot = next_w();
             issue_stage<4, true>(d, aA + st * kGroupBytes, aRing + slot * kPpStageB, kPpLbo128, idesc128, st == 0);
+            if (kPpTurns && st == 3) mbar_arrive(&turn[1 - t]);
             umma_commit_pair(&w_empty[slot]);
             ++g;
           }
@@ -229,15 +280,38 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
         const uint32_t half = full_bytes / 2;
         const uint32_t slot = g % kPpRing;
         mbar_wait(&w_empty[slot], ((g / kPpRing) & 1) ^ 1, p.dbg, 100 + slot, 8);
-        mbar_expect_tx(&w_full[slot], half);
-        bulk_g2s(sRing + slot * kPpStageB, src + rank * half, half, &w_full[slot]);
+        if (kPpDirect) {
+          // the peer's half stage completes its bytes directly on the leader's barrier: no relay hop
+          if (rank == 0) {
+            mbar_expect_tx(&w_full[slot], full_bytes);
+            bulk_g2s(sRing + slot * kPpStageB, src, half, &w_full[slot]);
+          } else {
+            // rows of 512 bytes: row index of this half stage in the stream
+            const int row = static_cast<int>((src + half - p.wstream) >> 9);
+            tma2d_g2s_pair_bar(sRing + slot * kPpStageB, half == kPpStageB ? &maps.m16 : &maps.m8, 0, row,
+                               mapa_u32(&w_full[slot], 0));
+          }
+        } else {
+          mbar_expect_tx(&w_full[slot], half);
+          bulk_g2s(sRing + slot * kPpStageB, src + rank * half, half, &w_full[slot]);
+        }
         ++g;
       };
       auto push_bias = [&](const uint8_t* src) {
         const uint32_t slot = gb % kPpBiasRing;
         mbar_wait(&b_empty[slot], ((gb / kPpBiasRing) & 1) ^ 1, p.dbg, 120 + slot, 8);
-        mbar_expect_tx(&b_full[slot], kPpBiasB);
-        bulk_g2s(sBiasRing + slot * kPpBiasB, src + rank * kPpBiasB, kPpBiasB, &b_full[slot]);
+        if (kPpDirect) {
+          if (rank == 0) {
+            mbar_expect_tx(&b_full[slot], 2 * kPpBiasB);
+            bulk_g2s(sBiasRing + slot * kPpBiasB, src, kPpBiasB, &b_full[slot]);
+          } else {
+            const int row = static_cast<int>((src + kPpBiasB - p.wstream) >> 9);
+            tma2d_g2s_pair_bar(sBiasRing + slot * kPpBiasB, &maps.m4, 0, row, mapa_u32(&b_full[slot], 0));
+          }
+        } else {
+          mbar_expect_tx(&b_full[slot], kPpBiasB);
+          bulk_g2s(sBiasRing + slot * kPpBiasB, src + rank * kPpBiasB, kPpBiasB, &b_full[slot]);
+        }
         ++gb;
       };
       for (int unit = unit0; unit < n_units; unit += unit_step) {
@@ -259,7 +333,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
   } else if (warp == kPpMmaWarp0) {
     if (rank != 0) {
       // ===================== peer CTA: relay "my half stage has landed" to the leader's barriers =====================
-      if (lane == 0) {
+      if (lane == 0 && !kPpDirect) {
         uint32_t g = 0, gb = 0;
         for (int unit = unit0; unit < n_units; unit += unit_step) {
           for (int step = 0; step < 10; ++step) {
@@ -335,7 +409,8 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
     const int wg = warp >> 2;                       // owns the 32-column pieces wg, wg+2, wg+4, wg+6
     const int row = (warp & 3) * 32 + lane;         // tile row == TMEM lane
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
+    const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0 && p.prof_mode != 5;
+    uint32_t eit = 0;
     long long t_d = 0;
     const long long t_start = prof ? clock64() : 0;
     uint32_t par_d = 0;   // bit tile: parity of the next d_full phase
@@ -364,13 +439,14 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
       tmem_ld_wait();
       f(c0 + 192, vb);
     };
-    for (int unit = unit0; unit < n_units; unit += unit_step) {
+    for (int unit = unit0; unit < n_units; unit += unit_step, ++eit) {
       float sigma_part[2] = {0.0f, 0.0f};
       for (int step = 0; step < 10; ++step) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           uint8_t* const a_row = sA + t * kABufBytes + row * 16;
           wait_d(t, 300 + step * 2 + t);
+          if (threadIdx.x == 0) trace(eit, 300000 + t * 10000 + step * 100);   // epilogue of (t, step) starts
           if (step < 9) {
             if (step == 7) {
               float sp = 0.0f;
@@ -390,6 +466,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) nerf_mlp_pp_kernel(const NerfPa
               });
             }
             warp_arrive<true>(&a_done[t], lane);
+            if (threadIdx.x == 0) trace(eit, 400000 + t * 10000 + step * 100);   // ... and has ended (warp 0)
           } else {
             // step 9: view branch (N = 128 -> D[t] columns [0,128)); this warp owns columns 32*wg and 64 + 32*wg
             const long long tile = 4LL * unit + 2 * t + rank;
@@ -518,7 +595,7 @@ nerf_view_bias_kernel(long long n_rays, const float* __restrict__ viewdirs, long
 }
 
 template <bool BF16>
-int launch_nerf_pp(const NerfParams& p, int grid, cudaStream_t st) {
+int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, int grid, cudaStream_t st) {
   R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -532,13 +609,13 @@ int launch_nerf_pp(const NerfParams& p, int grid, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16>, p));
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16>, p, maps));
   return R2L_OK;
 }
 
 // grid must be even (CTA pairs); weights packed in the pair layout WITHOUT the view stage (mlp_api.cu)
-int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st) {
-  return bf16 ? launch_nerf_pp<true>(p, grid, st) : launch_nerf_pp<false>(p, grid, st);
+int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, int grid, cudaStream_t st) {
+  return bf16 ? launch_nerf_pp<true>(p, maps, grid, st) : launch_nerf_pp<false>(p, maps, grid, st);
 }
 
 int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,

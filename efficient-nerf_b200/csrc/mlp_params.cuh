@@ -1,5 +1,6 @@
 // Kernel parameter blocks and launcher prototypes shared by mlp_api.cu, mlp_nerf.cu, mlp_r2l.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,6 +31,12 @@ struct NerfParams {
   const float* vb;          // ping-pong kernel only: per-ray view-branch bias [n_rays][128] (nerf_view_bias_kernel)
 };
 
+// Tensor maps over the ping-pong kernel's stage stream seen as rows of 256 x 16-bit (512 bytes): boxes of 32 / 16 / 8
+// rows = one CTA's half of a K=64 stage (N 256), of a K=64 stage (N 128), of a bias stage
+struct NerfPpMaps {
+  CUtensorMap m16, m8, m4;
+};
+
 struct R2lParams {
   const uint8_t* wstream;
   const float* w_tail;      // [3][256]
@@ -54,7 +61,7 @@ struct R2lParams {
 int nerf_mlp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st);
 int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, int grid, cudaStream_t st);
 // CTA-pair "ping-pong" NeRF kernel (mlp_nerf_pp.cu): grid even, pair-layout stream without the view stage
-int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st);
+int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, int grid, cudaStream_t st);
 int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,
                           const float* wvd, const float* bv, float* vb, cudaStream_t st);
 

@@ -152,6 +152,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// 2-D tiled tensor copy global -> this CTA's shared memory whose completion bytes are signalled on an mbarrier of
+// EITHER CTA of the pair (.cta_group::2; address from mapa_u32).  tmap: CUtensorMap in kernel-parameter space.
+__device__ __forceinline__ void tma2d_g2s_pair_bar(void* smem_dst, const void* tmap, int c0, int c1,
+                                                   uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], "
+      "[%4];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+      : "memory");
+}
+
 // ------------------------------- TMEM --------------------------------------------
 // Whole-warp collective.  Writes the TMEM base address to *smem_slot.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {

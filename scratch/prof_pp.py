@@ -19,9 +19,23 @@ with torch.no_grad():
         L.call("r2l_nerf_profile", h.h, N, S, L.ptr(ro), ro.stride(0), L.ptr(rd), rd.stride(0), L.ptr(vd), vd.stride(0),
                L.ptr(z), L.ptr(raw), L.ptr(prof), L.stream_ptr())
     torch.cuda.synchronize()
+    import os
     p = prof.double().cpu()[0::2]   # leader CTAs
     tot = p[:, 0].mean()
     import os
+    if os.environ.get("R2L_PROF_MODE") == "5":
+        prof = torch.zeros(512, 8, dtype=torch.int64, device="cuda")
+        L.call("r2l_nerf_profile", h.h, N, S, L.ptr(ro), ro.stride(0), L.ptr(rd), rd.stride(0), L.ptr(vd), vd.stride(0),
+               L.ptr(z), L.ptr(raw), L.ptr(prof), L.stream_ptr())
+        torch.cuda.synchronize()
+        flat = prof.cpu().reshape(-1)
+        ev = [(int(flat[9 + 2 * i]), int(flat[8 + 2 * i])) for i in range(600) if int(flat[8 + 2 * i]) != 0]
+        ev.sort(); t0 = ev[0][0]
+        kinds = {1: "issue", 2: "a_done", 3: "epi-start", 4: "epi-end"}
+        for tm, tag in ev:
+            k, t, step, st = tag // 100000, (tag // 10000) % 10, (tag // 100) % 100, tag % 100
+            print(f"{tm - t0:7d}  T{t} step {step} {kinds[k]}" + (f" stage {'P' if st == 9 else st}" if k == 1 else ""))
+        sys.exit(0)
     if os.environ.get("R2L_PROF_MODE") == "4":
         pa = prof.double().cpu()
         n_tl = 160000 * 192 / 128 / 148 * 10
