@@ -291,6 +291,7 @@ def main():
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         mev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         launches0 = E._lib.launch_count
+        kernels0 = E._lib.kernel_launches()
         barrier()
         sampler.mark()
         t_wall0 = time.perf_counter()
@@ -302,6 +303,7 @@ def main():
         barrier()
         t_wall = time.perf_counter() - t_wall0
         launches = E._lib.launch_count - launches0
+        kernels = E._lib.kernel_launches() - kernels0
         clocks = sampler.stop() if rank == 0 else None
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         mlp_ms = sum(a.elapsed_time(b) for a, b in mev) / steps if args.workload == "r2l" else None
@@ -341,7 +343,7 @@ def main():
                 "wall_ms_per_step_incl_flush": t_wall / steps * 1e3,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 48,
                         "d2h_bytes_per_step": RAYS * 3 * 4, "ms_per_step": e2e_ms / e2e_steps},
-                "gpu_launches": int(launches), "abi_calls": int(launches),
+                "gpu_launches": int(kernels), "abi_calls": int(launches),
                 "clocks": clocks}
         flops = FLOP_PER_RAY[args.workload] * RAYS
         if args.workload == "r2l":

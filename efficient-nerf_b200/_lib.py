@@ -21,6 +21,7 @@ _c_vp = ctypes.c_void_p
 SIGNATURES = {
     "r2l_last_error": [],
     "r2l_abi_version": [],
+    "r2l_kernel_launches": [],
     "r2l_get_rays": [_c_int, _c_int, _c_dbl, _c_f32p, _c_f32p, _c_f32p, _c_vp],
     "r2l_ndc_rays": [_c_ll, _c_int, _c_int, _c_dbl, _c_dbl, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_vp],
     "r2l_normalize_dirs": [_c_ll, _c_f32p, _c_ll, _c_f32p, _c_vp],
@@ -55,7 +56,7 @@ SIGNATURES = {
     "r2l_tc_gemm_probe": [_c_int, _c_int, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_int, _c_vp],
     "r2l_tc_gemm_probe_pair": [_c_int, _c_int, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_vp],
 }
-_RESTYPES = {"r2l_last_error": ctypes.c_char_p}
+_RESTYPES = {"r2l_last_error": ctypes.c_char_p, "r2l_kernel_launches": ctypes.c_longlong}
 
 _lock = threading.Lock()
 _lib = None
@@ -94,6 +95,11 @@ def call(name, *args):
     lib = load()
     launch_count += 1
     check(getattr(lib, name)(*args), name)
+
+
+def kernel_launches():
+    """CUDA kernels launched by the library so far (counted inside the library, not ABI calls)."""
+    return int(load().r2l_kernel_launches())
 
 
 def require_cuda():

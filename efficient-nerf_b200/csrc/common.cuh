@@ -32,8 +32,10 @@ int fail(int code, const char* fmt, ...);
                          __FILE__, __LINE__);                                                       \
   } while (0)
 
+// every kernel launch of the library is followed by one of these: it also counts the launch (r2l_kernel_launches)
 #define R2L_LAUNCH_CHECK()                                                                          \
   do {                                                                                              \
+    ::r2l::count_launch();                                                                          \
     cudaError_t _e = cudaGetLastError();                                                            \
     if (_e != cudaSuccess)                                                                          \
       return ::r2l::fail(::r2l::R2L_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                   \
@@ -43,5 +45,6 @@ int fail(int code, const char* fmt, ...);
 static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 int sm_count();
+void count_launch();
 
 }  // namespace r2l

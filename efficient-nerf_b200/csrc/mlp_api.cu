@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -28,6 +29,9 @@ int fail(int code, const char* fmt, ...) {
   g_last_error = buf;
   return code;
 }
+static std::atomic<long long> g_kernel_launches{0};
+void count_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -418,7 +422,10 @@ using namespace r2l;
 extern "C" {
 
 const char* r2l_last_error(void) { return g_last_error.c_str(); }
-int r2l_abi_version(void) { return 2; }
+int r2l_abi_version(void) { return 3; }
+
+// Number of CUDA kernels this library has launched so far in this process (all entry points, all streams).
+long long r2l_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 // D [128, N] fp32 = A [128, K] fp32 (rounded to 16 bit) x W [N, K]^T fp32 (rounded to 16 bit).
 // K multiple of 32, <= 320; N multiple of 32, 32..256.  dtype: 0 = fp16, 1 = bf16.
@@ -571,6 +578,7 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
   }
   if (rc == R2L_OK) {
     pack_view_stage_kernel<<<(128 * 32 + 255) / 256, 256, 0, st>>>(views_w, 283, views_b, dst + off, m->bf16 ? 1 : 0);
+    count_launch();
     if (cudaGetLastError() != cudaSuccess) rc = fail(R2L_ERR_CUDA, "r2l_nerf_create: pack_view_stage launch failed");
     off += 128ull * 32;
   }

@@ -610,6 +610,7 @@ int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, int grid, cudaSt
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16>, p, maps));
+  count_launch();
   return R2L_OK;
 }
 

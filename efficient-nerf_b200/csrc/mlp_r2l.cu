@@ -463,6 +463,7 @@ int launch_r2l(const R2lParams& p, int grid, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   R2L_CUDA(cudaLaunchKernelEx(&cfg, r2l_mlp_kernel<BF16, PAIR>, p));
+  count_launch();
   return R2L_OK;
 }
 

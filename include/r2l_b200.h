@@ -25,6 +25,8 @@ extern "C" {
 
 const char* r2l_last_error(void);
 int r2l_abi_version(void);
+/* Number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches). */
+long long r2l_kernel_launches(void);
 
 /* ---- rays --------------------------------------------------------------------------------- */
 
