@@ -40,9 +40,9 @@ H = W = 400
 RAYS = H * W
 FLOP_PER_RAY = {"r2l": 11789824, "nerf": 303824896}   # BASELINE.md §2 (unpadded MACs x2)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1b_ncu_r2l_mlp.txt; profiles/r1b_ncu_nerf_mlp.txt: coarse + fine launch of one frame).  The MLP
+# (profiles/r1c_ncu_r2l_mlp.txt; profiles/r1c_ncu_nerf_mlp.txt: coarse + fine launch of one frame).  The MLP
 # kernels are tensor-bound: the traffic is the packed weights once (L2 resident afterwards) + points in, rgb / raw out.
-NCU_TRAFFIC_BYTES = {"r2l": 43340288 + 216320, "nerf": (50719744 + 112569344) + (137016576 + 437029376)}
+NCU_TRAFFIC_BYTES = {"r2l": 43346176 + 115456, "nerf": (132048896 + 124964864) + (218109184 + 442763776)}
 
 
 def dist_env():
@@ -306,6 +306,8 @@ def main():
         kernels = E._lib.kernel_launches() - kernels0
         clocks = sampler.stop() if rank == 0 else None
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        if os.environ.get("BENCH_VERBOSE"):
+            print("per-step ms:", " ".join(f"{a.elapsed_time(b):.2f}" for a, b in ev[:40]), file=sys.stderr)
         mlp_ms = sum(a.elapsed_time(b) for a, b in mev) / steps if args.workload == "r2l" else None
 
         # ---------------- end-to-end timing through the public API with host buffers
@@ -353,15 +355,15 @@ def main():
                                 "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step; "
                                                f"burst {peaks['tf_burst']})",
                                 "kernel_ms": mlp_ms, "algorithmic_flop_per_launch": flops,
-                                "traffic": NCU_TRAFFIC_BYTES["r2l"], "traffic_unit": "B/launch (ncu, profiles/r1b)"}
+                                "traffic": NCU_TRAFFIC_BYTES["r2l"], "traffic_unit": "B/launch (ncu, profiles/r1c)"}
         else:
             ach = flops / (dev_ms / steps * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "nerf_mlp_kernel (coarse+fine, whole frame)",
+            line["roofline"] = {"bound": "tensor", "kernel": "nerf_mlp_pp_kernel (coarse+fine, whole frame)",
                                 "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                                 "frac": ach / peaks["tf_sust"], "peak_source": f"{peaks['src']} bf16_tflops_sustained",
                                 "kernel_ms": dev_ms / steps, "algorithmic_flop_per_launch": flops,
                                 "traffic": NCU_TRAFFIC_BYTES["nerf"],
-                                "traffic_unit": "B/frame = coarse + fine launch (ncu, profiles/r1b)"}
+                                "traffic_unit": "B/frame = coarse + fine launch (ncu, profiles/r1c)"}
         if world == 1 and not args.no_cpu_baseline:
             sample = 16384 if args.workload == "r2l" else 1024
             line["cpu_baseline"], _ = cpu_reference(O, args.workload, 2, 1, sample)
