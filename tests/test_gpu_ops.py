@@ -149,7 +149,7 @@ def test_raw2outputs_golden_and_nan_propagation(E, golden):
     assert torch.isnan(out[1]).sum().item() == 1  # the empty ray: disp = 1/max(1e-10, 0/0) = NaN like torch.max
 
 
-@pytest.mark.parametrize("S", [2, 31, 64, 128, 192, 257])
+@pytest.mark.parametrize("S", [2, 31, 64, 100, 128, 160, 192, 200, 256, 257])   # every blocked-kernel K, full and ragged; 257: generic kernel
 def test_raw2outputs_vs_oracle(E, O, S):
     torch.manual_seed(S)
     N = 513
