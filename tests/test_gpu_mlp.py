@@ -144,6 +144,41 @@ def test_nerf_fused_encode_matches_api_path(E, O):
     assert maxabs(raw, ref) < 2e-3
 
 
+def test_nerf_pingpong_kernel_vs_single_cta_kernel(E, O, monkeypatch):
+    """The CTA-pair ping-pong kernel (default) against the single-CTA chasing kernel (R2L_NERF_PP=0) on the same
+    inputs: same 16-bit operands, fp32 accumulation, so they agree far inside the 2e-3 gate (the view branch is
+    evaluated in fp32 instead of 16 bit in the ping-pong kernel); ragged sizes exercise partial units / tiles.
+    At full-frame size the ping-pong kernel must be bit-reproducible run to run (two concurrent issuer threads and a
+    shared weight ring: a protocol race would show up as run-to-run differences)."""
+    sdc, _ = O.nerf_state_dicts(0)
+    monkeypatch.setenv("R2L_NERF_PP", "0")
+    single = load_nerf(E, sdc, "fp16")
+    h0 = single.packed_handle()
+    monkeypatch.setenv("R2L_NERF_PP", "1")
+    pp = load_nerf(E, sdc, "fp16")
+    h1 = pp.packed_handle()
+    assert h0 is not h1
+    c2w = O.pose_spherical(10., -30., 4.)[:3, :4].cuda()
+    ro, rd = E.get_rays(400, 400, O.LEGO["focal"], c2w)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    vd = E.normalize_dirs(rd)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        for N, S in ((1, 64), (3, 43), (517, 64), (2049, 192)):   # 1 row short of / beyond unit boundaries
+            z = torch.sort(torch.rand(N, S, device="cuda") * 4 + 2, -1)[0]
+            a = single.forward_samples(ro[:N], rd[:N], vd[:N], z)
+            b = pp.forward_samples(ro[:N], rd[:N], vd[:N], z)
+            assert a.shape == b.shape == (N, S, 4)
+            assert maxabs(a, b) < 5e-4, (N, S, maxabs(a, b))
+        N, S = 160000, 192
+        z = torch.sort(torch.rand(N, S, device="cuda") * 4 + 2, -1)[0]
+        ref = pp.forward_samples(ro, rd, vd, z).clone()
+        assert bool(torch.isfinite(ref).all())
+        for _ in range(3):
+            assert torch.equal(pp.forward_samples(ro, rd, vd, z), ref)
+        assert maxabs(single.forward_samples(ro, rd, vd, z), ref) < 5e-4
+
+
 def render_golden(E, O, golden, name, precision):
     g = golden(name)
     sdc, sdf = O.nerf_state_dicts(0)
