@@ -19,6 +19,7 @@ import torch
 
 from . import _lib
 from .nerf_raybased import NeRF
+from .run_nerf_raybased_helpers import _dev  # noqa: E402
 from .run_nerf_raybased_helpers import (get_rays, ndc_rays, normalize_dirs, raw2outputs, sample_pdf, merge_sorted,
                                         _host_noise, _make_u)
 
@@ -215,3 +216,57 @@ def render_r2l(model, point_sampler, c2w, positional_embedder=None):
     if positional_embedder is None:
         raise ValueError("positional_embedder is required for the non-fused path")
     return model(positional_embedder(pts))
+
+
+def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                model_name="nerf", point_sampler=None, positional_embedder=None, learn_depth=False):
+    """The test loop around the hot path (main.py:189-400): render every pose, stack the frames, and — with ground
+    truth — the reference's per-frame metrics, computed on the device (`metrics.image_errors`: one error/MSE pass
+    and one SSIM pass for the whole stack instead of a host round trip per frame).
+
+    model_name == 'nerf' renders through `render` (main.py:283-290); anything else is the R2L branch
+    `model(positional_embedder(point_sampler.sample_test(c2w)))` (main.py:292-321).  Returns (rgbs [N,H,W,3],
+    disps, misc) with misc['test_loss', 'test_psnr', 'test_psnr_v2', 'test_ssim', 'errors'] as in main.py:384-394.
+    Out of scope: PNG writing (`savedir` must be None), LPIPS and FLIP (misc has no such keys),
+    `given_render_path_rays`."""
+    from . import metrics
+    if savedir is not None:
+        raise NotImplementedError("render_path: image files are written by the caller (PNG I/O is out of scope)")
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = int(H / render_factor), int(W / render_factor), focal / render_factor
+    net = render_kwargs["network_fn"]
+    was_training = getattr(net, "training", False)
+    if hasattr(net, "eval"):
+        net.eval()
+    rgbs, disps = [], []
+    with torch.no_grad():
+        for c2w in render_poses:
+            c2w = _lib.as_f32_cuda(c2w, name="c2w")[:3, :4]
+            if model_name in ("nerf",):
+                rgb, disp, acc, _ = render(H, W, focal, chunk=chunk, c2w=c2w, **render_kwargs)
+            else:
+                if point_sampler is None:
+                    raise ValueError("render_path: the R2L branch needs point_sampler")
+                out = render_r2l(net, point_sampler, c2w, positional_embedder)
+                rgb = out[:, :3] if learn_depth else out
+                rgb = rgb.reshape(H, W, 3)
+                disp = rgb   # placeholder, as in the reference (main.py:321)
+            rgbs.append(rgb)
+            disps.append(disp)
+        rgbs = torch.stack(rgbs, 0) if rgbs else torch.zeros((0, H, W, 3), device=_dev())
+        disps = torch.stack(disps, 0) if disps else torch.zeros((0, H, W), device=_dev())
+        misc = {}
+        if gt_imgs is not None and rgbs.shape[0] > 0:
+            gt = _lib.as_f32_cuda(gt_imgs, rgbs.device, "gt_imgs")[:, :H, :W, :].contiguous()
+            m = metrics.image_errors(rgbs, gt)
+            test_loss = m["mse"].double().mean().to(torch.float32)   # equal-size frames: mean of means == global mean
+            misc["test_loss"] = test_loss
+            misc["test_psnr"] = metrics.mse2psnr(test_loss)
+            misc["test_psnr_v2"] = m["psnr"].mean()
+            misc["test_ssim"] = m["ssim"].mean()
+            misc["errors"] = m["errors"]
+    if was_training and hasattr(net, "train"):
+        net.train()
+    return rgbs, disps, misc
+

@@ -87,6 +87,21 @@ int r2l_sample_pdf(long long n_rays, int nb, int Ni, const float* bins, long lon
 int r2l_merge_sorted(long long n_rays, int na, int nbv, const float* za, const float* zb, float* z_out,
                      float* z_std, void* stream);
 
+/* ---- image metrics of the render_path caller ------------------------------------ */
+
+/* abs_err [n_img][n_per_img] = |a - b| (may be NULL; main.py:331) and sum_sq [n_img] (device double, zeroed by the
+ * call) = sum (a-b)^2, one pass.  img2mse (helpers:19) = sum_sq / n_per_img; mse2psnr (helpers:20) = -10 log10(mse).
+ * replaces the per-frame error / PSNR stage of render_path, main.py:330-332, 384-390. */
+int r2l_image_error(int n_img, long long n_per_img, const float* a, const float* b, float* abs_err, double* sum_sq,
+                    void* stream);
+
+/* SSIM of utils/ssim_torch.py:27-54 as called from main.py:46,333-335: a, b [n_img][H][W][3] fp32 (image i at
+ * a + i*img_stride floats); taps = HOST pointer to the 11 normalised Gaussian taps (ssim_torch.py:10-16);
+ * sum_out [n_img] (device double, zeroed by the call) = sum of the SSIM map over the 3 channels;
+ * SSIM_i = sum_out[i] / (3 H W). */
+int r2l_ssim(int n_img, int H, int W, const float* a, const float* b, long long img_stride, const float* taps,
+             double* sum_out, void* stream);
+
 /* ---- MLPs ---------------------------------------------------------------------------------- */
 
 /* Y = act(X W^T + b [+ R]) in fp32 on CUDA cores (act: 0 none, 1 relu, 2 sigmoid); the

@@ -318,3 +318,44 @@ def render_r2l(sd, H, W, focal, near, far, c2w, n_sample=16, L=10, n_blocks=43, 
 
 def psnr(a, b):
     return float(-10. * torch.log10(torch.mean((a - b)**2)))
+
+
+# ----------------------------------------------------------------------------------------------------
+# Image metrics of render_path (main.py:330-335, 384-391)
+# ----------------------------------------------------------------------------------------------------
+def img2mse(x, y):
+    """utils/run_nerf_raybased_helpers.py:19."""
+    return torch.mean((x - y)**2)
+
+
+def mse2psnr(x):
+    """utils/run_nerf_raybased_helpers.py:20."""
+    return -10. * torch.log(x) / torch.log(torch.Tensor([10.]))
+
+
+def ssim_window(window_size=11, sigma=1.5, channel=3):
+    """utils/ssim_torch.py:10-25: 1-D Gaussian (python-double exp into an fp32 tensor, normalised in fp32), its outer
+    product, expanded to one filter per channel."""
+    from math import exp
+    g = torch.Tensor([exp(-(x - window_size // 2)**2 / float(2 * sigma**2)) for x in range(window_size)])
+    g = (g / g.sum()).unsqueeze(1)
+    w2 = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0)
+    return w2.expand(channel, 1, window_size, window_size).contiguous()
+
+
+def ssim(img, ref, window_size=11):
+    """utils/ssim_torch.py:27-54 through main.py:46: img, ref [C, H, W] -> scalar (size_average=True)."""
+    import torch.nn.functional as F
+    a, b = img.unsqueeze(0), ref.unsqueeze(0)
+    ch = a.shape[1]
+    w = ssim_window(window_size, 1.5, ch).type_as(a)
+    pad = window_size // 2
+    mu1 = F.conv2d(a, w, padding=pad, groups=ch)
+    mu2 = F.conv2d(b, w, padding=pad, groups=ch)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(a * a, w, padding=pad, groups=ch) - mu1_sq
+    s2 = F.conv2d(b * b, w, padding=pad, groups=ch) - mu2_sq
+    s12 = F.conv2d(a * b, w, padding=pad, groups=ch) - mu1_mu2
+    C1, C2 = 0.01**2, 0.03**2
+    m = ((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))
+    return m.mean()

@@ -111,3 +111,14 @@ def test_r2l(golden, O):
         assert same(pts, g["pts"])
         rgb = O.r2l_forward(sd, O.embed_r2l(pts, 10))
     assert close(rgb, g["rgb"], 1e-5)
+
+
+def test_image_metrics(golden, O):
+    """ssim / img2mse / mse2psnr restatements against the fixture written by the reference's own code."""
+    g = golden("metrics")
+    for n in "abc":
+        rgb, gt = t(g[f"rgb_{n}"]), t(g[f"gt_{n}"])
+        f = lambda k: float(np.asarray(g[f"{k}_{n}"]).reshape(-1)[0])
+        assert float(O.ssim(rgb.permute(2, 0, 1), gt.permute(2, 0, 1))) == f("ssim")
+        mse = O.img2mse(rgb, gt)
+        assert float(mse) == f("mse") and float(O.mse2psnr(mse)) == f("psnr")
