@@ -129,7 +129,10 @@ class R2LWorkload:
     name = "r2l"
     kernels_per_step = 2   # point_sample_kernel + r2l_mlp_kernel
 
-    def __init__(self, E, O, precision):
+    def __init__(self, E, O, precision, poses_per_launch=1):
+        self.P = int(poses_per_launch)
+        self.rays_per_step = RAYS * self.P
+        self.block = None
         sd = O.r2l_state_dict(0)
         net = E.NeRF_v3_2(O.r2l_args(), 1008, 3, precision=precision)
         net.load_state_dict(sd)
@@ -140,7 +143,10 @@ class R2LWorkload:
         self.ev = None
 
     def step(self, c2w_dev, mlp_events=None):
-        pts = self.ps.sample_test(c2w_dev)
+        # c2w_dev: [P, 3, 4] — P consecutive test poses rendered by ONE sampler launch + ONE fused-MLP launch
+        pts = self.ps.sample_test_batch(c2w_dev) if c2w_dev.dim() == 3 else self.ps.sample_test(c2w_dev)
+        if self.block is not None:          # --shard rays: this rank's contiguous block of the frame's rays
+            pts = pts[self.block[0]:self.block[1]]
         if mlp_events is not None:
             mlp_events[0].record()
         rgb = self.net.forward_points(pts)
@@ -150,15 +156,20 @@ class R2LWorkload:
 
     def describe(self):
         return {"workload": "R2L lego_noview resmlp W256 D88, n_sample_per_ray=16, 400x400 synthetic poses "
-                            "(BASELINE configs[1]); step = 1 pose = 160000 rays",
-                "rays_per_step": RAYS, "operands": self.net.precision, "accumulate": "fp32"}
+                            f"(BASELINE configs[1]); step = one launch of {self.P} consecutive test pose(s) = "
+                            f"{self.rays_per_step} rays (1250 tiles of 128 rays per frame leave a ragged 9th wave on "
+                            "148 SMs; batching poses fills whole waves)",
+                "poses_per_launch": self.P, "rays_per_step": self.rays_per_step, "operands": self.net.precision,
+                "accumulate": "fp32"}
 
 
 class NerfWorkload:
     name = "nerf"
     kernels_per_step = 13
 
-    def __init__(self, E, O, precision):
+    def __init__(self, E, O, precision, poses_per_launch=1):
+        self.P, self.rays_per_step = 1, RAYS
+        self.block = None
         sdc, sdf = O.nerf_state_dicts(0)
         self.coarse = E.NeRF(8, 256, 63, 27, 5, [4], True, precision=precision)
         self.fine = E.NeRF(8, 256, 63, 27, 5, [4], True, precision=precision)
@@ -171,6 +182,14 @@ class NerfWorkload:
                        near=2., far=6.)
 
     def step(self, c2w_dev, mlp_events=None):
+        if c2w_dev.dim() == 3:
+            c2w_dev = c2w_dev[0]
+        if self.block is not None:          # --shard rays: render only this rank's block of the frame's rays
+            ro, rd = self.E.get_rays(H, W, self.focal, c2w_dev)
+            s0, s1 = self.block
+            rays = torch.stack([ro.reshape(-1, 3)[s0:s1], rd.reshape(-1, 3)[s0:s1]], 0)
+            rgb, disp, acc, _ = self.E.render_image(H, W, self.focal, chunk=32768, rays=rays, **self.kw)
+            return rgb.reshape(-1, 3)
         rgb, disp, acc, _ = self.E.render_image(H, W, self.focal, chunk=32768, c2w=c2w_dev, **self.kw)
         return rgb.reshape(-1, 3)
 
@@ -249,6 +268,12 @@ def main():
     ap.add_argument("--workload", choices=["r2l", "nerf"], default="r2l")
     ap.add_argument("--precision", choices=["fp16", "bf16"], default="fp16")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--poses-per-launch", type=int, default=0,
+                    help="R2L: test poses rendered per launch (step); default 4.  NeRF always renders 1 frame per step")
+    ap.add_argument("--shard", choices=["poses", "rays"], default="poses",
+                    help="poses (default): rank r renders poses r, r+G, ... (weak scaling, no data-path collective); "
+                         "rays: every frame is split into contiguous ray blocks over the ranks and the tiles are "
+                         "all-gathered with NCCL (strong scaling: ms per frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
@@ -272,12 +297,28 @@ def main():
     import efficient_nerf_b200 as E
     from oracle import ref_torch as O   # synthetic poses / seeded weights (and the cpu_baseline leg)
     E._lib.load()
-    wl = (R2LWorkload if args.workload == "r2l" else NerfWorkload)(E, O, args.precision)
+    by_rays = args.shard == "rays"
+    P = (args.poses_per_launch or (1 if by_rays else 4)) if args.workload == "r2l" else 1
+    wl = (R2LWorkload if args.workload == "r2l" else NerfWorkload)(E, O, args.precision, P)
+    if by_rays:
+        if P != 1:
+            raise SystemExit("--shard rays renders one frame per step")
+        wl.block = E.sharding.shard_rays(RAYS, rank, world)
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
-    poses = make_poses(O, steps + warmup, offset=rank, stride=world)     # pose-sharded: rank r, r+G, ...
+    # pose-sharded: rank r renders poses r, r+G, ...; ray-sharded: every rank works on the SAME pose sequence
+    flat = make_poses(O, (steps + warmup) * P, offset=0 if by_rays else rank, stride=1 if by_rays else world)
+    poses = [torch.stack(flat[i * P:(i + 1) * P], 0).contiguous() for i in range(steps + warmup)]   # [P, 3, 4] per step
     poses_dev = [p.cuda() for p in poses]
+    RAYS_STEP = wl.rays_per_step
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    frame_buf = torch.empty((RAYS, 3), dtype=torch.float32, device="cuda") if by_rays else None
+
+    def run_step(pose, mev=None):
+        out = wl.step(pose, mev)
+        if by_rays:     # NCCL all-gather of the finished tiles: the whole frame on every rank
+            out = E.sharding.gather_rays_into(out.contiguous(), frame_buf, RAYS)
+        return out
     peaks = measured_peaks()
 
     # ---------------- device-resident timing
@@ -286,7 +327,7 @@ def main():
         if rank == 0:
             sampler.start()
         for i in range(warmup):
-            wl.step(poses_dev[i])
+            run_step(poses_dev[i])
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         mev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -298,7 +339,7 @@ def main():
         for i in range(steps):
             flush.zero_()                              # L2 flush, outside the event bracket
             ev[i][0].record()
-            out = wl.step(poses_dev[warmup + i], mev[i])
+            out = run_step(poses_dev[warmup + i], mev[i])
             ev[i][1].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
@@ -312,16 +353,17 @@ def main():
 
         # ---------------- end-to-end timing through the public API with host buffers
         pose_host = [p.pin_memory() for p in poses]
-        frame_host = torch.empty((RAYS, 3), dtype=torch.float32).pin_memory()
-        c2w_buf = torch.empty((3, 4), dtype=torch.float32, device="cuda")
+        frame_host = torch.empty((RAYS_STEP, 3), dtype=torch.float32).pin_memory()
+        c2w_buf = torch.empty((P, 3, 4), dtype=torch.float32, device="cuda")
         e2e_steps = steps
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(e2e_steps):
             c2w_buf.copy_(pose_host[warmup + i], non_blocking=True)          # H2D of this step's input
-            out = wl.step(c2w_buf)
-            frame_host.copy_(out, non_blocking=True)                          # D2H of this step's result
+            out = run_step(c2w_buf)
+            if not by_rays or rank == 0:
+                frame_host.copy_(out, non_blocking=True)                      # D2H of this step's result
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
@@ -330,24 +372,29 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
-    total_rays = RAYS * steps * world
+    n_jobs = 1 if by_rays else world      # ray-sharded: all ranks work on the same frames
+    total_rays = RAYS_STEP * steps * n_jobs
     value = total_rays / (dev_ms * 1e-3) / 1e6
-    e2e_value = RAYS * e2e_steps * world / (e2e_ms * 1e-3) / 1e6
+    e2e_value = RAYS_STEP * e2e_steps * n_jobs / (e2e_ms * 1e-3) / 1e6
 
     if rank == 0:
         line = {"metric": "render_throughput", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
-                "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True,
+                "scaling": "strong" if by_rays else "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": dict(wl.describe(), sharding="pose round-robin, no data-path collective",
+                "config": dict(wl.describe(),
+                               sharding=("contiguous ray blocks of every frame (multiples of 128 rays) + one NCCL "
+                                         "all_gather_into_tensor of the rgb tiles per frame, inside the timed region"
+                                         if by_rays else "pose round-robin, no data-path collective"),
                                l2="flushed between steps (256 MiB memset outside the event brackets)",
                                timing="sum of per-step CUDA-event durations, max over ranks"),
-                "ms_per_frame_400x400": dev_ms / steps,
+                "ms_per_frame_400x400": dev_ms / steps / P,
                 "wall_ms_per_step_incl_flush": t_wall / steps * 1e3,
-                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 48,
-                        "d2h_bytes_per_step": RAYS * 3 * 4, "ms_per_step": e2e_ms / e2e_steps},
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 48 * P,
+                        "d2h_bytes_per_step": RAYS_STEP * 3 * 4, "ms_per_step": e2e_ms / e2e_steps},
                 "gpu_launches": int(kernels), "abi_calls": int(launches),
                 "clocks": clocks}
-        flops = FLOP_PER_RAY[args.workload] * RAYS
+        flops = FLOP_PER_RAY[args.workload] * RAYS_STEP / (world if by_rays else 1)   # per rank and launch
         if args.workload == "r2l":
             ach = flops / (mlp_ms * 1e-3) / 1e12
             line["roofline"] = {"bound": "tensor", "kernel": "r2l_mlp_kernel", "achieved": ach,
@@ -394,6 +441,10 @@ def extras(E, O, peaks, precision, main_workload):
         other = "nerf" if main_workload == "r2l" else "r2l"
         wl = (R2LWorkload if other == "r2l" else NerfWorkload)(E, O, precision)
         pose = make_poses(O, 1)[0].cuda()
+        if main_workload == "r2l":   # the same R2L frame rendered one pose per launch (ragged last wave of tiles)
+            w1 = R2LWorkload(E, O, precision, 1)
+            ms1 = timeit(lambda: w1.step(pose), n=50)
+            out["r2l_one_pose_per_launch"] = {"ms_per_frame_400x400": ms1, "Mrays_per_s": RAYS / ms1 / 1e3}
         ms = timeit(lambda: wl.step(pose), n=5 if other == "nerf" else 20)
         fl = FLOP_PER_RAY[other] * RAYS
         out[other] = {"ms_per_frame_400x400": ms, "Mrays_per_s": RAYS / ms / 1e3,

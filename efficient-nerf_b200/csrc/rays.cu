@@ -137,10 +137,13 @@ __global__ void points_from_rays_kernel(long long n, int S, const float* __restr
 }
 
 // PointSampler.sample_test: rays from the pixel grid + c2w, then pts on shared z_vals
-// (model/nerf_raybased.py:94-102).  One thread per (ray, sample).
+// (model/nerf_raybased.py:94-102).  One thread per (ray, sample); blockIdx.y = pose of a batch (c2w [n][3][4],
+// pts [n][H*W][S*3]).
 __global__ void point_sample_kernel(int H, int W, float focal, const float* __restrict__ c2w,
                                     const float* __restrict__ z_vals, int S, float* __restrict__ pts) {
   const long long total = static_cast<long long>(H) * W * S;
+  c2w += 12 * blockIdx.y;
+  pts += 3 * total * blockIdx.y;
   const float half_w = static_cast<float>(W * 0.5);
   const float half_h = static_cast<float>(H * 0.5);
   float c[12];
@@ -239,6 +242,21 @@ int r2l_point_sample(int H, int W, double focal, const float* c2w, const float* 
   const long long total = static_cast<long long>(H) * W * S;
   point_sample_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       H, W, static_cast<float>(focal), c2w, z_vals, S, pts);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+int r2l_point_sample_batch(int n_poses, int H, int W, double focal, const float* c2w, const float* z_vals, int S,
+                           float* pts, void* stream) {
+  R2L_CHECK_ARG(n_poses >= 0 && n_poses <= 65535 && H > 0 && W > 0 && S > 0 && focal != 0.0,
+                "r2l_point_sample_batch: bad sizes");
+  if (n_poses == 0) return R2L_OK;
+  R2L_CHECK_ARG(c2w && z_vals && pts, "r2l_point_sample_batch: null pointer");
+  const long long total = static_cast<long long>(H) * W * S;
+  int gx = grid_for(total, 256) / n_poses;
+  if (gx < 1) gx = 1;
+  point_sample_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_poses)), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(H, W, static_cast<float>(focal), c2w, z_vals, S, pts);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }

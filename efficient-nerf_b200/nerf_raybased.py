@@ -520,6 +520,21 @@ class PointSampler():
     def sample_test(self, c2w):  # c2w: [3, 4]
         return self._sample(c2w)  # [H*W, n_sample*3]
 
+    def sample_test_batch(self, c2ws):
+        """sample_test for P poses in one launch: c2ws [P, 3|4, 4] -> [P*H*W, n_sample*3] (pose-major), so that one
+        fused-MLP launch renders P frames (full waves of 128-ray tiles instead of a ragged last wave per frame)."""
+        dev = self.z_vals.device
+        c = _lib.as_f32_cuda(c2ws, dev, "c2ws")
+        if c.dim() != 3 or c.shape[-1] != 4 or c.shape[-2] < 3:
+            raise ValueError(f"c2ws must be [P, 3, 4] or [P, 4, 4], got {tuple(c.shape)}")
+        c = c[:, :3, :4].contiguous()
+        P = c.shape[0]
+        pts = torch.empty((P * self.H * self.W, self.n_sample * 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("r2l_point_sample_batch", P, self.H, self.W, self.focal, _lib.ptr(c), _lib.ptr(self.z_vals),
+                      self.n_sample, _lib.ptr(pts), _lib.stream_ptr(dev))
+        return pts
+
     def sample_test2(self, c2w):
         return self._sample(c2w).view(self.H * self.W, self.n_sample, 3)
 

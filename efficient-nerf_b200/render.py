@@ -208,7 +208,9 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
 def render_r2l(model, point_sampler, c2w, positional_embedder=None):
     """R2L branch of render_path (main.py:285-325): one frame = one un-chunked forward.
     Uses the fused encode+MLP kernel when the model supports it; returns rgb [H*W, 3]."""
-    pts = point_sampler.sample_test(c2w)
+    c = c2w if isinstance(c2w, torch.Tensor) else torch.as_tensor(c2w)
+    # a stack of poses [P, 3, 4] renders P frames with ONE launch each of the sampler and the fused MLP -> [P*H*W, 3]
+    pts = point_sampler.sample_test_batch(c) if c.dim() == 3 else point_sampler.sample_test(c2w)
     if model.precision != "fp32" and model.supports_tensor_core_path():
         L = positional_embedder.L if positional_embedder is not None else 10
         if L == 10 and pts.shape[-1] * 21 == model.input_dim:

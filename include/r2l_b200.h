@@ -57,6 +57,11 @@ int r2l_points_from_rays(long long n, int S, const float* rays_o, long long o_st
 int r2l_point_sample(int H, int W, double focal, const float* c2w, const float* z_vals, int S, float* pts,
                      void* stream);
 
+/* The same for a batch of poses in one launch: c2w [n_poses][3][4] -> pts [n_poses][H*W][S*3] (the test loop of
+ * main.py:297-301 renders one pose per call; batching poses lets one fused-MLP launch fill whole waves of tiles). */
+int r2l_point_sample_batch(int n_poses, int H, int W, double focal, const float* c2w, const float* z_vals, int S,
+                           float* pts, void* stream);
+
 /* ---- positional encoding ------------------------------------------------------------------ */
 
 /* layout 0: Embedder.embed (utils/run_nerf_raybased_helpers.py:24-74), x [rows, D] -> [rows, D*(1+2L)]

@@ -435,3 +435,20 @@ def test_nerf_800x800_rays_vs_oracle(E, O):
         rgb, disp, acc, extras = E.render_image(cam["H"], cam["W"], cam["focal"], chunk=32768, c2w=c2w.cuda(), **kw)
     assert tuple(rgb.shape) == (800, 800, 3) and bool(torch.isfinite(rgb).all())
     assert maxabs(rgb.reshape(-1, 3)[idx.cuda()], ref["rgb_map"]) <= RGB_TOL
+
+
+def test_r2l_pose_batch_equals_single_poses(E, O):
+    """PointSampler.sample_test_batch / render_r2l with a stack of poses: bit-identical to one pose per call."""
+    sd = O.r2l_state_dict(0)
+    net = load_r2l(E, O, sd, "fp16")
+    Hh, Ww = 30, 50   # 1500 rays per frame: not a multiple of the 128-ray tile, so frames share tiles
+    ps = E.PointSampler(Hh, Ww, 60., 16, 2., 6.)
+    poses = torch.stack([O.pose_spherical(th, -30., 4.)[:3, :4] for th in (-120., -10., 75.)], 0).cuda()
+    with torch.no_grad():
+        pb = ps.sample_test_batch(poses)
+        p1 = torch.cat([ps.sample_test(p) for p in poses], 0)
+        assert pb.shape == (3 * Hh * Ww, 48) and torch.equal(pb, p1)
+        fb = E.render_r2l(net, ps, poses)
+        f1 = torch.cat([E.render_r2l(net, ps, p) for p in poses], 0)
+    assert fb.shape == (3 * Hh * Ww, 3) and torch.equal(fb, f1)
+    assert ps.sample_test_batch(poses[:0]).shape == (0, 48)

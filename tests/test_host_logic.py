@@ -45,6 +45,12 @@ full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
 s0, s1 = E.sharding.shard_rays(n)
 out = E.sharding.gather_rays(full[s0:s1].clone(), n)
 assert torch.equal(out, full), "gather_rays mismatch"
+for n2 in (1000, 1024):   # ragged split (fallback path) and equal blocks (one all_gather_into_tensor)
+    full2 = torch.arange(n2 * 3, dtype=torch.float32).reshape(n2, 3)
+    a0, a1 = E.sharding.shard_rays(n2)
+    buf = torch.full((n2, 3), -1.)
+    res = E.sharding.gather_rays_into(full2[a0:a1].clone(), buf, n2)
+    assert res is buf and torch.equal(buf, full2), "gather_rays_into mismatch"
 mine = [torch.full((8, 3), float(i)) for i in E.sharding.shard_poses(5)]
 frames = E.sharding.gather_frames(mine, 5)
 assert [float(f[0, 0]) for f in frames] == [0., 1., 2., 3., 4.], "gather_frames mismatch"
