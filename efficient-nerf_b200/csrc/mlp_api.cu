@@ -149,49 +149,20 @@ struct Mlp {
   float* vb_ws = nullptr;          // workspace: per-ray view-branch bias [vb_cap rays][128]
   long long vb_cap = 0;
   NerfPpMaps* pp_maps = nullptr;   // tensor maps over wstream_pp
+  R2lPairMaps* r2l_maps = nullptr; // R2L pair mode: tensor maps over wstream
   // R2L
   int n_points = 0, n_blocks = 0, sigmoid_out = 1, outer_skip = 1;
   float b_tail[3] = {0.f, 0.f, 0.f};
 };
 
-// R2L_PAIR=1 selects the CTA-pair kernel (tcgen05.mma.cta_group::2, half the L2 -> shared-memory weight traffic);
-// measured equal in throughput to the single-CTA kernel under the power cap (1.677 ms vs 1.678 ms per R2L frame,
-// 1.74 GHz vs 1.65 GHz), so the single-CTA kernel stays the default until the pair kernel's spare shared memory is
-// used to overlap the epilogue.
-// R2L_NERF_PP=0 selects the single-CTA chasing NeRF kernel (mlp_nerf.cu) instead of the CTA-pair ping-pong kernel.
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-static int encode_rows_map(CUtensorMap* out, void* base, size_t bytes, int box_rows) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    R2L_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
-    if (sym == nullptr || q != cudaDriverEntryPointSuccess)
-      return fail(R2L_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-    fn = reinterpret_cast<EncodeFn>(sym);
-  }
-  const cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(bytes / 512)};
-  const cuuint64_t strides[1] = {512};
-  const cuuint32_t box[2] = {256, static_cast<cuuint32_t>(box_rows)};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(R2L_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
-  return R2L_OK;
-}
-
-// NeRF handles use the CTA-pair ping-pong kernel (mlp_nerf_pp.cu: 41.6 vs 44.8 ms per 400x400 frame on B200);
-// R2L_NERF_PP=0 selects the single-CTA chasing kernel (mlp_nerf.cu) instead.
-static int nerf_pp_default() {
-  const char* e = getenv("R2L_NERF_PP");
-  return (e != nullptr && e[0] == '0') ? 0 : 1;
-}
+// R2L handles use the CTA-pair kernel (tcgen05.mma.cta_group::2: half the L2 -> shared-memory weight traffic and half
+// the B-operand shared-memory reads per FLOP).  With a relay thread forwarding the peer's stage arrivals it only
+// matched the single-CTA kernel (1.677 vs 1.678 ms per frame: higher clocks under the power cap, more cycles);
+// with the peer's half stages signalling the leader's barrier directly (cp.async.bulk.tensor...cta_group::2) it is
+// 1.9 % faster sustained (99.6 vs 97.8 Mrays/s at 1.68 vs 1.57 GHz).  R2L_PAIR=0 selects the single-CTA kernel.
 static int pair_mode_default() {
   const char* e = getenv("R2L_PAIR");
-  return (e != nullptr && e[0] == '1') ? 1 : 0;
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
 }
 
 static int alloc_debug(Mlp* m) {
@@ -233,6 +204,7 @@ static void destroy(Mlp* m) {
   if (m->aux) cudaFree(m->aux);
   if (m->dbg_host) cudaFreeHost(m->dbg_host);
   delete m->pp_maps;
+  delete m->r2l_maps;
   delete m;
 }
 
@@ -842,6 +814,12 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
     off += 256ull * 256;
   }
   if (rc != R2L_OK) return cleanup(rc);
+  if (m->pair == 1) {
+    m->r2l_maps = new R2lPairMaps();
+    rc = encode_rows_map(&m->r2l_maps->m16, m->wstream, m->wbytes, 32);
+    if (rc == R2L_OK) rc = encode_rows_map(&m->r2l_maps->m4, m->wstream, m->wbytes, 8);
+    if (rc != R2L_OK) return cleanup(rc);
+  }
   cudaError_t e = cudaMemcpyAsync(m->aux, tail_w, 768 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->b_tail, tail_b, 12, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -883,7 +861,7 @@ static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_
   } else {
     grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   }
-  return r2l_mlp_launch(m->bf16, m->pair == 1, p, grid, st);
+  return r2l_mlp_launch(m->bf16, m->pair == 1, p, m->r2l_maps, grid, st);
 }
 
 // Fused PositionalEmbedder + NeRF_v3_2 on sampled points: pts [n_rays, n_points*3] -> rgb [n_rays, 3].

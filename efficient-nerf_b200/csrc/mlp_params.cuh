@@ -59,7 +59,12 @@ struct R2lParams {
 };
 
 int nerf_mlp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st);
-int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, int grid, cudaStream_t st);
+// Tensor maps over the R2L pair-layout stage stream (rows of 512 bytes): boxes of 32 / 8 rows = one CTA's half of a
+// K=64 weight stage / of a bias stage
+struct R2lPairMaps {
+  CUtensorMap m16, m4;
+};
+int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, const R2lPairMaps* maps, int grid, cudaStream_t st);
 // CTA-pair "ping-pong" NeRF kernel (mlp_nerf_pp.cu): grid even, pair-layout stream without the view stage
 int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, int grid, cudaStream_t st);
 int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,

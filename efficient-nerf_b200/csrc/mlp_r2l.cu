@@ -46,7 +46,7 @@ static_assert(kR2lOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
 // the B-operand shared-memory reads per SM), the leader CTA's MMA thread issues for both, and all "operand ready"
 // barriers live in the leader and collect the warps of both CTAs; MMA completion is multicast to both.
 template <bool BF16, bool PAIR>
-__global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams p) {
+__global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams p, const __grid_constant__ R2lPairMaps maps) {
   constexpr int kRing = PAIR ? 8 : 4;
   constexpr int kBiasRing = PAIR ? 4 : 2;
   constexpr uint32_t kStageB = PAIR ? kStageBytes / 2 : kStageBytes;          // bytes of a stage held by THIS CTA
@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) {
-      mbar_init(&w_full[i], (PAIR && rank == 0) ? 2 : 1);   // leader: own producer + the peer's relay
+      mbar_init(&w_full[i], 1);   // PAIR: the peer's half stage completes its bytes on the leader's barrier
       mbar_init(&w_empty[i], 1);
     }
     for (int i = 0; i < kBiasRing; ++i) {
-      mbar_init(&b_full[i], (PAIR && rank == 0) ? 2 : 1);
+      mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8 * kCtas);
@@ -121,16 +121,27 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       auto push = [&]() {
         const uint32_t slot = g % kRing;
         mbar_wait_x<PAIR>(&w_empty[slot], ((g / kRing) & 1) ^ 1, p.dbg, 100 + slot);
-        mbar_expect_tx(&w_full[slot], kStageB);
-        bulk_g2s(sRing + slot * kStageB, src + rank * kStageB, kStageB, &w_full[slot]);
+        if (PAIR && rank != 0) {
+          // cp.async.bulk.tensor...cta_group::2 may signal the LEADER's barrier: no relay hop (see mlp_nerf_pp.cu)
+          tma2d_g2s_pair_bar(sRing + slot * kStageB, &maps.m16, 0, static_cast<int>((src + kStageB - p.wstream) >> 9),
+                             mapa_u32(&w_full[slot], 0));
+        } else {
+          mbar_expect_tx(&w_full[slot], PAIR ? 2 * kStageB : kStageB);
+          bulk_g2s(sRing + slot * kStageB, src, kStageB, &w_full[slot]);
+        }
         src += kStageBytes;
         ++g;
       };
       auto push_bias = [&]() {
         const uint32_t slot = gb % kBiasRing;
         mbar_wait_x<PAIR>(&b_empty[slot], ((gb / kBiasRing) & 1) ^ 1, p.dbg, 120 + slot);
-        mbar_expect_tx(&b_full[slot], kBiasB);
-        bulk_g2s(sBiasRing + slot * kBiasB, src + rank * kBiasB, kBiasB, &b_full[slot]);
+        if (PAIR && rank != 0) {
+          tma2d_g2s_pair_bar(sBiasRing + slot * kBiasB, &maps.m4, 0, static_cast<int>((src + kBiasB - p.wstream) >> 9),
+                             mapa_u32(&b_full[slot], 0));
+        } else {
+          mbar_expect_tx(&b_full[slot], PAIR ? 2 * kBiasB : kBiasB);
+          bulk_g2s(sBiasRing + slot * kBiasB, src, kBiasB, &b_full[slot]);
+        }
         src += kBiasStageBytes;
         ++gb;
       };
@@ -146,30 +157,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
     }
   } else if (warp == kR2lMmaWarp) {
     if (PAIR && rank != 0) {
-      // ===================== peer CTA: relay "my half stage has landed" to the leader's barriers =====================
-      if (lane == 0) {
-        uint32_t g = 0, gb = 0;
-        auto relay = [&]() {
-          const uint32_t slot = g % kRing;
-          mbar_wait(&w_full[slot], (g / kRing) & 1, p.dbg, 150 + slot);
-          mbar_arrive_cluster(mapa_u32(&w_full[slot], 0));
-          ++g;
-        };
-        auto relay_bias = [&]() {
-          const uint32_t slot = gb % kBiasRing;
-          mbar_wait(&b_full[slot], (gb / kBiasRing) & 1, p.dbg, 170 + slot);
-          mbar_arrive_cluster(mapa_u32(&b_full[slot], 0));
-          ++gb;
-        };
-        for (int unit = unit0; unit < n_units; unit += unit_step) {
-          relay_bias();
-          for (int i = 0; i < n_chunks * 4; ++i) relay();
-          for (int l = 0; l < 2 * nb; ++l) {
-            relay_bias();
-            for (int i = 0; i < 4; ++i) relay();
-          }
-        }
-      }
+      // peer CTA: nothing to do here (its half stages signal the leader's barriers directly)
     } else
     // ===================== MMA issuer (leader CTA) =====================
     if (lane == 0) {
@@ -447,7 +435,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
 }
 
 template <bool BF16, bool PAIR>
-int launch_r2l(const R2lParams& p, int grid, cudaStream_t st) {
+int launch_r2l(const R2lParams& p, const R2lPairMaps& maps, int grid, cudaStream_t st) {
   R2L_CUDA(cudaFuncSetAttribute(r2l_mlp_kernel<BF16, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kR2lSmemBytes));
   cudaLaunchConfig_t cfg = {};
@@ -462,15 +450,19 @@ int launch_r2l(const R2lParams& p, int grid, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  R2L_CUDA(cudaLaunchKernelEx(&cfg, r2l_mlp_kernel<BF16, PAIR>, p));
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, r2l_mlp_kernel<BF16, PAIR>, p, maps));
   count_launch();
   return R2L_OK;
 }
 
 // pair: CTA-pair mode (the weights must have been packed in the pair layout); grid is then a multiple of 2
-int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, int grid, cudaStream_t st) {
-  if (pair) return bf16 ? launch_r2l<true, true>(p, grid, st) : launch_r2l<false, true>(p, grid, st);
-  return bf16 ? launch_r2l<true, false>(p, grid, st) : launch_r2l<false, false>(p, grid, st);
+int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, const R2lPairMaps* maps, int grid, cudaStream_t st) {
+  static const R2lPairMaps none = {};
+  if (pair) {
+    R2L_CHECK_ARG(maps != nullptr, "r2l_mlp_launch: the CTA-pair kernel needs tensor maps");
+    return bf16 ? launch_r2l<true, true>(p, *maps, grid, st) : launch_r2l<false, true>(p, *maps, grid, st);
+  }
+  return bf16 ? launch_r2l<true, false>(p, none, grid, st) : launch_r2l<false, false>(p, none, grid, st);
 }
 
 }  // namespace r2l

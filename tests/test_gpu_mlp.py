@@ -301,10 +301,13 @@ def test_r2l_fused_vs_reference(E, O, golden, precision, tol):
 
 
 @pytest.mark.parametrize("n_points", [4, 8, 16])
-def test_r2l_head_accumulators_and_packed_weights(E, O, n_points):
+def test_r2l_head_accumulators_and_packed_weights(E, O, n_points, monkeypatch):
     """Debug hooks: the packed weight stream is the expected permutation, and the head layer's raw tcgen05
-    accumulators equal the fp16-rounded reference product (K = 64 per point, accumulated over chunks)."""
+    accumulators equal the fp16-rounded reference product (K = 64 per point, accumulated over chunks).
+    Pinned to the single-CTA stream layout (R2L_PAIR=0); the CTA-pair layout (two N-halves per stage) is covered by
+    test_tcgen05_gemm_probe_cta_pair and by every R2L parity test, which run the default pair kernel."""
     import ctypes
+    monkeypatch.setenv("R2L_PAIR", "0")
     L = E._lib
     torch.manual_seed(n_points)
     net = E.NeRF_v3_2(O.r2l_args(netdepth=6), n_points * 63, 3, precision="fp16").cuda().eval()
@@ -435,6 +438,28 @@ def test_nerf_800x800_rays_vs_oracle(E, O):
         rgb, disp, acc, extras = E.render_image(cam["H"], cam["W"], cam["focal"], chunk=32768, c2w=c2w.cuda(), **kw)
     assert tuple(rgb.shape) == (800, 800, 3) and bool(torch.isfinite(rgb).all())
     assert maxabs(rgb.reshape(-1, 3)[idx.cuda()], ref["rgb_map"]) <= RGB_TOL
+
+
+def test_r2l_pair_kernel_vs_single_cta_kernel(E, O, monkeypatch):
+    """The CTA-pair R2L kernel (default) against the single-CTA kernel (R2L_PAIR=0): the same math on the same 16-bit
+    operands (M = 256 vs 128 tiles only), so they agree to accumulation-order noise; ragged ray counts cover a
+    missing peer tile; full-frame reruns must be bit-reproducible."""
+    sd = O.r2l_state_dict(0)
+    monkeypatch.setenv("R2L_PAIR", "0")
+    single = load_r2l(E, O, sd, "fp16")
+    single.packed_handle()
+    monkeypatch.setenv("R2L_PAIR", "1")
+    pair = load_r2l(E, O, sd, "fp16")
+    pair.packed_handle()
+    ps = E.PointSampler(400, 400, O.LEGO["focal"], 16, 2., 6.)
+    pts = ps.sample_test(O.pose_spherical(20., -30., 4.)[:3, :4].cuda())
+    with torch.no_grad():
+        for n in (1, 127, 129, 257, 160000):
+            a, b = single.forward_points(pts[:n]), pair.forward_points(pts[:n])
+            assert a.shape == b.shape == (n, 3) and maxabs(a, b) < 2e-4, (n, maxabs(a, b))
+        ref = pair.forward_points(pts).clone()
+        for _ in range(3):
+            assert torch.equal(pair.forward_points(pts), ref)
 
 
 def test_r2l_pose_batch_equals_single_poses(E, O):
