@@ -155,6 +155,36 @@ struct Mlp {
   float b_tail[3] = {0.f, 0.f, 0.f};
 };
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static int encode_rows_map(CUtensorMap* out, void* base, size_t bytes, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    R2L_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+    if (sym == nullptr || q != cudaDriverEntryPointSuccess)
+      return fail(R2L_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  const cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(bytes / 512)};
+  const cuuint64_t strides[1] = {512};
+  const cuuint32_t box[2] = {256, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(R2L_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return R2L_OK;
+}
+
+// NeRF handles use the CTA-pair ping-pong kernel (mlp_nerf_pp.cu: 41.6 vs 44.8 ms per 400x400 frame on B200);
+// R2L_NERF_PP=0 selects the single-CTA chasing kernel (mlp_nerf.cu) instead.
+static int nerf_pp_default() {
+  const char* e = getenv("R2L_NERF_PP");
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
+}
 // R2L handles use the CTA-pair kernel (tcgen05.mma.cta_group::2: half the L2 -> shared-memory weight traffic and half
 // the B-operand shared-memory reads per FLOP).  With a relay thread forwarding the peer's stage arrivals it only
 // matched the single-CTA kernel (1.677 vs 1.678 ms per frame: higher clocks under the power cap, more cycles);
