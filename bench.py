@@ -449,6 +449,26 @@ def extras(E, O, peaks, precision, main_workload):
         fl = FLOP_PER_RAY[other] * RAYS
         out[other] = {"ms_per_frame_400x400": ms, "Mrays_per_s": RAYS / ms / 1e3,
                       "tensor_TFLOPs": fl / ms / 1e9, "frac_of_sustained_peak": fl / ms / 1e9 / peaks["tf_sust"]}
+        # the other BASELINE configs, one frame each (configs[3]: 800x800; configs[4]: LLFF fern 504x378, NDC, 64+64)
+        if main_workload == "r2l":
+            cam8 = O.LEGO_800
+            r2l = R2LWorkload(E, O, precision, 1)
+            ps8 = E.PointSampler(cam8["H"], cam8["W"], cam8["focal"], 16, 2., 6.)
+            n8 = cam8["H"] * cam8["W"]
+            ms = timeit(lambda: r2l.net.forward_points(ps8.sample_test(pose)), n=20)
+            out["r2l_800x800"] = {"ms_per_frame": ms, "Mrays_per_s": n8 / ms / 1e3,
+                                  "tensor_TFLOPs": FLOP_PER_RAY["r2l"] * n8 / ms / 1e9}
+            nw = wl if other == "nerf" else NerfWorkload(E, O, precision)
+            kw8 = dict(nw.kw)
+            ms = timeit(lambda: E.render_image(cam8["H"], cam8["W"], cam8["focal"], chunk=32768, c2w=pose, **kw8), n=3, warm=1)
+            out["nerf_800x800"] = {"ms_per_frame": ms, "Mrays_per_s": n8 / ms / 1e3,
+                                   "tensor_TFLOPs": FLOP_PER_RAY["nerf"] * n8 / ms / 1e9}
+            fern = O.FERN
+            kwf = dict(nw.kw, N_importance=64, white_bkgd=False, ndc=True, near=0., far=1.)
+            nf = fern["H"] * fern["W"]
+            ms = timeit(lambda: E.render_image(fern["H"], fern["W"], fern["focal"], chunk=32768, c2w=pose, **kwf), n=3, warm=1)
+            out["nerf_fern_504x378_ndc_64+64"] = {"ms_per_frame": ms, "Mrays_per_s": nf / ms / 1e3,
+                                                  "tensor_TFLOPs": 227868672 * nf / ms / 1e9}
         # HBM-bound kernels on 4x the frame (inputs > L2): raw2outputs S=192, sample_pdf Ni=128
         N = 4 * RAYS
         raw = torch.randn(N, 192, 4, device="cuda")
