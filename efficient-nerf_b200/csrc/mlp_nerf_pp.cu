@@ -26,6 +26,11 @@
 //     5) — sin/cos of 128 points is ~2 k issue slots, the encoder warps are otherwise idle.
 //   * The view branch is a per-ray fp32 bias vb (computed by nerf_view_bias_kernel into a caller workspace) added in
 //     the last epilogue instead of an extra K-stage: it needs no shared memory.
+//   * Tried and measured slower on the same box (160000 x 192 samples: 29.7-30.1 ms for this version): a 5-slot ring
+//     paid for by writing the point block over columns [0,64) of the tile's own activation buffer (skip layer with
+//     its point stage last): 30.3 ms; the same with a one-directional lag token for issuer T1: 30.6-30.7 ms.  In the
+//     schedule the issuers settle into, the ring is not what limits a tile: its chain issue -> drain behind the other
+//     tile's queued MMAs -> epilogue (which waits for the other tile's epilogue: same 8 warps) -> wake-ups is.
 //   * No per-group chasing barriers: a tile-layer starts when the tile's previous epilogue has signalled a_done[t]
 //     (one barrier, 16 warp arrivals), which also closes every TMEM / shared-memory write-after-read hazard.
 // Per tile: 10 steps (see mlp_nerf.cu): 0 = W0 P, 1-4, 5 = W5 [P, h], 6, 7 (+sigma), 8 = feature, 9 = views (N 128).
@@ -54,6 +59,9 @@ constexpr bool kPpDirect = true;
 // issuers settle ~1200 cycles apart, weights are prefetched a layer ahead and the tensor pipe idles only between
 // layers (~20 %, in-kernel timeline: scratch/prof_pp.py, R2L_PROF_MODE=5).
 constexpr bool kPpTurns = R2L_PP_TURNS != 0;
+// 2: ONE-directional: only issuer T1 waits (until T0 has issued its tile-layer), T0 never waits for T1 — a minimum
+// lag for T1 without making the tiles mutually exclusive.
+constexpr bool kPpLagOnly = R2L_PP_TURNS == 2;
 constexpr uint32_t kPpStageB = kStageBytes / 2;       // 16 KiB: this CTA's N-half of a K=64 stage
 constexpr uint32_t kPpBiasB = kBiasStageBytes / 2;    // 4 KiB
 constexpr uint32_t kPpLbo256 = 128 * 16;              // 128 B-rows per CTA (N = 256)
@@ -200,7 +208,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
         }
         if (step == 0 || step == 5) wait_p();
         uint32_t slot = next_w();
-        if (kPpTurns && !(t == 0 && n_turn == 0)) {
+        if (kPpTurns && !(t == 0 && (n_turn == 0 || kPpLagOnly))) {
           // my turn: the other issuer has issued all MMAs of its tile-layer (keeps the two tiles' MMA phases apart on
           // the in-order tensor pipe, so a tile's accumulator completes ~2176 cycles after its first MMA, not ~4000)
           const long long c0 = prof ? clock64() : 0;
@@ -225,7 +233,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
           if (step == 0 || step == 5) {
             trace(it, 100000 + t * 10000 + step * 100 + 9);
             issue_stage<4, true>(d, aP, aRing + slot * kPpStageB, kPpLbo256, idesc256, false);
-            if (kPpTurns && step == 0) mbar_arrive(&turn[1 - t]);
+            if (kPpTurns && step == 0 && !(kPpLagOnly && t == 1)) mbar_arrive(&turn[1 - t]);
             umma_commit_pair(&w_empty[slot]);
             umma_commit_pair(&p_free[t]);
             ++g;
@@ -238,7 +246,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
               issue_stage<4, true>(d, aA + st * kGroupBytes, aRing + slot * kPpStageB, kPpLbo256, idesc256, false);
               // step 5 has 5 stages for a 4-slot ring: its last stage can only be loaded after the OTHER tile has
               // used the first one, so the turn is passed one stage early there
-              if (kPpTurns && st == (step == 5 ? 2 : 3)) mbar_arrive(&turn[1 - t]);
+              if (kPpTurns && st == (step == 5 ? 2 : 3) && !(kPpLagOnly && t == 1)) mbar_arrive(&turn[1 - t]);
               umma_commit_pair(&w_empty[slot]);
               ++g;
             }
@@ -248,7 +256,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
           for (int st = 0; st < 4; ++st) {
             if (st > 0) slot = next_w();
             issue_stage<4, true>(d, aA + st * kGroupBytes, aRing + slot * kPpStageB, kPpLbo128, idesc128, st == 0);
-            if (kPpTurns && st == 3) mbar_arrive(&turn[1 - t]);
+            if (kPpTurns && st == 3 && !(kPpLagOnly && t == 1)) mbar_arrive(&turn[1 - t]);
             umma_commit_pair(&w_empty[slot]);
             ++g;
           }

@@ -134,8 +134,9 @@ __device__ __forceinline__ void sincos_octaves(float x, float (&s)[L], float (&c
 // (the NeRF Embedder order, utils/run_nerf_raybased_helpers.py:24-56; weights are permuted to
 // this order at pack time for the R2L head, model/nerf_raybased.py:198-208).
 // dst = base of the block's 8 chunks (chunk stride kChunkBytes), written as 8 x 16-byte stores.
+// (split in two so that a caller can compute the encoding BEFORE it is allowed to overwrite the destination)
 template <bool BF16>
-__device__ __forceinline__ void encode_point_block(uint8_t* dst, int row, float px, float py, float pz) {
+__device__ __forceinline__ void encode_point_packed(float px, float py, float pz, uint4 (&q)[8]) {
   float v[64];
   v[0] = px;
   v[1] = py;
@@ -164,13 +165,22 @@ __device__ __forceinline__ void encode_point_block(uint8_t* dst, int row, float 
   v[63] = 0.0f;
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) {
-    uint4 q;
-    q.x = pack2<BF16>(v[8 * ch + 0], v[8 * ch + 1]);
-    q.y = pack2<BF16>(v[8 * ch + 2], v[8 * ch + 3]);
-    q.z = pack2<BF16>(v[8 * ch + 4], v[8 * ch + 5]);
-    q.w = pack2<BF16>(v[8 * ch + 6], v[8 * ch + 7]);
-    *reinterpret_cast<uint4*>(dst + ch * kChunkBytes + row * 16) = q;
+    q[ch].x = pack2<BF16>(v[8 * ch + 0], v[8 * ch + 1]);
+    q[ch].y = pack2<BF16>(v[8 * ch + 2], v[8 * ch + 3]);
+    q[ch].z = pack2<BF16>(v[8 * ch + 4], v[8 * ch + 5]);
+    q[ch].w = pack2<BF16>(v[8 * ch + 6], v[8 * ch + 7]);
   }
+}
+// the 8 packed chunks of a point block -> row `row` of the block at dst
+__device__ __forceinline__ void store_point_block(uint8_t* dst, int row, const uint4 (&q)[8]) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + ch * kChunkBytes + row * 16) = q[ch];
+}
+template <bool BF16>
+__device__ __forceinline__ void encode_point_block(uint8_t* dst, int row, float px, float py, float pz) {
+  uint4 q[8];
+  encode_point_packed<BF16>(px, py, pz, q);
+  store_point_block(dst, row, q);
 }
 
 // Write 32 fp32 values as the 32-wide block (4 chunks) of row `row`.
