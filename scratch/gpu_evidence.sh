@@ -5,7 +5,7 @@ O=gpurun_out/${1:-r1}; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/smi.log 2>&1; nproc >> $O/smi.log
 timeout 900 python -m pytest tests -m gpu -x -q > $O/tests_gpu.log 2>&1; echo "tests rc=$?"
 timeout 600 python bench.py > $O/bench_r2l.json 2> $O/bench_r2l.err; echo "bench r2l rc=$?"
-timeout 600 python bench.py --workload nerf --steps 10 --warmup 3 --no-extras > $O/bench_nerf.json 2> $O/bench_nerf.err; echo "bench nerf rc=$?"
+timeout 600 python bench.py --workload nerf --steps 20 --warmup 3 --no-extras > $O/bench_nerf.json 2> $O/bench_nerf.err; echo "bench nerf rc=$?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_r2l.json 2> $O/bench_ref_r2l.err; echo "ref rc=$?"
 if [ "${2:-full}" = "full" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_r2l.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $O/ncu_r2l.log 2>&1; echo "ncu list r2l rc=$?"
