@@ -83,20 +83,46 @@ class _AsyncNpySaver:
             job = self.q.get()
             if job is None:
                 return
+            barrier = None
             try:
-                datadir, first, arr, split_size = job
+                datadir, first, arr, split_size, barrier = job
                 for j in range(arr.shape[0] // split_size):
                     np.save(os.path.join(datadir, f"data_{first + j}.npy"), arr[j * split_size:(j + 1) * split_size])
             except Exception as e:  # surfaced by close()
                 self.err.append(e)
+            finally:
+                if barrier is not None:
+                    barrier.done()
 
-    def submit(self, datadir, first, arr, split_size, n_parts):
+    class Barrier:
+        """Counts the jobs of one submit() call; wait() returns when all of them have been written."""
+
+        def __init__(self, _n_hint=0):
+            self.n, self.cv = 0, threading.Condition()
+
+        def add(self):
+            with self.cv:
+                self.n += 1
+
+        def done(self):
+            with self.cv:
+                self.n -= 1
+                self.cv.notify_all()
+
+        def wait(self):
+            with self.cv:
+                while self.n > 0:
+                    self.cv.wait()
+
+    def submit(self, datadir, first, arr, split_size, n_parts, barrier=None):
         """Split the group's files into n_parts contiguous jobs."""
         n_files = arr.shape[0] // split_size
         per = (n_files + n_parts - 1) // max(1, n_parts)
         for a in range(0, n_files, max(1, per)):
             b = min(n_files, a + per)
-            self.q.put((datadir, first + a, arr[a * split_size:b * split_size], split_size))
+            if barrier is not None:
+                barrier.add()
+            self.q.put((datadir, first + a, arr[a * split_size:b * split_size], split_size, barrier))
 
     def close(self):
         for _ in self.threads:
@@ -185,7 +211,48 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
 
     drawer = threading.Thread(target=draw_groups, daemon=True)
     drawer.start()
+    # GPU path: poses are written straight into a [rows, C] group buffer (two, alternating); the group's shuffle
+    # (one device gather) and its read-back into pinned host memory run on a side stream while the next group
+    # renders; a finisher thread hands each host group to the .npy writers when its copy event has fired.
+    on_gpu = render_fn is None and device is not None and device.type == "cuda"
+    finisher = None
+    if on_gpu:
+        n_buf = 3   # pinned host groups in flight: one being filled, up to two with the writers
+        copy_stream = torch.cuda.Stream(device)
+        group_bufs = [torch.empty((n_rows, C), dtype=torch.float32, device=device) for _ in range(2)]
+        shuffled = torch.empty((n_rows, C), dtype=torch.float32, device=device)
+        host_bufs = [torch.empty((n_rows, C), dtype=torch.float32).pin_memory() for _ in range(n_buf)]
+        host_free = queue.Queue()
+        for b in range(n_buf):
+            host_free.put(b)
+        buf_idle = [None, None]          # event: the side stream has finished reading group_bufs[i]
+        fin_q = queue.Queue()
+        fin_err = []
+
+        def finish_groups():
+            try:
+                while True:
+                    job = fin_q.get()
+                    if job is None:
+                        return
+                    ev, b, first = job
+                    ev.synchronize()
+                    host = host_bufs[b].numpy()
+                    # the writers read the pinned buffer in place, so it goes back to the free list only when this
+                    # group's files are on disk
+                    done = _AsyncNpySaver.Barrier(max(1, writer_threads))
+                    saver.submit(datadir, first, host[:F * split_size], split_size, n_parts=max(1, writer_threads),
+                                 barrier=done)
+                    done.wait()
+                    host_free.put(b)
+            except Exception as e:
+                fin_err.append(e)
+                host_free.put(-1)
+
+        finisher = threading.Thread(target=finish_groups, daemon=True)
+        finisher.start()
     try:
+        n_done = 0
         while True:
             item = todo.get()
             if item is None:
@@ -196,7 +263,13 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
             if stream == "per_group":
                 torch.manual_seed(seed + g)   # CPU-generator draws inside the renders (t_rand, u, noise)
             rows = []
-            for pose, focal_ in zip(poses, focals):
+            gbuf = None
+            if on_gpu:
+                gi = n_done & 1
+                gbuf = group_bufs[gi]
+                if buf_idle[gi] is not None:
+                    torch.cuda.current_stream(device).wait_event(buf_idle[gi])
+            for k, (pose, focal_) in enumerate(zip(poses, focals)):
                 c2w = pose[:3, :4]
                 if render_fn is not None:
                     o, d = _host_rays(H, W, focal_, c2w)
@@ -207,16 +280,45 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
                 if learn_depth:
                     depth = depth[..., None]
                     parts.append(o + d * depth.expand_as(d) if learn_depth == 'surface' else depth)
-                rows.append(torch.cat([p.reshape(H * W, -1).float() for p in parts], -1))
+                parts = [p.reshape(H * W, -1).float() for p in parts]
+                if gbuf is not None:
+                    torch.cat(parts, -1, out=gbuf[k * H * W:(k + 1) * H * W])
+                else:
+                    rows.append(torch.cat(parts, -1))
                 if progress is not None:
-                    progress(g, len(rows))
-            data = torch.cat(rows, 0)                       # [i_save*H*W, C]
-            data = data[ix.to(data.device)]
-            host = data.cpu().numpy() if data.is_cuda else data.numpy()
-            assert host.dtype == np.float32 and host.shape[1] == C
-            saver.submit(datadir, first, host[:F * split_size], split_size, n_parts=max(1, writer_threads))
+                    progress(g, k + 1)
+            if gbuf is not None:
+                b = host_free.get()
+                if fin_err:
+                    raise fin_err[0]
+                rendered = torch.cuda.Event()
+                rendered.record(torch.cuda.current_stream(device))
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(rendered)
+                    torch.index_select(gbuf, 0, ix.to(device, non_blocking=True), out=shuffled)   # data[ix1][ix2]
+                    host_bufs[b].copy_(shuffled, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                buf_idle[n_done & 1] = ev
+                fin_q.put((ev, b, first))
+            else:
+                data = torch.cat(rows, 0)                       # [i_save*H*W, C]
+                data = data[ix.to(data.device)]
+                host = data.cpu().numpy() if data.is_cuda else data.numpy()
+                assert host.dtype == np.float32 and host.shape[1] == C
+                saver.submit(datadir, first, host[:F * split_size], split_size, n_parts=max(1, writer_threads))
             written.extend(range(first, first + F))
+            n_done += 1
+        if finisher is not None:
+            fin_q.put(None)
+            finisher.join()
+            finisher = None
+            if fin_err:
+                raise fin_err[0]
     finally:
+        if finisher is not None:     # error path: let the finisher drain and stop
+            fin_q.put(None)
+            finisher.join()
         saver.close()
     return written
 
