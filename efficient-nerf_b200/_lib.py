@@ -29,6 +29,7 @@ SIGNATURES = {
     "r2l_points_from_rays": [_c_ll, _c_int, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_vp],
     "r2l_point_sample": [_c_int, _c_int, _c_dbl, _c_f32p, _c_f32p, _c_int, _c_f32p, _c_vp],
     "r2l_point_sample_batch": [_c_int, _c_int, _c_int, _c_dbl, _c_f32p, _c_f32p, _c_int, _c_f32p, _c_vp],
+    "r2l_plucker": [_c_ll, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_vp],
     "r2l_embed": [_c_ll, _c_int, _c_int, _c_int, _c_int, _c_f32p, _c_f32p, _c_vp],
     "r2l_raw2outputs": [_c_ll, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_ll, _c_f32p, _c_int, _c_f32p, _c_f32p,
                         _c_f32p, _c_f32p, _c_f32p, _c_vp],

@@ -89,6 +89,26 @@ __global__ void normalize_dirs_kernel(long long n, const float* __restrict__ d, 
   }
 }
 
+// Pluecker ray coordinates [d, o x d] (model/nerf_raybased.py:170-190).  ATen's CPU cross kernel evaluates each
+// component a1*b2 - a2*b1 as fma(a1, b2, -round(a2*b1)) (pinned against the reference's outputs in
+// tests/golden/sampler_extra.npz: bit-exact in that form, 73/630 elements off by 1 ulp with two rounded products);
+// the same form here.  o_stride == 0 broadcasts one origin (sample_test_plucker).
+__global__ void plucker_kernel(long long n, const float* __restrict__ o, long long o_stride,
+                               const float* __restrict__ d, long long d_stride, float* __restrict__ out) {
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < n;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float ox = o[p * o_stride], oy = o[p * o_stride + 1], oz = o[p * o_stride + 2];
+    const float dx = d[p * d_stride], dy = d[p * d_stride + 1], dz = d[p * d_stride + 2];
+    float* r = out + 6 * p;
+    r[0] = dx;
+    r[1] = dy;
+    r[2] = dz;
+    r[3] = __fmaf_rn(oy, dz, -__fmul_rn(oz, dy));
+    r[4] = __fmaf_rn(oz, dx, -__fmul_rn(ox, dz));
+    r[5] = __fmaf_rn(ox, dy, -__fmul_rn(oy, dx));
+  }
+}
+
 // z_vals = near*(1-t) + far*t  (or lindisp), optional stratified perturbation (main.py:676-699)
 __global__ void z_vals_kernel(long long n, int S, const float* __restrict__ near, const float* __restrict__ far,
                               long long nf_stride, const float* __restrict__ t_vals, int lindisp,
@@ -209,6 +229,17 @@ int r2l_normalize_dirs(long long n, const float* dirs, long long stride, float* 
   if (n == 0) return R2L_OK;
   R2L_CHECK_ARG(dirs && out, "r2l_normalize_dirs: null pointer");
   normalize_dirs_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, dirs, stride, out);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+int r2l_plucker(long long n, const float* rays_o, long long o_stride, const float* rays_d, long long d_stride,
+                float* out, void* stream) {
+  R2L_CHECK_ARG(n >= 0 && (o_stride == 0 || o_stride >= 3) && d_stride >= 3, "r2l_plucker: bad sizes");
+  if (n == 0) return R2L_OK;
+  R2L_CHECK_ARG(rays_o && rays_d && out, "r2l_plucker: null pointer");
+  plucker_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, rays_o, o_stride, rays_d, d_stride,
+                                                                                 out);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }

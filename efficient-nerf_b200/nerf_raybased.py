@@ -561,6 +561,65 @@ class PointSampler():
                           _lib.ptr(pts), _lib.stream_ptr(dev))
         return pts
 
+    def sample_train_cnnstyle(self, rays_o, rays_d, perturb, t_rand=None):
+        """CNN-style patches (model/nerf_raybased.py:149-168; `sample_train2` :128-147 is the same code): rays_o /
+        rays_d [n_img, ph, pw, 3] -> pts [n_img, ph, pw, n_sample, 3]; with perturb > 0 ONE stratification offset
+        per image (t_rand [n_img], drawn on the CPU generator like the reference, or injected)."""
+        dev = self.z_vals.device
+        ro = _lib.as_f32_cuda(rays_o, dev, "rays_o")
+        rd = _lib.as_f32_cuda(rays_d, dev, "rays_d")
+        if ro.dim() != 4 or ro.shape[-1] != 3 or rd.shape != ro.shape:
+            raise ValueError(f"rays_o / rays_d must be [n_img, ph, pw, 3], got {tuple(ro.shape)} / {tuple(rd.shape)}")
+        S = self.n_sample
+        n_img = ro.shape[0]
+        n = ro.numel() // 3
+        pts = torch.empty(tuple(ro.shape[:3]) + (S, 3), dtype=torch.float32, device=dev)
+        ro2, rd2 = ro.reshape(-1, 3).contiguous(), rd.reshape(-1, 3).contiguous()
+        with torch.cuda.device(dev):
+            if perturb > 0.:
+                if t_rand is None:
+                    t_rand = torch.rand(n_img)  # CPU generator, then uploaded (model:160)
+                tr = _lib.as_f32_cuda(t_rand, dev, "t_rand").reshape(n_img, 1)
+                mids = .5 * (self.z_vals[1:] + self.z_vals[:-1])
+                upper = torch.cat([mids, self.z_vals[-1:]], -1)
+                lower = torch.cat([self.z_vals[:1], mids], -1)
+                z_img = lower + (upper - lower) * tr                                  # [n_img, S]
+                z = z_img[:, None, :].expand(n_img, n // n_img, S).reshape(n, S).contiguous()
+                _lib.call("r2l_points_from_rays", n, S, _lib.ptr(ro2), 3, _lib.ptr(rd2), 3, _lib.ptr(z), S,
+                          _lib.ptr(pts), _lib.stream_ptr(dev))
+            else:
+                z = self.z_vals.contiguous()
+                _lib.call("r2l_points_from_rays", n, S, _lib.ptr(ro2), 3, _lib.ptr(rd2), 3, _lib.ptr(z), 0,
+                          _lib.ptr(pts), _lib.stream_ptr(dev))
+        return pts
+
+    sample_train2 = sample_train_cnnstyle   # "kept for back-compatibility" in the reference: identical body
+
+    def _plucker(self, ro, o_stride, rd):
+        n = rd.shape[0]
+        out = torch.empty((n, 6), dtype=torch.float32, device=rd.device)
+        with torch.cuda.device(rd.device):
+            _lib.call("r2l_plucker", n, _lib.ptr(ro), o_stride, _lib.ptr(rd), 3, _lib.ptr(out),
+                      _lib.stream_ptr(rd.device))
+        return out
+
+    def sample_train_plucker(self, rays_o, rays_d):
+        """Pluecker coordinates [rays_d, rays_o x rays_d] as the ray representation (model:170-176)."""
+        dev = self.z_vals.device
+        ro = _lib.as_f32_cuda(rays_o, dev, "rays_o").reshape(-1, 3).contiguous()
+        rd = _lib.as_f32_cuda(rays_d, dev, "rays_d").reshape(-1, 3).contiguous()
+        if ro.shape != rd.shape:
+            raise ValueError("rays_o and rays_d must have the same shape")
+        return self._plucker(ro, 3, rd)
+
+    def sample_test_plucker(self, c2w):  # c2w: [3, 4]
+        """model:178-190 (the `--plucker` branch of render_path, main.py:296-298): [H*W, 6]."""
+        from .run_nerf_raybased_helpers import get_rays
+        dev = self.z_vals.device
+        c = _lib.as_f32_cuda(c2w, dev, "c2w")[:3, :4].contiguous()
+        _, rd = get_rays(self.H, self.W, self.focal, c)
+        return self._plucker(c[:3, 3].contiguous(), 0, rd.reshape(-1, 3))
+
 
 class PositionalEmbedder():
 
@@ -576,3 +635,12 @@ class PositionalEmbedder():
         if self.lazy and x.dim() == 2:
             return LazyEmbedding(_lib.as_f32_cuda(x), self.L, self.include_input)
         return _embed(x, self.L, self.include_input, 1)  # [n_ray, dim_pts*(2L+1)]
+
+    def embed_cnnstyle(self, x):
+        """model:218-223 (and `embed` :210-216, the same code): x [..., dim] -> [..., dim, 2L+1]; the same numbers as
+        __call__, without flattening the feature axes."""
+        x = _lib.as_f32_cuda(x)
+        y = _embed(x.reshape(-1, x.shape[-1]), self.L, self.include_input, 1)
+        return y.reshape(tuple(x.shape) + (self.embed_dim,))
+
+    embed = embed_cnnstyle

@@ -62,6 +62,11 @@ int r2l_point_sample(int H, int W, double focal, const float* c2w, const float* 
 int r2l_point_sample_batch(int n_poses, int H, int W, double focal, const float* c2w, const float* z_vals, int S,
                            float* pts, void* stream);
 
+/* Pluecker ray representation out [n,6] = [rays_d, cross(rays_o, rays_d)]; o_stride == 0 broadcasts one origin.
+ * replaces PointSampler.sample_train_plucker / sample_test_plucker, model/nerf_raybased.py:170-190 (main.py:296-298). */
+int r2l_plucker(long long n, const float* rays_o, long long o_stride, const float* rays_d, long long d_stride,
+                float* out, void* stream);
+
 /* ---- positional encoding ------------------------------------------------------------------ */
 
 /* layout 0: Embedder.embed (utils/run_nerf_raybased_helpers.py:24-74), x [rows, D] -> [rows, D*(1+2L)]

@@ -359,3 +359,40 @@ def ssim(img, ref, window_size=11):
     C1, C2 = 0.01**2, 0.03**2
     m = ((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))
     return m.mean()
+
+
+# ----------------------------------------------------------------------------------------------------
+# Remaining PointSampler / PositionalEmbedder forms (model/nerf_raybased.py:128-190, 210-223)
+# ----------------------------------------------------------------------------------------------------
+def sample_train_cnnstyle(z_vals, rays_o, rays_d, perturb, t_rand=None):
+    """model:149-168 (= sample_train2 :128-147): rays [n_img, ph, pw, 3]; one offset t_rand [n_img] per image."""
+    z = z_vals[None, None, None, :].expand(*rays_o.shape[:3], z_vals.shape[0])
+    if perturb > 0.:
+        mids = .5 * (z[..., 1:] + z[..., :-1])
+        upper = torch.cat([mids, z[..., -1:]], dim=-1)
+        lower = torch.cat([z[..., :1], mids], dim=-1)
+        t = t_rand[:, None, None, None].expand_as(z)
+        z = lower + (upper - lower) * t
+    return rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+
+
+def plucker(rays_o, rays_d):
+    """model:170-176: [rays_d, cross(rays_o, rays_d)]."""
+    return torch.cat([rays_d, torch.cross(rays_o, rays_d, dim=-1)], dim=-1)
+
+
+def sample_test_plucker(H, W, focal, c2w):
+    """model:178-190."""
+    ro, rd = get_rays(H, W, focal, c2w)
+    rd = rd.reshape(-1, 3)
+    return plucker(c2w[:3, -1].expand(rd.shape), rd)
+
+
+def embed_cnnstyle(x, L, include_input=True):
+    """model:210-223: [..., dim] -> [..., dim, 2L+1]."""
+    w = 2**torch.linspace(0, L - 1, steps=L)
+    y = x[..., :, None] * w
+    y = torch.cat([torch.sin(y), torch.cos(y)], dim=-1)
+    if include_input:
+        y = torch.cat([y, x.unsqueeze(dim=-1)], dim=-1)
+    return y

@@ -246,3 +246,25 @@ def test_merge_sorted(E):
         bq = torch.sort(torch.round(b * 4) / 4, -1)[0]
         out, _ = E.merge_sorted(aq.cuda(), bq.cuda(), want_std=True)
         exact(out, torch.sort(torch.cat([aq, bq], -1), -1)[0], f"tied merge {na}+{nbv}")
+
+
+# ------------------------------------------------------------------ remaining PointSampler / PositionalEmbedder forms
+def test_sampler_extra_forms_golden(E, golden):
+    """sample_train_cnnstyle / sample_train2 (one stratification offset per image), Pluecker rays
+    (sample_train_plucker / sample_test_plucker, the --plucker branch of render_path) and the unflattened
+    embed / embed_cnnstyle against the outputs of the reference's own classes (oracle/make_golden_sampler.py)."""
+    g = golden("sampler_extra")
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    ps = E.PointSampler(H, W, focal, 8, 2., 6.)
+    ro, rd = cu(g["ro"]), cu(g["rd"])
+    close(ps.sample_train_cnnstyle(ro, rd, 1., t_rand=t(g["t_rand"])), g["pts_perturb"], 2e-6, "cnnstyle perturb")
+    close(ps.sample_train2(ro, rd, 0.), g["pts_det"], 2e-6, "cnnstyle det")
+    assert ps.sample_train_cnnstyle(ro, rd, 0.).shape == (3, 5, 7, 8, 3)
+    exact(ps.sample_train_plucker(ro.reshape(-1, 3), rd.reshape(-1, 3)), g["plucker_train"], "plucker train")
+    close(ps.sample_test_plucker(cu(g["c2w"])), g["plucker_test"], 2e-6, "plucker test")
+    pe = E.PositionalEmbedder(5)
+    e = pe.embed_cnnstyle(cu(g["x"]))
+    assert e.shape == (2, 3, 4, 6, 3, 11)
+    close(e, g["embed_L5"], 2e-6, "embed_cnnstyle")
+    close(pe.embed(cu(g["x"])), g["embed_L5"], 2e-6, "embed")
+

@@ -122,3 +122,16 @@ def test_image_metrics(golden, O):
         assert float(O.ssim(rgb.permute(2, 0, 1), gt.permute(2, 0, 1))) == f("ssim")
         mse = O.img2mse(rgb, gt)
         assert float(mse) == f("mse") and float(O.mse2psnr(mse)) == f("psnr")
+
+
+def test_sampler_extra_forms(golden, O):
+    """CNN-style point sampling, Pluecker rays and the unflattened embedding against the reference's own outputs."""
+    g = golden("sampler_extra")
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    z = 2. * (1 - torch.linspace(0., 1., 8)) + 6. * torch.linspace(0., 1., 8)
+    ro, rd = t(g["ro"]), t(g["rd"])
+    assert torch.equal(O.sample_train_cnnstyle(z, ro, rd, 1., t(g["t_rand"])), t(g["pts_perturb"]))
+    assert torch.equal(O.sample_train_cnnstyle(z, ro, rd, 0.), t(g["pts_det"]))
+    assert torch.equal(O.plucker(ro.reshape(-1, 3), rd.reshape(-1, 3)), t(g["plucker_train"]))
+    assert torch.equal(O.sample_test_plucker(H, W, focal, t(g["c2w"])), t(g["plucker_test"]))
+    assert torch.equal(O.embed_cnnstyle(t(g["x"]), 5), t(g["embed_L5"]))
