@@ -19,7 +19,26 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .run_nerf_raybased_helpers import Embedder, get_embedder, raw2outputs, _embed  # noqa: F401 (re-exported)
+from .run_nerf_raybased_helpers import Embedder, get_embedder, _embed  # noqa: F401 (re-exported)
+from .run_nerf_raybased_helpers import raw2outputs as _raw2outputs
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False, global_step=-1, print=print):
+    """The module's own twin of raw2outputs (model/nerf_raybased.py:226-295: same math, `global_step` / `print` in
+    place of `verbose`)."""
+    return _raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd, pytest)
+
+
+def batchify(fn, chunk):
+    """model/nerf_raybased.py:298-309."""
+    from .render import batchify as _b
+    return _b(fn, chunk)
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """model/nerf_raybased.py:312-334."""
+    from .render import run_network as _r
+    return _r(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk)
 
 DEFAULT_PRECISION = "fp16"   # 'fp16' | 'bf16' | 'fp32'
 _DTYPE_CODE = {"fp16": 0, "bf16": 1}

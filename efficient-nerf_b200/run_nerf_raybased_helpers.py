@@ -230,3 +230,57 @@ def merge_sorted(z_vals, z_samples, want_std=False):
         _lib.call("r2l_merge_sorted", N, na, nbv, _lib.ptr(za), _lib.ptr(zb), _lib.ptr(out), _lib.ptr(z_std),
                   _lib.stream_ptr(za.device))
     return (out, z_std) if want_std else out
+
+
+# ----------------------------------------------------------------------------- the rest of the module's call surface
+def get_rays_np(H, W, focal, c2w):
+    """helpers:428-441: the numpy twin of get_rays (dataset preprocessing).  Computed by the same device kernel and
+    copied back, so both forms agree; returns numpy arrays like the reference."""
+    c = c2w if isinstance(c2w, torch.Tensor) else torch.as_tensor(np.asarray(c2w, dtype=np.float32))
+    f = float(focal.item() if hasattr(focal, "item") else focal)
+    ro, rd = get_rays(H, W, f, c)
+    return ro.cpu().numpy(), rd.cpu().numpy()
+
+
+to_array = lambda x: x if isinstance(x, np.ndarray) else x.data.cpu().numpy()   # helpers:16
+
+
+def to_tensor(x):
+    """helpers:14-15: onto the module's device (here: the current CUDA device)."""
+    return x.to(_dev()) if isinstance(x, torch.Tensor) else torch.Tensor(x).to(_dev())
+
+
+def undataparallel(input):
+    """helpers:408-425."""
+    from .compat import undataparallel as _u
+    return _u(input)
+
+
+def load_weights_v2(model, ckpt, key):
+    """helpers:362-382: load ckpt[key] when model and weights agree on the DataParallel `module.` prefix."""
+    model_dp = any(name.startswith('module.') for name, _ in model.named_modules())
+    state_dict = ckpt[key]
+    weights_dp = any(k.startswith('module.') for k in state_dict)
+    if model_dp == weights_dp:
+        model.load_state_dict(state_dict)
+    else:
+        raise NotImplementedError
+
+
+def load_weights(model, ckpt_path, key):
+    """helpers:347-359 (without smilelogging's path check): strips `module.` and loads ckpt[key]."""
+    from .compat import load_checkpoint
+    ckpt = load_checkpoint(ckpt_path)
+    model.load_state_dict(undataparallel(dict(ckpt[key])) if not isinstance(ckpt[key], torch.nn.Module) else
+                          ckpt[key].state_dict())
+    return ckpt_path, ckpt
+
+
+def __getattr__(name):
+    # batchify / run_network live in render.py (their main.py twins, :51-104); the reference's helpers module has
+    # them too (helpers:147-183), so `from utils.run_nerf_raybased_helpers import run_network` keeps working
+    if name in ("batchify", "run_network"):
+        from . import render
+        return getattr(render, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+

@@ -114,3 +114,33 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "Mrays/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_mirror_exposes_the_reference_call_surface(E):
+    """Every name the reference's two hot-path modules define (def / class / lambda at module level, and the methods
+    of their classes) exists under the same name in the mirror — minus what DESIGN.md §7 declares out of scope
+    (translate_origin*, parse_expid_iter, get_selected_coords, visualize_3d: training / plotting helpers;
+    NeRF.load_weights_from_keras).  Lists taken from utils/run_nerf_raybased_helpers.py and model/nerf_raybased.py."""
+    helpers = ["to_tensor", "to_array", "to8b", "img2mse", "mse2psnr", "Embedder", "get_embedder", "raw2outputs",
+               "batchify", "run_network", "get_rays", "ndc_rays", "sample_pdf", "load_weights", "load_weights_v2",
+               "undataparallel", "get_rays_np"]
+    for n in helpers:
+        assert hasattr(E.run_nerf_raybased_helpers, n), f"run_nerf_raybased_helpers.{n} missing"
+    model = {"Embedder": ["create_embedding_fn", "embed"], "get_embedder": [], "raw2outputs": [], "batchify": [],
+             "run_network": [], "get_activation": [], "NeRF": ["forward"], "ResMLP": ["forward"],
+             "NeRF_v3_2": ["forward"],
+             "PointSampler": ["sample_test", "sample_test2", "sample_train", "sample_train2", "sample_train_cnnstyle",
+                              "sample_train_plucker", "sample_test_plucker"],
+             "PositionalEmbedder": ["__call__", "embed", "embed_cnnstyle"]}
+    for n, methods in model.items():
+        assert hasattr(E.nerf_raybased, n), f"nerf_raybased.{n} missing"
+        for m in methods:
+            assert hasattr(getattr(E.nerf_raybased, n), m), f"nerf_raybased.{n}.{m} missing"
+    import inspect
+    sig = inspect.signature(E.nerf_raybased.raw2outputs)
+    assert list(sig.parameters) == ["raw", "z_vals", "rays_d", "raw_noise_std", "white_bkgd", "pytest", "global_step",
+                                    "print"]
+    sig = inspect.signature(E.run_nerf_raybased_helpers.sample_pdf)
+    assert list(sig.parameters)[:5] == ["bins", "weights", "N_samples", "det", "pytest"]
+    for n in ("render", "render_rays", "batchify_rays", "batchify", "run_network", "render_path", "raw2outputs"):
+        assert hasattr(E.render, n), f"render.{n} missing"
