@@ -730,13 +730,20 @@ int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long lo
   R2L_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "r2l_nerf_forward_embedded: out must be 16-byte aligned");
   int rc = check_dbg(m, "r2l_nerf_forward_embedded");
   if (rc != R2L_OK) return rc;
-  NerfParams p{};
-  p.S = 1;
-  p.n_rows = M;
-  p.raw = out;
-  p.embedded = x;
-  p.emb_stride = ldx;
-  return nerf_run(m, p, static_cast<cudaStream_t>(stream));
+  // On this path every row is its own "ray" for the per-row view-branch bias workspace of the ping-pong kernel
+  // (512 B per row), so large inputs are processed in blocks of 2^20 rows (a multiple of the 512-row unit).
+  const long long block = m->nerf_pp ? (1LL << 20) : M;
+  for (long long off = 0; off < M; off += block) {
+    NerfParams p{};
+    p.S = 1;
+    p.n_rows = (M - off < block) ? (M - off) : block;
+    p.raw = out + off * 4;
+    p.embedded = x + off * ldx;
+    p.emb_stride = ldx;
+    rc = nerf_run(m, p, static_cast<cudaStream_t>(stream));
+    if (rc != R2L_OK) return rc;
+  }
+  return R2L_OK;
 }
 
 // Profiling hook: r2l_nerf_forward + per-CTA cycle counters prof[n_CTAs][8] (device int64): [0] MMA thread total,

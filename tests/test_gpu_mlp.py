@@ -125,6 +125,20 @@ def test_nerf_forward_tensor_core(E, O, precision, tol):
         assert maxabs(out, ref) < tol, (precision, M, maxabs(out, ref))
 
 
+def test_nerf_forward_embedded_large_input_is_blocked(E, O):
+    """NeRF.forward(x) on more rows than one 2^20-row block of the API path: same values as the rows alone."""
+    sdc, _ = O.nerf_state_dicts(0)
+    net = load_nerf(E, sdc, "fp16")
+    torch.manual_seed(4)
+    M = (1 << 20) + 777
+    x = torch.randn(M, 90, device="cuda") * 0.5
+    with torch.no_grad():
+        y = net(x)
+        assert y.shape == (M, 4) and bool(torch.isfinite(y).all())
+        for lo, hi in ((0, 300), ((1 << 20) - 100, (1 << 20) + 300), (M - 200, M)):
+            assert torch.equal(y[lo:hi], net(x[lo:hi].contiguous())), (lo, hi)
+
+
 def test_nerf_fused_encode_matches_api_path(E, O):
     """forward_samples (encoding fused in-kernel) == forward(embedded) on the same points."""
     sdc, _ = O.nerf_state_dicts(0)
