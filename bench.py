@@ -504,6 +504,14 @@ def extras(E, O, peaks, precision, main_workload):
         ms = timeit(lambda: E.sample_pdf(bins, w, 128, det=True))
         gbs = N * 1012 / ms / 1e6
         out["sample_pdf_Ni128"] = {"ms": ms, "GB_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm"], "rays": N}
+        # the fused form render_rays uses (mids + sample_pdf + sorted merge + z_std): 512 B in, 772 B out per ray
+        zc = z[:, :64].contiguous()
+        wc = torch.rand(N, 64, device="cuda")
+        ut = torch.linspace(0., 1., 128)
+        ms = timeit(lambda: E.run_nerf_raybased_helpers.hier_sample(zc, wc, 128, ut))
+        gbs = N * 1284 / ms / 1e6
+        out["hier_sample_64+128"] = {"ms": ms, "GB_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm"], "rays": N,
+                                     "note": "the unfused kernels move 2548 B/ray for the same result"}
     return out
 
 

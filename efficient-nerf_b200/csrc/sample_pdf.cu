@@ -253,6 +253,178 @@ sample_pdf_fast_kernel(long long n_rays, const float* __restrict__ bins, long lo
   }
 }
 
+// ---- fused hierarchical sampling: mids + sample_pdf + sorted merge + z_std in ONE kernel ----------------------------
+// main.py:720-733, 750 for the configuration every BASELINE render uses (64 coarse samples, a shared `u` table):
+//   z_vals_mid = .5 * (z[1:] + z[:-1]);  z_samples = sample_pdf(z_vals_mid, weights[1:-1], Ni, det);
+//   z_all = sort(cat[z, z_samples]);     z_std = std(z_samples, unbiased=False)
+// The unfused path runs two elementwise torch kernels, sample_pdf and merge_sort and moves 2.5 KB per ray through
+// HBM; here a ray costs 512 B in and 4*(64+Ni) B out, and the merge is almost free: a sample drawn from bin
+// [mid_b, mid_{b+1}] has exactly the coarse depths z_0..z_b (and possibly z_{b+1}) below it, so its merged position
+// is k + b + 1 + (z_{b+1} <= s) (verified / corrected by a local scan, so any ascending z is handled exactly); the
+// coarse depths find theirs by a 7-step search over the (ascending) samples in shared memory.  Rays whose z or
+// samples are NOT ascending (never the case with a non-decreasing u and stratified z) take a bitonic sort instead.
+// Same arithmetic, in the same order, as sample_pdf_fast_kernel and merge_sort_kernel: results are bit-identical.
+template <int NIT>
+__global__ void __launch_bounds__(kPdfWarps * 32)
+hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const float* __restrict__ weights,
+                   const float* __restrict__ u, float* __restrict__ z_out, float* __restrict__ z_std,
+                   float* __restrict__ samples_out, long long* __restrict__ inds_out) {
+  constexpr int NS = 64, NB = 63, NW = 62, Ni = 32 * NIT, NO = NS + Ni, P2 = 32;
+  constexpr int PSORT = (NO <= 128) ? 128 : 256;
+  __shared__ __align__(16) float s_w_all[kPdfWarps][64];
+  __shared__ __align__(16) float2 s_cb_all[kPdfWarps][64];   // (cdf_j, bins_j), j < 63; [63] = (+inf, 0)
+  __shared__ __align__(16) float s_z_all[kPdfWarps][64];
+  __shared__ __align__(16) float s_o_all[kPdfWarps][PSORT];  // samples (fast path) / sort buffer (fallback)
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float* const s_w = s_w_all[wib];
+  float2* const s_cb = s_cb_all[wib];
+  float* const s_z = s_z_all[wib];
+  float* const s_o = s_o_all[wib];
+  float ureg[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) ureg[it] = __ldg(u + it * 32 + lane);
+  if (lane == 0) s_cb[63] = make_float2(__int_as_float(0x7f800000), 0.f);
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kPdfWarps + wib;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kPdfWarps;
+  for (long long ray = warp0; ray < n_rays; ray += nwarps) {
+    const float* rz = z_vals + ray * NS;
+    const float* rw = weights + ray * NS + 1;   // weights[..., 1:-1]
+    const float z0 = __ldg(rz + lane), z1 = __ldg(rz + lane + 32);
+    s_z[lane] = z0;
+    s_z[lane + 32] = z1;
+    s_w[lane] = __fadd_rn(__ldg(rw + lane), 1e-5f);
+    if (lane + 32 < NW) s_w[lane + 32] = __fadd_rn(__ldg(rw + lane + 32), 1e-5f);
+    __syncwarp();
+    // bins_j = .5 * (z_{j+1} + z_j): one rounded add, an exact halving
+    const float b0 = __fmul_rn(0.5f, __fadd_rn(s_z[lane + 1], z0));
+    const float b1 = (lane + 32 < NB) ? __fmul_rn(0.5f, __fadd_rn(s_z[lane + 33], z1)) : 0.f;
+    bool asc = (z0 <= s_z[lane + 1]) && (lane + 33 > 63 || z1 <= s_z[lane + 33]);
+    const float total = aten_row_sum_ct<NW>(s_w, lane);
+    const float2 wp = *reinterpret_cast<const float2*>(s_w + 2 * lane);
+    const double p0 = (2 * lane < NW) ? static_cast<double>(__fdiv_rn(wp.x, total)) : 0.0;
+    const double p1 = (2 * lane + 1 < NW) ? static_cast<double>(__fdiv_rn(wp.y, total)) : 0.0;
+    double p = p0 + p1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double q = shfl_up_f64_(p, o);
+      if (lane >= o) p += q;
+    }
+    double excl = shfl_up_f64_(p, 1);
+    if (lane == 0) excl = 0.0;
+    __syncwarp();
+    s_cb[lane].y = b0;
+    if (lane + 32 < NB) s_cb[lane + 32].y = b1;
+    if (lane == 0) s_cb[0].x = 0.0f;
+    if (2 * lane < NW) s_cb[2 * lane + 1].x = static_cast<float>(excl + p0);
+    if (2 * lane + 1 < NW) s_cb[2 * lane + 2].x = static_cast<float>(excl + (p0 + p1));
+    __syncwarp();
+    float sv[NIT];
+    int cle[NIT];      // #{coarse z <= sample}
+    double sum = 0.0;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const float uk = ureg[it];
+      int pos = 0;
+#pragma unroll
+      for (int st = P2; st > 0; st >>= 1) {
+        if (s_cb[pos + st - 1].x <= uk) pos += st;
+      }
+      const int below = max(pos - 1, 0);
+      const int above = min(pos, NB - 1);
+      const float2 lo = s_cb[below], hi = s_cb[above];
+      float denom = __fsub_rn(hi.x, lo.x);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(uk, lo.x), denom);
+      const float sm_ = __fadd_rn(lo.y, __fmul_rn(t, __fsub_rn(hi.y, lo.y)));
+      sv[it] = sm_;
+      sum += static_cast<double>(sm_);
+      s_o[it * 32 + lane] = sm_;
+      if (samples_out != nullptr) samples_out[ray * Ni + it * 32 + lane] = sm_;
+      if (inds_out != nullptr) inds_out[ray * Ni + it * 32 + lane] = pos;
+      // coarse depths not above the sample: z_0..z_below lie below mid_below <= sample; then a local scan
+      int c = below + 1;
+      while (c < NS && s_z[c] <= sm_) ++c;
+      while (c > 0 && s_z[c - 1] > sm_) --c;
+      cle[it] = c;
+    }
+    __syncwarp();
+    // samples ascending?  (sample k lives at s_o[k], k = it*32 + lane)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int k = it * 32 + lane;
+      if (k + 1 < Ni) asc = asc && (sv[it] <= s_o[k + 1]);
+      asc = asc && (sv[it] == sv[it]);
+    }
+    if (z_std != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int lo_ = __double2loint(sum), hi_ = __double2hiint(sum);
+        lo_ = __shfl_xor_sync(0xffffffffu, lo_, o);
+        hi_ = __shfl_xor_sync(0xffffffffu, hi_, o);
+        sum += __hiloint2double(hi_, lo_);
+      }
+      const double mean = sum / Ni;
+      double ss = 0.0;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const double d = static_cast<double>(sv[it]) - mean;
+        ss += d * d;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int lo_ = __double2loint(ss), hi_ = __double2hiint(ss);
+        lo_ = __shfl_xor_sync(0xffffffffu, lo_, o);
+        hi_ = __shfl_xor_sync(0xffffffffu, hi_, o);
+        ss += __hiloint2double(hi_, lo_);
+      }
+      if (lane == 0) z_std[ray] = static_cast<float>(sqrt(ss / Ni));
+    }
+    float* const out = z_out + ray * NO;
+    if (__all_sync(0xffffffffu, asc)) {
+      // stable rank merge, coarse depths first on ties: rank(z_i) = i + #{s < z_i}, rank(s_k) = k + #{z <= s_k}
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) out[it * 32 + lane + cle[it]] = sv[it];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        const float v = h ? z1 : z0;
+        int lo_ = 0, hi_ = Ni;   // first sample >= v
+        while (lo_ < hi_) {
+          const int mid = (lo_ + hi_) >> 1;
+          if (s_o[mid] < v) lo_ = mid + 1; else hi_ = mid;
+        }
+        out[i + lo_] = v;
+      }
+    } else {
+      // general path: bitonic sort of [samples, z, +inf padding] in shared memory (values only)
+      __syncwarp();
+      s_o[Ni + lane] = z0;
+      s_o[Ni + 32 + lane] = z1;
+      for (int j = NO + lane; j < PSORT; j += 32) s_o[j] = __int_as_float(0x7f800000);
+      __syncwarp();
+      for (int k = 2; k <= PSORT; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < PSORT; i += 32) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const float a = s_o[i], b = s_o[ixj];
+              const bool up = ((i & k) == 0);
+              if ((a > b) == up) {
+                s_o[i] = b;
+                s_o[ixj] = a;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      for (int j = lane; j < NO; j += 32) out[j] = s_o[j];
+    }
+    __syncwarp();
+  }
+}
+
 // z_out = sort(cat[z_a, z_b]) per ray (values only, ascending; main.py:730-732) and
 // z_std = std(z_b, unbiased=False) (main.py:750).  Warp-level bitonic sort in shared memory.
 __global__ void __launch_bounds__(kPdfWarps * 32)
@@ -386,6 +558,28 @@ int r2l_sample_pdf(long long n_rays, int nb, int Ni, const float* bins, long lon
     R2L_CUDA(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sample_pdf_kernel<<<static_cast<int>(blocks), kPdfWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       n_rays, nb, Ni, bins, bins_stride, weights, w_stride, u, u_per_ray, samples, inds_out, row_pad);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+int r2l_hier_sample(long long n_rays, int n_coarse, int Ni, const float* z_vals, const float* weights, const float* u,
+                    float* z_out, float* z_std, float* samples, long long* inds_out, void* stream) {
+  R2L_CHECK_ARG(n_rays >= 0, "r2l_hier_sample: bad sizes");
+  R2L_CHECK_ARG(n_coarse == 64 && (Ni == 128 || Ni == 64),
+                "r2l_hier_sample: fused path needs 64 coarse samples and 64 or 128 fine samples (got %d, %d); use "
+                "r2l_sample_pdf + r2l_merge_sorted", n_coarse, Ni);
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(z_vals && weights && u && z_out, "r2l_hier_sample: null pointer");
+  long long blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  auto st = static_cast<cudaStream_t>(stream);
+  if (Ni == 128)
+    hier_sample_kernel<4><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, z_out, z_std,
+                                                                              samples, inds_out);
+  else
+    hier_sample_kernel<2><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, z_out, z_std,
+                                                                              samples, inds_out);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }

@@ -20,6 +20,7 @@ import torch
 from . import _lib
 from .nerf_raybased import NeRF
 from .run_nerf_raybased_helpers import _dev  # noqa: E402
+from .run_nerf_raybased_helpers import hier_sample, hier_sample_supported  # noqa: E402
 from .run_nerf_raybased_helpers import (get_rays, ndc_rays, normalize_dirs, raw2outputs, sample_pdf, merge_sorted,
                                         _host_noise, _make_u)
 
@@ -113,15 +114,23 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     debug = {}
     if N_importance > 0:
         rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
-        z_vals_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
         if u is None:
             u, _ = _make_u([N_rays], N_importance, det=(perturb == 0.), pytest=pytest)
-        if return_debug:
-            z_samples, inds = sample_pdf(z_vals_mid, weights[..., 1:-1], N_importance, u=u, return_inds=True)
-            debug.update(z_vals0=z_vals, weights0=weights, raw0=raw, inds=inds, z_samples=z_samples)
+        if hier_sample_supported(z_vals, weights, N_importance, u):
+            # every deterministic render: mids, inverse-CDF sampling, sorted merge and z_std in one kernel
+            z_all, z_std, z_samples, inds = hier_sample(z_vals, weights, N_importance, u, want_samples=return_debug,
+                                                        want_inds=return_debug)
+            if return_debug:
+                debug.update(z_vals0=z_vals, weights0=weights, raw0=raw, inds=inds, z_samples=z_samples)
+            z_vals = z_all
         else:
-            z_samples = sample_pdf(z_vals_mid, weights[..., 1:-1], N_importance, u=u)
-        z_vals, z_std = merge_sorted(z_vals, z_samples, want_std=True)
+            z_vals_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+            if return_debug:
+                z_samples, inds = sample_pdf(z_vals_mid, weights[..., 1:-1], N_importance, u=u, return_inds=True)
+                debug.update(z_vals0=z_vals, weights0=weights, raw0=raw, inds=inds, z_samples=z_samples)
+            else:
+                z_samples = sample_pdf(z_vals_mid, weights[..., 1:-1], N_importance, u=u)
+            z_vals, z_std = merge_sorted(z_vals, z_samples, want_std=True)
         run_fn = network_fn if network_fine is None else network_fine
         raw = query(z_vals, run_fn)
         if noise1 is None and raw_noise_std > 0.:

@@ -219,6 +219,35 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False, u=None, return
     return (samples, inds) if return_inds else samples
 
 
+def hier_sample_supported(z_vals, weights, N_importance, u):
+    """True when the fused kernel applies: 64 coarse samples, 64 / 128 fine samples, ONE non-decreasing host-side `u`
+    table shared by all rays (det=True: every rendering configuration)."""
+    return (isinstance(z_vals, torch.Tensor) and z_vals.is_cuda and z_vals.dim() == 2 and z_vals.shape[1] == 64
+            and z_vals.dtype == torch.float32 and weights.shape == z_vals.shape and weights.is_cuda
+            and weights.dtype == torch.float32 and N_importance in (64, 128)
+            and isinstance(u, torch.Tensor) and not u.is_cuda and u.dim() == 1 and u.shape[0] == N_importance
+            and bool((u[1:] >= u[:-1]).all()))
+
+
+def hier_sample(z_vals, weights, N_importance, u, want_samples=False, want_inds=False):
+    """Fused main.py:720-733,750: z_vals_mid -> sample_pdf(weights[..., 1:-1], u) -> sort(cat[z_vals, z_samples]) and
+    std(z_samples), one launch.  Returns (z_all [N, 64+Ni], z_std [N], z_samples | None, inds | None); bit-identical to
+    sample_pdf + merge_sorted (tested)."""
+    z = z_vals.contiguous()
+    w = weights.contiguous()
+    dev = z.device
+    N = z.shape[0]
+    ud = _lib.as_f32_cuda(u, dev, "u")
+    out = torch.empty((N, 64 + N_importance), dtype=torch.float32, device=dev)
+    z_std = torch.empty((N,), dtype=torch.float32, device=dev)
+    samples = torch.empty((N, N_importance), dtype=torch.float32, device=dev) if want_samples else None
+    inds = torch.empty((N, N_importance), dtype=torch.int64, device=dev) if want_inds else None
+    with torch.cuda.device(dev):
+        _lib.call("r2l_hier_sample", N, 64, int(N_importance), _lib.ptr(z), _lib.ptr(w), _lib.ptr(ud), _lib.ptr(out),
+                  _lib.ptr(z_std), _lib.ptr(samples), _lib.ptr(inds), _lib.stream_ptr(dev))
+    return out, z_std, samples, inds
+
+
 def merge_sorted(z_vals, z_samples, want_std=False):
     """z = sort(cat[z_vals, z_samples], -1) (main.py:730-732); optionally std(z_samples) (main.py:750)."""
     za = _lib.as_f32_cuda(z_vals, name="z_vals")

@@ -229,6 +229,40 @@ def test_sample_pdf_full_frame_properties(E):
     assert torch.equal(s, s2)                               # deterministic
 
 
+@pytest.mark.parametrize("Ni", [64, 128])
+def test_hier_sample_fused_equals_unfused(E, Ni):
+    """r2l_hier_sample (mids + sample_pdf + sorted merge + z_std in one kernel) against the separate kernels, bit for
+    bit: stratified z, peaky / flat / all-zero weights (ties among the samples), and rows whose z is NOT ascending
+    (the in-kernel bitonic fallback)."""
+    torch.manual_seed(Ni)
+    N = 5000
+    t_vals = torch.linspace(0., 1., 64)
+    z = (2. * (1. - t_vals) + 6. * t_vals).expand(N, 64).clone()
+    mids = .5 * (z[:, 1:] + z[:, :-1])
+    upper, lower = torch.cat([mids, z[:, -1:]], -1), torch.cat([z[:, :1], mids], -1)
+    z[N // 2:] = (lower + (upper - lower) * torch.rand(N, 64))[N // 2:]          # stratified rows
+    w = torch.rand(N, 64)**8
+    w[::3] = torch.rand(N, 64)[::3]
+    w[5] = 0.                      # flat pdf
+    w[7, 10:50] = 0.               # long zero run: many equal cdf entries
+    z[11] = z[11].flip(-1)         # descending z: fallback path
+    z[12, 20], z[12, 40] = z[12, 40].clone(), z[12, 20].clone()
+    u = torch.linspace(0., 1., Ni)
+    zc, wc = z.cuda(), w.cuda()
+    assert E.run_nerf_raybased_helpers.hier_sample_supported(zc, wc, Ni, u)
+    assert not E.run_nerf_raybased_helpers.hier_sample_supported(zc, wc, Ni, torch.rand(Ni))       # not sorted
+    assert not E.run_nerf_raybased_helpers.hier_sample_supported(zc[:, :32], wc[:, :32], Ni, u)    # 32 coarse samples
+    z_all, z_std, smp, inds = E.run_nerf_raybased_helpers.hier_sample(zc, wc, Ni, u, want_samples=True, want_inds=True)
+    mids_c = (.5 * (zc[..., 1:] + zc[..., :-1])).contiguous()
+    s_ref, i_ref = E.sample_pdf(mids_c, wc[..., 1:-1], Ni, u=u, return_inds=True)
+    m_ref, std_ref = E.merge_sorted(zc, s_ref, want_std=True)
+    exact(smp, s_ref, "fused samples"), exact(inds, i_ref, "fused inds")
+    exact(z_all, m_ref, "fused merged depths"), exact(z_std, std_ref, "fused z_std")
+    exact(z_all, torch.sort(torch.cat([z, s_ref.cpu()], -1), -1)[0], "fused vs torch.sort")
+    e = E.run_nerf_raybased_helpers.hier_sample(zc[:0], wc[:0], Ni, u)
+    assert e[0].shape == (0, 64 + Ni) and e[1].shape == (0,)
+
+
 def test_merge_sorted(E):
     torch.manual_seed(0)
     for na, nbv in ((64, 128), (64, 64), (16, 7), (0, 33), (100, 300)):
