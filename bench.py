@@ -356,9 +356,10 @@ def main():
         launches = E._lib.launch_count - launches0
         kernels = E._lib.kernel_launches() - kernels0
         clocks = sampler.stop() if rank == 0 else None
-        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        dev_ms = sum(step_ms)
         if os.environ.get("BENCH_VERBOSE"):
-            print("per-step ms:", " ".join(f"{a.elapsed_time(b):.2f}" for a, b in ev[:40]), file=sys.stderr)
+            print("per-step ms:", " ".join(f"{x:.2f}" for x in step_ms[:40]), file=sys.stderr)
         mlp_ms = sum(a.elapsed_time(b) for a, b in mev) / steps if args.workload == "r2l" else None
 
         # ---------------- end-to-end timing through the public API with host buffers
@@ -400,7 +401,9 @@ def main():
 
     if rank == 0:
         line = {"metric": "render_throughput", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
-                "warmup": warmup, "warmup_extra_steps": extra_warm, "ms_per_step": dev_ms / steps, "higher_is_better": True,
+                "warmup": warmup, "warmup_extra_steps": extra_warm, "ms_per_step": dev_ms / steps,
+                "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_min": float(min(step_ms)),
+                "ms_per_step_max": float(max(step_ms)), "higher_is_better": True,
                 "scaling": "strong" if by_rays else "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": dict(wl.describe(),
