@@ -28,7 +28,9 @@
 //     the last epilogue instead of an extra K-stage: it needs no shared memory.
 //   * Tried and measured slower on the same box (160000 x 192 samples: 29.7-30.1 ms for this version): a 5-slot ring
 //     paid for by writing the point block over columns [0,64) of the tile's own activation buffer (skip layer with
-//     its point stage last): 30.3 ms; the same with a one-directional lag token for issuer T1: 30.6-30.7 ms.  In the
+//     its point stage last): 30.3 ms; the same with a one-directional lag token for issuer T1: 30.6-30.7 ms; with
+//     symmetric turn tokens (strict alternation): 32.4 ms — one issuer at a time issues a stage every ~590 cycles,
+//     slower than the pipe's 512, so two issuers working concurrently (and the tiles in near lockstep) win.  In the
 //     schedule the issuers settle into, the ring is not what limits a tile: its chain issue -> drain behind the other
 //     tile's queued MMAs -> epilogue (which waits for the other tile's epilogue: same 8 warps) -> wake-ups is.
 //   * No per-group chasing barriers: a tile-layer starts when the tile's previous epilogue has signalled a_done[t]
