@@ -28,6 +28,7 @@ communication; rank r takes groups r, r+G, ...  Random streams:
 import os
 import queue
 import threading
+import time
 
 import numpy as np
 import torch
@@ -200,11 +201,22 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
                 for _ in range(i_save):
                     poses.append(get_rand_pose(rng))
                     focals.append(focal * (rng.rand() + 1) if use_rand_focal else focal)
-                # drawn even for groups this rank skips: same global stream as the reference
-                ix1 = rng.permutation(n_rows)
-                ix2 = rng.permutation(n_rows)
+                # the group's poses are published BEFORE its two permutations are drawn (same stream order as the
+                # reference: poses, focals, then the permutations), so the GPU starts rendering the group while the
+                # host spends ~1 s on np.random.permutation(16M) x 2; the renderer picks the shuffle up when it is done
+                ix_box = {"ready": threading.Event()}
                 if mine:
-                    todo.put((g, first, poses, focals, torch.from_numpy(ix1[ix2])))   # data[ix1][ix2] == data[ix1[ix2]]
+                    todo.put((g, first, poses, focals, ix_box))
+                try:
+                    # drawn even for groups this rank skips: same global stream as the reference
+                    ix1 = rng.permutation(n_rows)
+                    ix2 = rng.permutation(n_rows)
+                    ix_box["ix"] = torch.from_numpy(ix1[ix2]) if mine else None   # data[ix1][ix2] == data[ix1[ix2]]
+                except Exception as e:
+                    ix_box["err"] = e
+                    raise
+                finally:
+                    ix_box["ready"].set()
             todo.put(None)
         except Exception as e:
             todo.put(e)
@@ -259,7 +271,8 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
                 break
             if isinstance(item, Exception):
                 raise item
-            g, first, poses, focals, ix = item
+            g, first, poses, focals, ix_box = item
+            _t0 = time.time()
             if stream == "per_group":
                 torch.manual_seed(seed + g)   # CPU-generator draws inside the renders (t_rand, u, noise)
             rows = []
@@ -287,8 +300,18 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
                     rows.append(torch.cat(parts, -1))
                 if progress is not None:
                     progress(g, k + 1)
+            _t1 = time.time()
+            ix_box["ready"].wait()
+            _t2 = time.time()
+            if "err" in ix_box:
+                raise ix_box["err"]
+            ix = ix_box["ix"]
             if gbuf is not None:
                 b = host_free.get()
+                if os.environ.get("R2L_CD_TIMING"):
+                    torch.cuda.synchronize()
+                    print(f"[create_data] group {g}: enqueue {_t1 - _t0:.2f} s, wait perm {_t2 - _t1:.2f} s, "
+                          f"wait host buffer {time.time() - _t2:.2f} s (incl. device sync)", flush=True)
                 if fin_err:
                     raise fin_err[0]
                 rendered = torch.cuda.Event()
