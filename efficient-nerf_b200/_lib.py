@@ -35,7 +35,8 @@ SIGNATURES = {
                         _c_f32p, _c_f32p, _c_f32p, _c_vp],
     "r2l_sample_pdf": [_c_ll, _c_int, _c_int, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_int, _c_f32p, _c_vp,
                        _c_vp],
-    "r2l_hier_sample": [_c_ll, _c_int, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_vp, _c_vp],
+    "r2l_hier_sample": [_c_ll, _c_int, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_vp,
+                        _c_vp],
     "r2l_merge_sorted": [_c_ll, _c_int, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_vp],
     "r2l_image_error": [_c_int, _c_ll, _c_f32p, _c_f32p, _c_f32p, _c_vp, _c_vp],
     "r2l_ssim": [_c_int, _c_int, _c_int, _c_f32p, _c_f32p, _c_ll, _c_vp, _c_vp, _c_vp],

@@ -261,13 +261,14 @@ sample_pdf_fast_kernel(long long n_rays, const float* __restrict__ bins, long lo
 // HBM; here a ray costs 512 B in and 4*(64+Ni) B out, and the merge is almost free: a sample drawn from bin
 // [mid_b, mid_{b+1}] has exactly the coarse depths z_0..z_b (and possibly z_{b+1}) below it, so its merged position
 // is k + b + 1 + (z_{b+1} <= s) (verified / corrected by a local scan, so any ascending z is handled exactly); the
-// coarse depths find theirs by a 7-step search over the (ascending) samples in shared memory.  Rays whose z or
-// samples are NOT ascending (never the case with a non-decreasing u and stratified z) take a bitonic sort instead.
+// coarse depths find theirs by a 7-step search over the (ascending) samples in shared memory.  With a stochastic
+// per-ray u (create_data) the samples come out unordered: they alone are bitonic-sorted in shared memory, then the
+// same rank merge runs with searches on both sides.  Rows whose z is not ascending take a full bitonic sort.
 // Same arithmetic, in the same order, as sample_pdf_fast_kernel and merge_sort_kernel: results are bit-identical.
 template <int NIT>
 __global__ void __launch_bounds__(kPdfWarps * 32)
 hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const float* __restrict__ weights,
-                   const float* __restrict__ u, float* __restrict__ z_out, float* __restrict__ z_std,
+                   const float* __restrict__ u, int u_per_ray, float* __restrict__ z_out, float* __restrict__ z_std,
                    float* __restrict__ samples_out, long long* __restrict__ inds_out) {
   constexpr int NS = 64, NB = 63, NW = 62, Ni = 32 * NIT, NO = NS + Ni, P2 = 32;
   constexpr int PSORT = (NO <= 128) ? 128 : 256;
@@ -282,8 +283,10 @@ hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const flo
   float* const s_z = s_z_all[wib];
   float* const s_o = s_o_all[wib];
   float ureg[NIT];
+  if (!u_per_ray) {
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) ureg[it] = __ldg(u + it * 32 + lane);
+    for (int it = 0; it < NIT; ++it) ureg[it] = __ldg(u + it * 32 + lane);
+  }
   if (lane == 0) s_cb[63] = make_float2(__int_as_float(0x7f800000), 0.f);
   const long long warp0 = static_cast<long long>(blockIdx.x) * kPdfWarps + wib;
   const long long nwarps = static_cast<long long>(gridDim.x) * kPdfWarps;
@@ -295,11 +298,16 @@ hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const flo
     s_z[lane + 32] = z1;
     s_w[lane] = __fadd_rn(__ldg(rw + lane), 1e-5f);
     if (lane + 32 < NW) s_w[lane + 32] = __fadd_rn(__ldg(rw + lane + 32), 1e-5f);
+    if (u_per_ray) {
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) ureg[it] = __ldg(u + ray * Ni + it * 32 + lane);
+    }
     __syncwarp();
     // bins_j = .5 * (z_{j+1} + z_j): one rounded add, an exact halving
     const float b0 = __fmul_rn(0.5f, __fadd_rn(s_z[lane + 1], z0));
     const float b1 = (lane + 32 < NB) ? __fmul_rn(0.5f, __fadd_rn(s_z[lane + 33], z1)) : 0.f;
-    bool asc = (z0 <= s_z[lane + 1]) && (lane + 33 > 63 || z1 <= s_z[lane + 33]);
+    const bool z_asc = __all_sync(0xffffffffu, (z0 <= s_z[lane + 1]) && (lane + 33 > 63 || z1 <= s_z[lane + 33]));
+    bool asc = true;   // samples ascending and free of NaNs
     const float total = aten_row_sum_ct<NW>(s_w, lane);
     const float2 wp = *reinterpret_cast<const float2*>(s_w + 2 * lane);
     const double p0 = (2 * lane < NW) ? static_cast<double>(__fdiv_rn(wp.x, total)) : 0.0;
@@ -354,7 +362,7 @@ hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const flo
     for (int it = 0; it < NIT; ++it) {
       const int k = it * 32 + lane;
       if (k + 1 < Ni) asc = asc && (sv[it] <= s_o[k + 1]);
-      asc = asc && (sv[it] == sv[it]);
+      asc = asc && (sv[it] == sv[it]);   // a NaN sample fails both this and the no_nan test: general path
     }
     if (z_std != nullptr) {
 #pragma unroll
@@ -381,10 +389,59 @@ hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const flo
       if (lane == 0) z_std[ray] = static_cast<float>(sqrt(ss / Ni));
     }
     float* const out = z_out + ray * NO;
-    if (__all_sync(0xffffffffu, asc)) {
+    const bool s_asc = __all_sync(0xffffffffu, asc);
+    bool s_nan = false;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) s_nan = s_nan || (sv[it] != sv[it]);
+    const bool no_nan = !__any_sync(0xffffffffu, s_nan);
+    if (z_asc && s_asc) {
       // stable rank merge, coarse depths first on ties: rank(z_i) = i + #{s < z_i}, rank(s_k) = k + #{z <= s_k}
 #pragma unroll
       for (int it = 0; it < NIT; ++it) out[it * 32 + lane + cle[it]] = sv[it];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        const float v = h ? z1 : z0;
+        int lo_ = 0, hi_ = Ni;   // first sample >= v
+        while (lo_ < hi_) {
+          const int mid = (lo_ + hi_) >> 1;
+          if (s_o[mid] < v) lo_ = mid + 1; else hi_ = mid;
+        }
+        out[i + lo_] = v;
+      }
+    } else if (z_asc && no_nan) {
+      // stochastic u (create_data, training-style renders): the samples come out unordered.  Sort the Ni samples
+      // alone (bitonic, Ni is a power of two), then the same rank merge with searches on both sides.
+      __syncwarp();
+      for (int k = 2; k <= Ni; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            const int i = it * 32 + lane;
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const float a = s_o[i], b = s_o[ixj];
+              const bool up = ((i & k) == 0);
+              if ((a > b) == up) {
+                s_o[i] = b;
+                s_o[ixj] = a;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int k = it * 32 + lane;
+        const float v = s_o[k];
+        int lo_ = 0, hi_ = NS;   // first coarse depth > v
+        while (lo_ < hi_) {
+          const int mid = (lo_ + hi_) >> 1;
+          if (s_z[mid] <= v) lo_ = mid + 1; else hi_ = mid;
+        }
+        out[k + lo_] = v;
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int i = lane + 32 * h;
@@ -563,7 +620,7 @@ int r2l_sample_pdf(long long n_rays, int nb, int Ni, const float* bins, long lon
 }
 
 int r2l_hier_sample(long long n_rays, int n_coarse, int Ni, const float* z_vals, const float* weights, const float* u,
-                    float* z_out, float* z_std, float* samples, long long* inds_out, void* stream) {
+                    int u_per_ray, float* z_out, float* z_std, float* samples, long long* inds_out, void* stream) {
   R2L_CHECK_ARG(n_rays >= 0, "r2l_hier_sample: bad sizes");
   R2L_CHECK_ARG(n_coarse == 64 && (Ni == 128 || Ni == 64),
                 "r2l_hier_sample: fused path needs 64 coarse samples and 64 or 128 fine samples (got %d, %d); use "
@@ -575,11 +632,11 @@ int r2l_hier_sample(long long n_rays, int n_coarse, int Ni, const float* z_vals,
   if (blocks > cap) blocks = cap;
   auto st = static_cast<cudaStream_t>(stream);
   if (Ni == 128)
-    hier_sample_kernel<4><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, z_out, z_std,
-                                                                              samples, inds_out);
+    hier_sample_kernel<4><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, u_per_ray,
+                                                                              z_out, z_std, samples, inds_out);
   else
-    hier_sample_kernel<2><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, z_out, z_std,
-                                                                              samples, inds_out);
+    hier_sample_kernel<2><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, u_per_ray,
+                                                                              z_out, z_std, samples, inds_out);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }

@@ -220,13 +220,15 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False, u=None, return
 
 
 def hier_sample_supported(z_vals, weights, N_importance, u):
-    """True when the fused kernel applies: 64 coarse samples, 64 / 128 fine samples, ONE non-decreasing host-side `u`
-    table shared by all rays (det=True: every rendering configuration)."""
-    return (isinstance(z_vals, torch.Tensor) and z_vals.is_cuda and z_vals.dim() == 2 and z_vals.shape[1] == 64
+    """True when the fused kernel applies: 64 coarse samples, 64 / 128 fine samples, `u` either ONE table [Ni] shared
+    by all rays (det=True: every rendering configuration) or per-ray variates [N, Ni] (stochastic renders)."""
+    if not (isinstance(z_vals, torch.Tensor) and z_vals.is_cuda and z_vals.dim() == 2 and z_vals.shape[1] == 64
             and z_vals.dtype == torch.float32 and weights.shape == z_vals.shape and weights.is_cuda
-            and weights.dtype == torch.float32 and N_importance in (64, 128)
-            and isinstance(u, torch.Tensor) and not u.is_cuda and u.dim() == 1 and u.shape[0] == N_importance
-            and bool((u[1:] >= u[:-1]).all()))
+            and weights.dtype == torch.float32 and N_importance in (64, 128) and isinstance(u, torch.Tensor)):
+        return False
+    if u.dim() == 1:
+        return u.shape[0] == N_importance
+    return u.dim() == 2 and tuple(u.shape) == (z_vals.shape[0], N_importance)
 
 
 def hier_sample(z_vals, weights, N_importance, u, want_samples=False, want_inds=False):
@@ -243,8 +245,9 @@ def hier_sample(z_vals, weights, N_importance, u, want_samples=False, want_inds=
     samples = torch.empty((N, N_importance), dtype=torch.float32, device=dev) if want_samples else None
     inds = torch.empty((N, N_importance), dtype=torch.int64, device=dev) if want_inds else None
     with torch.cuda.device(dev):
-        _lib.call("r2l_hier_sample", N, 64, int(N_importance), _lib.ptr(z), _lib.ptr(w), _lib.ptr(ud), _lib.ptr(out),
-                  _lib.ptr(z_std), _lib.ptr(samples), _lib.ptr(inds), _lib.stream_ptr(dev))
+        _lib.call("r2l_hier_sample", N, 64, int(N_importance), _lib.ptr(z), _lib.ptr(w), _lib.ptr(ud),
+                  int(ud.dim() == 2), _lib.ptr(out), _lib.ptr(z_std), _lib.ptr(samples), _lib.ptr(inds),
+                  _lib.stream_ptr(dev))
     return out, z_std, samples, inds
 
 

@@ -250,7 +250,6 @@ def test_hier_sample_fused_equals_unfused(E, Ni):
     u = torch.linspace(0., 1., Ni)
     zc, wc = z.cuda(), w.cuda()
     assert E.run_nerf_raybased_helpers.hier_sample_supported(zc, wc, Ni, u)
-    assert not E.run_nerf_raybased_helpers.hier_sample_supported(zc, wc, Ni, torch.rand(Ni))       # not sorted
     assert not E.run_nerf_raybased_helpers.hier_sample_supported(zc[:, :32], wc[:, :32], Ni, u)    # 32 coarse samples
     z_all, z_std, smp, inds = E.run_nerf_raybased_helpers.hier_sample(zc, wc, Ni, u, want_samples=True, want_inds=True)
     mids_c = (.5 * (zc[..., 1:] + zc[..., :-1])).contiguous()
@@ -259,6 +258,16 @@ def test_hier_sample_fused_equals_unfused(E, Ni):
     exact(smp, s_ref, "fused samples"), exact(inds, i_ref, "fused inds")
     exact(z_all, m_ref, "fused merged depths"), exact(z_std, std_ref, "fused z_std")
     exact(z_all, torch.sort(torch.cat([z, s_ref.cpu()], -1), -1)[0], "fused vs torch.sort")
+    # stochastic variates: per-ray [N, Ni] (create_data) and an unsorted shared table -> samples come out unordered,
+    # the kernel sorts them alone and rank-merges; rows 11 / 12 (z not ascending) take the full bitonic sort
+    for uu in (torch.rand(N, Ni), torch.rand(Ni)):
+        assert E.run_nerf_raybased_helpers.hier_sample_supported(zc, wc, Ni, uu)
+        z_all, z_std, smp, inds = E.run_nerf_raybased_helpers.hier_sample(zc, wc, Ni, uu, want_samples=True,
+                                                                          want_inds=True)
+        s_ref, i_ref = E.sample_pdf(mids_c, wc[..., 1:-1], Ni, u=uu, return_inds=True)
+        m_ref, std_ref = E.merge_sorted(zc, s_ref, want_std=True)
+        exact(smp, s_ref, "fused samples (stochastic u)"), exact(inds, i_ref, "fused inds (stochastic u)")
+        exact(z_all, m_ref, "fused merged depths (stochastic u)"), exact(z_std, std_ref, "fused z_std (stochastic u)")
     e = E.run_nerf_raybased_helpers.hier_sample(zc[:0], wc[:0], Ni, u)
     assert e[0].shape == (0, 64 + Ni) and e[1].shape == (0,)
 
