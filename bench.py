@@ -133,6 +133,7 @@ class R2LWorkload:
         self.P = int(poses_per_launch)
         self.rays_per_step = RAYS * self.P
         self.block = None
+        self.graph = None
         sd = O.r2l_state_dict(0)
         net = E.NeRF_v3_2(O.r2l_args(), 1008, 3, precision=precision)
         net.load_state_dict(sd)
@@ -142,8 +143,19 @@ class R2LWorkload:
         self.net.packed_handle()
         self.ev = None
 
+    def enable_graph(self):
+        """--graph: sampler + fused MLP captured once into a CUDA graph, one replay per step."""
+        self.graph = self.E.GraphedR2L(self.net, self.ps, self.P, rows=self.block)
+
     def step(self, c2w_dev, mlp_events=None):
         # c2w_dev: [P, 3, 4] — P consecutive test poses rendered by ONE sampler launch + ONE fused-MLP launch
+        if self.graph is not None:
+            if mlp_events is not None:      # no events inside a graph: the bracket is the whole replay
+                mlp_events[0].record()
+            out = self.graph(c2w_dev)
+            if mlp_events is not None:
+                mlp_events[1].record()
+            return out
         pts = self.ps.sample_test_batch(c2w_dev) if c2w_dev.dim() == 3 else self.ps.sample_test(c2w_dev)
         if self.block is not None:          # --shard rays: this rank's contiguous block of the frame's rays
             pts = pts[self.block[0]:self.block[1]]
@@ -160,7 +172,7 @@ class R2LWorkload:
                             f"{self.rays_per_step} rays (1250 tiles of 128 rays per frame leave a ragged 9th wave on "
                             "148 SMs; batching poses fills whole waves)",
                 "poses_per_launch": self.P, "rays_per_step": self.rays_per_step, "operands": self.net.precision,
-                "accumulate": "fp32"}
+                "accumulate": "fp32", "cuda_graph": self.graph is not None}
 
 
 class NerfWorkload:
@@ -274,6 +286,8 @@ def main():
                     help="poses (default): rank r renders poses r, r+G, ... (weak scaling, no data-path collective); "
                          "rays: every frame is split into contiguous ray blocks over the ranks and the tiles are "
                          "all-gathered with NCCL (strong scaling: ms per frame)")
+    ap.add_argument("--graph", action="store_true",
+                    help="R2L: replay the step (sampler + fused MLP) as one CUDA graph instead of launching it from Python")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
@@ -304,6 +318,10 @@ def main():
         if P != 1:
             raise SystemExit("--shard rays renders one frame per step")
         wl.block = E.sharding.shard_rays(RAYS, rank, world)
+    if args.graph:
+        if args.workload != "r2l":
+            raise SystemExit("--graph is implemented for the R2L workload")
+        wl.enable_graph()
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
     # pose-sharded: rank r renders poses r, r+G, ...; ray-sharded: every rank works on the SAME pose sequence
@@ -362,6 +380,8 @@ def main():
         t_wall = time.perf_counter() - t_wall0
         launches = E._lib.launch_count - launches0
         kernels = E._lib.kernel_launches() - kernels0
+        if getattr(wl, "graph", None) is not None:     # replays do not pass through the library's launch counter
+            kernels += wl.graph.kernels_per_replay * steps
         clocks = sampler.stop() if rank == 0 else None
         step_ms = [a.elapsed_time(b) for a, b in ev]
         dev_ms = sum(step_ms)

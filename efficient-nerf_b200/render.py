@@ -229,6 +229,51 @@ def render_r2l(model, point_sampler, c2w, positional_embedder=None):
     return model(positional_embedder(pts))
 
 
+class GraphedR2L:
+    """The R2L frame (PointSampler kernel + fused encode/MLP kernel) captured ONCE into a CUDA graph and replayed per
+    pose: one graph launch per frame (or per stack of `n_poses` frames) instead of two kernel launches plus the
+    Python glue around them — what matters when a frame is sharded over many GPUs and takes a few hundred
+    microseconds.  `g(c2w)` copies the pose(s) into the graph's static input and replays; the returned tensor is the
+    graph's static output [n_poses*H*W, 3] (overwritten by the next call)."""
+
+    def __init__(self, model, point_sampler, n_poses=1, positional_embedder=None, rows=None):
+        dev = point_sampler.z_vals.device
+        self.n_poses = int(n_poses)
+        self.rows = rows
+        self.c2w = torch.zeros((self.n_poses, 3, 4), dtype=torch.float32, device=dev)
+        self.c2w[:, 0, 0] = self.c2w[:, 1, 1] = self.c2w[:, 2, 2] = 1.
+        model.packed_handle() if getattr(model, "precision", "fp32") != "fp32" else None
+
+        def run():
+            if self.rows is None:
+                return render_r2l(model, point_sampler, self.c2w if self.n_poses > 1 else self.c2w[0],
+                                  positional_embedder)
+            pts = point_sampler.sample_test(self.c2w[0])[self.rows[0]:self.rows[1]]   # one rank's ray block
+            return model.forward_points(pts)
+
+        with torch.no_grad():
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):      # warm-up outside capture (lazy initialisation, allocator)
+                for _ in range(2):
+                    run()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            k0 = _lib.kernel_launches()
+            with torch.cuda.graph(self.graph):
+                self.out = run()
+            self.kernels_per_replay = _lib.kernel_launches() - k0   # library kernels recorded in the graph
+
+    def __call__(self, c2w):
+        c = c2w if isinstance(c2w, torch.Tensor) else torch.as_tensor(c2w)
+        c = c.reshape(-1, c.shape[-2], 4)[:, :3, :4]
+        if c.shape[0] != self.n_poses:
+            raise ValueError(f"this graph renders {self.n_poses} pose(s) per replay, got {c.shape[0]}")
+        self.c2w.copy_(c, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
                 model_name="nerf", point_sampler=None, positional_embedder=None, learn_depth=False):
     """The test loop around the hot path (main.py:189-400): render every pose, stack the frames, and — with ground

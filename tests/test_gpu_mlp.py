@@ -491,3 +491,24 @@ def test_r2l_pose_batch_equals_single_poses(E, O):
         f1 = torch.cat([E.render_r2l(net, ps, p) for p in poses], 0)
     assert fb.shape == (3 * Hh * Ww, 3) and torch.equal(fb, f1)
     assert ps.sample_test_batch(poses[:0]).shape == (0, 48)
+
+
+def test_r2l_cuda_graph_replay_equals_eager(E, O):
+    """GraphedR2L: the sampler + fused MLP captured into a CUDA graph; replays with new poses reproduce the eager
+    frames bit for bit (1 pose and a stack of 3 poses per replay)."""
+    sd = O.r2l_state_dict(0)
+    net = load_r2l(E, O, sd, "fp16")
+    Hh, Ww = 40, 56
+    ps = E.PointSampler(Hh, Ww, 70., 16, 2., 6.)
+    poses = [O.pose_spherical(th, -30., 4.)[:3, :4].cuda() for th in (-150., -20., 15., 99., 140., 171.)]
+    with torch.no_grad():
+        g1 = E.GraphedR2L(net, ps, 1)
+        for p in poses[:3]:
+            assert torch.equal(g1(p), E.render_r2l(net, ps, p))
+        g3 = E.GraphedR2L(net, ps, 3)
+        for k in (0, 3):
+            stack = torch.stack(poses[k:k + 3], 0)
+            assert torch.equal(g3(stack), E.render_r2l(net, ps, stack))
+        with pytest.raises(ValueError):
+            g3(poses[0])
+
