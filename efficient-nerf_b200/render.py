@@ -81,6 +81,20 @@ def _fused_ok(net, viewdirs):
             and net.supports_tensor_core_path())
 
 
+_LINSPACE_CACHE = {}
+
+
+def _host_linspace_on(dev, n):
+    """torch.linspace(0, 1, n) computed on the HOST like the reference does (its fp32 values differ from a device
+    linspace in the last bit) and uploaded once per (device, n)."""
+    key = (dev.type, dev.index, int(n))
+    t = _LINSPACE_CACHE.get(key)
+    if t is None:
+        t = torch.linspace(0., 1., steps=int(n)).to(dev)
+        _LINSPACE_CACHE[key] = t
+    return t
+
+
 def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
                 return_depth=False, t_rand=None, u=None, noise0=None, noise1=None, return_debug=False):
@@ -92,7 +106,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     viewdirs = rb[:, -3:] if rb.shape[-1] > 8 else None
     near, far = rb[:, 6:7], rb[:, 7:8]
 
-    t_vals = torch.linspace(0., 1., steps=N_samples).to(dev)  # host linspace, uploaded (main.py:676)
+    t_vals = _host_linspace_on(dev, N_samples)  # host linspace, uploaded once per (device, N) (main.py:676)
     if perturb > 0. and t_rand is None:
         if pytest:
             np.random.seed(0)
@@ -115,7 +129,10 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     if N_importance > 0:
         rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
         if u is None:
-            u, _ = _make_u([N_rays], N_importance, det=(perturb == 0.), pytest=pytest)
+            if perturb == 0. and not pytest:
+                u = _host_linspace_on(dev, N_importance)   # det=True table (helpers:292), cached on the device
+            else:
+                u, _ = _make_u([N_rays], N_importance, det=(perturb == 0.), pytest=pytest)
         if hier_sample_supported(z_vals, weights, N_importance, u):
             # every deterministic render: mids, inverse-CDF sampling, sorted merge and z_std in one kernel
             z_all, z_std, z_samples, inds = hier_sample(z_vals, weights, N_importance, u, want_samples=return_debug,
