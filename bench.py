@@ -120,25 +120,21 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ workloads
-def make_poses(O, n, offset=0, stride=1):
-    return [O.pose_spherical(-180. + 360. * ((offset + k * stride) % 200) / 200., -30., 4.)[:3, :4].contiguous()
-            for k in range(n)]
+def make_poses(E, n, offset=0, stride=1):
+    return [E.synthetic.test_pose(offset + k * stride) for k in range(n)]
 
 
 class R2LWorkload:
     name = "r2l"
     kernels_per_step = 2   # point_sample_kernel + r2l_mlp_kernel
 
-    def __init__(self, E, O, precision, poses_per_launch=1):
+    def __init__(self, E, precision, poses_per_launch=1):
         self.P = int(poses_per_launch)
         self.rays_per_step = RAYS * self.P
         self.block = None
         self.graph = None
-        sd = O.r2l_state_dict(0)
-        net = E.NeRF_v3_2(O.r2l_args(), 1008, 3, precision=precision)
-        net.load_state_dict(sd)
-        self.net = net.cuda().eval()
-        self.ps = E.PointSampler(H, W, O.LEGO["focal"], 16, 2., 6.)
+        self.net = E.synthetic.seeded_r2l(0, precision)
+        self.ps = E.PointSampler(H, W, E.synthetic.LEGO["focal"], 16, 2., 6.)
         self.E = E
         self.net.packed_handle()
         self.ev = None
@@ -179,16 +175,12 @@ class NerfWorkload:
     name = "nerf"
     kernels_per_step = 13
 
-    def __init__(self, E, O, precision, poses_per_launch=1):
+    def __init__(self, E, precision, poses_per_launch=1):
         self.P, self.rays_per_step = 1, RAYS
         self.block = None
-        sdc, sdf = O.nerf_state_dicts(0)
-        self.coarse = E.NeRF(8, 256, 63, 27, 5, [4], True, precision=precision)
-        self.fine = E.NeRF(8, 256, 63, 27, 5, [4], True, precision=precision)
-        self.coarse.load_state_dict(sdc), self.fine.load_state_dict(sdf)
-        self.coarse, self.fine = self.coarse.cuda().eval(), self.fine.cuda().eval()
+        self.coarse, self.fine = E.synthetic.seeded_nerf_pair(0, precision)
         self.coarse.packed_handle(), self.fine.packed_handle()
-        self.E, self.focal = E, O.LEGO["focal"]
+        self.E, self.focal = E, E.synthetic.LEGO["focal"]
         self.kw = dict(network_query_fn=None, perturb=0., N_importance=128, network_fine=self.fine, N_samples=64,
                        network_fn=self.coarse, use_viewdirs=True, white_bkgd=True, raw_noise_std=0., ndc=False,
                        near=2., far=6.)
@@ -212,9 +204,11 @@ class NerfWorkload:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference(O, workload, steps, warmup, sample_rays):
+def cpu_reference(workload, steps, warmup, sample_rays):
     """The reference's algorithm (oracle port, torch CPU kernels = what the reference runs on CPU) on a bounded
-    sample of the same frame, all host threads."""
+    sample of the same frame, all host threads.  The ONLY place bench.py imports oracle/ (the checker is timed as the
+    CPU baseline; the GPU arm never touches it)."""
+    from oracle import ref_torch as O
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     cam = O.LEGO
@@ -247,11 +241,10 @@ def run_reference_arm(args):
     rank, local, world = dist_env()
     if rank != 0:
         return 0
-    from oracle import ref_torch as O
     sample = 8192 if args.workload == "r2l" else 512
     steps = max(1, min(args.steps, 3))
     warmup = min(args.warmup, 1)
-    cb, mean = cpu_reference(O, args.workload, steps, warmup, sample)
+    cb, mean = cpu_reference(args.workload, steps, warmup, sample)
     line = {"impl": "reference", "metric": "render_throughput", "value": cb["value"], "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -309,11 +302,10 @@ def main():
         torch.cuda.synchronize()
 
     import efficient_nerf_b200 as E
-    from oracle import ref_torch as O   # synthetic poses / seeded weights (and the cpu_baseline leg)
     E._lib.load()
     by_rays = args.shard == "rays"
     P = (args.poses_per_launch or (1 if by_rays else 4)) if args.workload == "r2l" else 1
-    wl = (R2LWorkload if args.workload == "r2l" else NerfWorkload)(E, O, args.precision, P)
+    wl = (R2LWorkload if args.workload == "r2l" else NerfWorkload)(E, args.precision, P)
     if by_rays:
         if P != 1:
             raise SystemExit("--shard rays renders one frame per step")
@@ -325,7 +317,7 @@ def main():
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
     # pose-sharded: rank r renders poses r, r+G, ...; ray-sharded: every rank works on the SAME pose sequence
-    flat = make_poses(O, (steps + warmup) * P, offset=0 if by_rays else rank, stride=1 if by_rays else world)
+    flat = make_poses(E, (steps + warmup) * P, offset=0 if by_rays else rank, stride=1 if by_rays else world)
     poses = [torch.stack(flat[i * P:(i + 1) * P], 0).contiguous() for i in range(steps + warmup)]   # [P, 3, 4] per step
     poses_dev = [p.cuda() for p in poses]
     RAYS_STEP = wl.rays_per_step
@@ -464,16 +456,16 @@ def main():
                                 "traffic_unit": "B/frame = coarse + fine launch (ncu, profiles/r1c)"}
         if world == 1 and not args.no_cpu_baseline:
             sample = 16384 if args.workload == "r2l" else 1024
-            line["cpu_baseline"], _ = cpu_reference(O, args.workload, 2, 1, sample)
+            line["cpu_baseline"], _ = cpu_reference(args.workload, 2, 1, sample)
         if world == 1 and not args.no_extras:
-            line["extras"] = extras(E, O, peaks, args.precision, args.workload)
+            line["extras"] = extras(E, peaks, args.precision, args.workload)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def extras(E, O, peaks, precision, main_workload):
+def extras(E, peaks, precision, main_workload):
     """Short secondary measurements reported beside the headline: the other model and the two HBM-bound kernels."""
     out = {}
     with torch.no_grad():
@@ -490,10 +482,10 @@ def extras(E, O, peaks, precision, main_workload):
             return a.elapsed_time(b) / n
 
         other = "nerf" if main_workload == "r2l" else "r2l"
-        wl = (R2LWorkload if other == "r2l" else NerfWorkload)(E, O, precision)
-        pose = make_poses(O, 1)[0].cuda()
+        wl = (R2LWorkload if other == "r2l" else NerfWorkload)(E, precision)
+        pose = make_poses(E, 1)[0].cuda()
         if main_workload == "r2l":   # the same R2L frame rendered one pose per launch (ragged last wave of tiles)
-            w1 = R2LWorkload(E, O, precision, 1)
+            w1 = R2LWorkload(E, precision, 1)
             ms1 = timeit(lambda: w1.step(pose), n=50)
             out["r2l_one_pose_per_launch"] = {"ms_per_frame_400x400": ms1, "Mrays_per_s": RAYS / ms1 / 1e3}
         ms = timeit(lambda: wl.step(pose), n=5 if other == "nerf" else 20)
@@ -502,19 +494,19 @@ def extras(E, O, peaks, precision, main_workload):
                       "tensor_TFLOPs": fl / ms / 1e9, "frac_of_sustained_peak": fl / ms / 1e9 / peaks["tf_sust"]}
         # the other BASELINE configs, one frame each (configs[3]: 800x800; configs[4]: LLFF fern 504x378, NDC, 64+64)
         if main_workload == "r2l":
-            cam8 = O.LEGO_800
-            r2l = R2LWorkload(E, O, precision, 1)
+            cam8 = E.synthetic.LEGO_800
+            r2l = R2LWorkload(E, precision, 1)
             ps8 = E.PointSampler(cam8["H"], cam8["W"], cam8["focal"], 16, 2., 6.)
             n8 = cam8["H"] * cam8["W"]
             ms = timeit(lambda: r2l.net.forward_points(ps8.sample_test(pose)), n=20)
             out["r2l_800x800"] = {"ms_per_frame": ms, "Mrays_per_s": n8 / ms / 1e3,
                                   "tensor_TFLOPs": FLOP_PER_RAY["r2l"] * n8 / ms / 1e9}
-            nw = wl if other == "nerf" else NerfWorkload(E, O, precision)
+            nw = wl if other == "nerf" else NerfWorkload(E, precision)
             kw8 = dict(nw.kw)
             ms = timeit(lambda: E.render_image(cam8["H"], cam8["W"], cam8["focal"], chunk=32768, c2w=pose, **kw8), n=3, warm=1)
             out["nerf_800x800"] = {"ms_per_frame": ms, "Mrays_per_s": n8 / ms / 1e3,
                                    "tensor_TFLOPs": FLOP_PER_RAY["nerf"] * n8 / ms / 1e9}
-            fern = O.FERN
+            fern = E.synthetic.FERN
             kwf = dict(nw.kw, N_importance=64, white_bkgd=False, ndc=True, near=0., far=1.)
             nf = fern["H"] * fern["W"]
             ms = timeit(lambda: E.render_image(fern["H"], fern["W"], fern["focal"], chunk=32768, c2w=pose, **kwf), n=3, warm=1)

@@ -17,6 +17,7 @@ from . import sharding
 from . import create_data
 from . import compat
 from . import metrics
+from . import synthetic
 from .run_nerf_raybased_helpers import (get_rays, ndc_rays, Embedder, get_embedder, raw2outputs, sample_pdf,
                                         normalize_dirs, merge_sorted)
 from .nerf_raybased import NeRF, ResMLP, NeRF_v3_2, PointSampler, PositionalEmbedder, LazyEmbedding, get_activation

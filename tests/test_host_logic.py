@@ -144,3 +144,27 @@ def test_mirror_exposes_the_reference_call_surface(E):
     assert list(sig.parameters)[:5] == ["bins", "weights", "N_samples", "det", "pytest"]
     for n in ("render", "render_rays", "batchify_rays", "batchify", "run_network", "render_path", "raw2outputs"):
         assert hasattr(E.render, n), f"render.{n} missing"
+
+
+def test_synthetic_workloads_equal_the_oracle_seeds(E, O):
+    """bench.py's GPU arm builds its models and poses from the package (never from oracle/); they must be the very
+    weights / poses the CPU reference arm renders (oracle/ref_torch.py seeded state dicts)."""
+    net = E.synthetic.seeded_r2l(0, "fp16", device="cpu")
+    sd = O.r2l_state_dict(0)
+    assert set(sd) == set(net.state_dict())
+    assert all(torch.equal(net.state_dict()[k], v) for k, v in sd.items())
+    coarse, fine = E.synthetic.seeded_nerf_pair(0, "fp16", device="cpu")
+    sdc, sdf = O.nerf_state_dicts(0)
+    assert all(torch.equal(coarse.state_dict()[k], v) for k, v in sdc.items())
+    assert all(torch.equal(fine.state_dict()[k], v) for k, v in sdf.items())
+    for k in (0, 3, 199, 200):
+        assert torch.equal(E.synthetic.test_pose(k), O.pose_spherical(-180. + 360. * (k % 200) / 200., -30., 4.)[:3, :4])
+    assert (E.synthetic.LEGO, E.synthetic.LEGO_800, E.synthetic.FERN) == (O.LEGO, O.LEGO_800, O.FERN)
+
+
+def test_bench_gpu_arm_does_not_import_the_oracle():
+    """Only the CPU legs of bench.py (cpu_baseline / --impl reference) may execute oracle/."""
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    assert src.count("from oracle") == 1
+    body = src.split("def cpu_reference", 1)[1].split("\ndef ", 1)[0]
+    assert "from oracle import ref_torch" in body
