@@ -18,6 +18,7 @@ from . import create_data
 from . import compat
 from . import metrics
 from . import synthetic
+from . import dropin
 from .run_nerf_raybased_helpers import (get_rays, ndc_rays, Embedder, get_embedder, raw2outputs, sample_pdf,
                                         normalize_dirs, merge_sorted)
 from .nerf_raybased import NeRF, ResMLP, NeRF_v3_2, PointSampler, PositionalEmbedder, LazyEmbedding, get_activation
