@@ -482,6 +482,279 @@ hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const flo
   }
 }
 
+// ---- the same fused step for an ASCENDING shared u table (det=True: linspace(0,1,Ni) — every render) ---------------
+// hier_sample_kernel<4> executes 975 warp instructions per ray and is issue-bound (ncu r1g: issue slots 76 % busy at
+// 13 % of the DRAM roofline): 4 x 6-step bisections, divergent local scans for the merge positions and two 7-step
+// searches of the coarse depths.  With u ascending none of the searches is needed:
+//   * inds_k = #{j : cdf_j <= u_k} = #{j : r_j <= k} with r_j = #{k : u_k < cdf_j}.  The lane that owns cdf_j gets r_j
+//     from ceil(cdf_j (Ni-1)) corrected against the real table (exact for ANY ascending table, O(1) for a linspace),
+//     the last j of every run of equal r marks s_i[r_j] = j+1, and an inclusive max-scan over k turns the marks into
+//     inds (cdf ascending => r ascending => one writer per address, no atomics).
+//   * a lane owns NIT CONSECUTIVE samples: neighbours compare in registers, samples / inds leave as 16-byte stores.
+//   * merged position of sample k = k + cle_k, cle_k = #{z <= s_k} = below+1+(z[below+1] <= s_k), verified with two
+//     more compares (any ascending z is still handled exactly: a failed check falls back to the scan);
+//   * merged position of z_i = i + #{s_k < z_i} = i + #{k : cle_k <= i}: the same mark + max-scan trick over cle.
+// Arithmetic and results are those of hier_sample_kernel (samples, inds and merged depths bit-identical; z_std sums the
+// same doubles in another order: equal to the last ulp of fp32 except when a rounding boundary is hit).  Rows with a
+// non-monotone or non-finite cdf (negative / NaN weights) take the bisection; rows whose z or samples are not
+// ascending take the bitonic sort.
+template <int NIT>
+__global__ void __launch_bounds__(kPdfWarps * 32)
+hier_sample_det_kernel(long long n_rays, const float* __restrict__ z_vals, const float* __restrict__ weights,
+                       const float* __restrict__ u, float* __restrict__ z_out, float* __restrict__ z_std,
+                       float* __restrict__ samples_out, long long* __restrict__ inds_out) {
+  constexpr int NS = 64, NB = 63, NW = 62, Ni = 32 * NIT, NO = NS + Ni, P2 = 32;
+  constexpr int PSORT = (NO <= 128) ? 128 : 256;
+  constexpr unsigned FULL = 0xffffffffu;
+  const float kInf = __int_as_float(0x7f800000);
+  __shared__ __align__(16) float s_up[Ni + 4];               // [0] = -inf, [k + 1] = u_k, [Ni + 1..] = +inf
+  __shared__ __align__(16) float s_w_all[kPdfWarps][64];
+  __shared__ __align__(16) float2 s_cb_all[kPdfWarps][64];   // (cdf_j, bins_j), j < 63; [63] = (+inf, 0)
+  __shared__ __align__(16) float s_z_all[kPdfWarps][68];     // [64..67] = +inf
+  __shared__ __align__(16) int s_i_all[kPdfWarps][Ni + 4];   // marks for inds (index r in [0, Ni])
+  __shared__ __align__(16) int s_c_all[kPdfWarps][68];       // marks for the coarse ranks (index cle in [0, 64])
+  __shared__ __align__(16) float s_o_all[kPdfWarps][PSORT];  // bitonic fallback only
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float* const s_w = s_w_all[wib];
+  float2* const s_cb = s_cb_all[wib];
+  float* const s_z = s_z_all[wib];
+  int* const s_i = s_i_all[wib];
+  int* const s_c = s_c_all[wib];
+  float* const s_o = s_o_all[wib];
+  for (int j = threadIdx.x; j < Ni; j += kPdfWarps * 32) s_up[j + 1] = __ldg(u + j);
+  if (threadIdx.x == 0) s_up[0] = -kInf;
+  if (threadIdx.x < 3) s_up[Ni + 1 + threadIdx.x] = kInf;
+  for (int j = lane; j < Ni + 4; j += 32) s_i[j] = 0;
+  for (int j = lane; j < 68; j += 32) s_c[j] = 0;
+  if (lane < 4) s_z[64 + lane] = kInf;
+  if (lane == 0) s_cb[63] = make_float2(kInf, 0.f);
+  __syncthreads();
+  float ureg[NIT];
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) ureg[i] = s_up[NIT * lane + i + 1];
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kPdfWarps + wib;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kPdfWarps;
+  for (long long ray = warp0; ray < n_rays; ray += nwarps) {
+    const float* rz = z_vals + ray * NS;
+    const float* rw = weights + ray * NS + 1;   // weights[..., 1:-1]
+    const float z0 = __ldg(rz + lane), z1 = __ldg(rz + lane + 32);
+    s_z[lane] = z0;
+    s_z[lane + 32] = z1;
+    s_w[lane] = __fadd_rn(__ldg(rw + lane), 1e-5f);
+    if (lane + 32 < NW) s_w[lane + 32] = __fadd_rn(__ldg(rw + lane + 32), 1e-5f);
+    __syncwarp();
+    const float zn0 = s_z[lane + 1], zn1 = s_z[lane + 33];   // [64] = +inf
+    const float b0 = __fmul_rn(0.5f, __fadd_rn(zn0, z0));
+    const float b1 = (lane + 32 < NB) ? __fmul_rn(0.5f, __fadd_rn(zn1, z1)) : 0.f;
+    const bool z_asc = __all_sync(FULL, (z0 <= zn0) && (lane == 31 || z1 <= zn1));
+    const float total = aten_row_sum_ct<NW>(s_w, lane);
+    const float2 wp = *reinterpret_cast<const float2*>(s_w + 2 * lane);
+    const double p0 = (2 * lane < NW) ? static_cast<double>(__fdiv_rn(wp.x, total)) : 0.0;
+    const double p1 = (2 * lane + 1 < NW) ? static_cast<double>(__fdiv_rn(wp.y, total)) : 0.0;
+    double p = p0 + p1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double q = shfl_up_f64_(p, o);
+      if (lane >= o) p += q;
+    }
+    double excl = shfl_up_f64_(p, 1);
+    if (lane == 0) excl = 0.0;
+    const float c1 = static_cast<float>(excl + p0);          // cdf[2 lane + 1]
+    const float c2 = static_cast<float>(excl + (p0 + p1));   // cdf[2 lane + 2]
+    const bool mono = __all_sync(FULL, (p0 >= 0.0) && (p1 >= 0.0) && (c2 < kInf));
+    __syncwarp();
+    s_cb[lane].y = b0;
+    if (lane + 32 < NB) s_cb[lane + 32].y = b1;
+    if (lane == 0) s_cb[0].x = 0.0f;
+    if (2 * lane < NW) s_cb[2 * lane + 1].x = c1;
+    if (2 * lane + 1 < NW) s_cb[2 * lane + 2].x = c2;
+    int pos[NIT];
+    if (mono) {
+      // r = #{k : u_k < c} for this lane's two cdf entries: guess from the linspace, one branch-free correction step,
+      // then verified (s_up[k + 1] = u_k, s_up[0] = -inf, s_up[Ni + 1..] = +inf: no bounds checks).  Lane 31 owns no
+      // entry: it runs the same code on its (valid) copies of the last cdf value and is overridden below.
+      int gA = min(max(static_cast<int>(ceilf(c1 * static_cast<float>(Ni - 1))), 0), Ni);
+      int gB = min(max(static_cast<int>(ceilf(c2 * static_cast<float>(Ni - 1))), 0), Ni);
+      gA += (s_up[gA + 1] < c1 ? 1 : 0) - (s_up[gA] >= c1 ? 1 : 0);
+      gB += (s_up[gB + 1] < c2 ? 1 : 0) - (s_up[gB] >= c2 ? 1 : 0);
+      const bool off = !(s_up[gA] < c1) || !(s_up[gA + 1] >= c1) || !(s_up[gB] < c2) || !(s_up[gB + 1] >= c2);
+      if (__any_sync(FULL, off)) {   // not a linspace (ties, clusters): walk
+        while (gA > 0 && s_up[gA] >= c1) --gA;
+        while (gA < Ni && s_up[gA + 1] < c1) ++gA;
+        while (gB > 0 && s_up[gB] >= c2) --gB;
+        while (gB < Ni && s_up[gB + 1] < c2) ++gB;
+        __syncwarp();
+      }
+      const int rA = (lane < 31) ? gA : Ni, rB = (lane < 31) ? gB : Ni;
+      const int rN = __shfl_down_sync(FULL, rA, 1);          // lane 30 sees lane 31's Ni: "last entry"
+      if (lane == 0 && rA != 0) s_i[0] = 1;                  // cdf_0 = 0: r_0 = 0
+      if (rA != rB) s_i[rA] = 2 * lane + 2;
+      if (lane < 31 && rB != rN) s_i[rB] = 2 * lane + 3;
+      __syncwarp();
+      int m[NIT];
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        m[i] = s_i[NIT * lane + i];
+        if (i > 0) m[i] = max(m[i], m[i - 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) s_i[NIT * lane + i] = 0;
+      if (lane == 0) s_i[Ni] = 0;
+      int incl = m[NIT - 1];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int q = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl = max(incl, q);
+      }
+      int ex = __shfl_up_sync(FULL, incl, 1);
+      if (lane == 0) ex = 0;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) pos[i] = max(m[i], ex);
+    } else {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        int q = 0;
+#pragma unroll
+        for (int st = P2; st > 0; st >>= 1) {
+          if (s_cb[q + st - 1].x <= ureg[i]) q += st;
+        }
+        pos[i] = q;
+      }
+    }
+    float sv[NIT];
+    int cle[NIT];      // #{coarse z <= sample}
+    double sum = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const float uk = ureg[i];
+      const int below = max(pos[i] - 1, 0);
+      const int above = min(pos[i], NB - 1);
+      const float2 lo = s_cb[below], hi = s_cb[above];
+      float denom = __fsub_rn(hi.x, lo.x);
+      if (denom < 1e-5f) denom = 1.0f;
+      // u_0 = cdf_0 = 0 and u_last = 1 = cdf_last make the numerator exactly 0 in most rays: a zero dividend sends
+      // the whole warp through the IEEE-divide slow path; +0 / denom = +0 for denom > 0 needs no divide
+      const float num = __fsub_rn(uk, lo.x);
+      const bool zero = (num == 0.0f) && (denom > 0.0f);
+      float t = __fdiv_rn(zero ? 1.0f : num, denom);
+      if (zero) t = num;
+      const float sm_ = __fadd_rn(lo.y, __fmul_rn(t, __fsub_rn(hi.y, lo.y)));
+      sv[i] = sm_;
+      sum += static_cast<double>(sm_);
+      const bool a = s_z[below] <= sm_, b = s_z[below + 1] <= sm_, d = s_z[below + 2] <= sm_;
+      cle[i] = below + 1 + (b ? 1 : 0);
+      bad = bad || !a || d;
+    }
+    if (__any_sync(FULL, bad)) {
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        int c = cle[i];
+        while (c < NS && s_z[c] <= sv[i]) ++c;
+        while (c > 0 && s_z[c - 1] > sv[i]) --c;
+        cle[i] = c;
+      }
+    }
+    if (samples_out != nullptr) {
+      float* so = samples_out + ray * Ni + NIT * lane;
+      if constexpr (NIT == 4) *reinterpret_cast<float4*>(so) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+      else *reinterpret_cast<float2*>(so) = make_float2(sv[0], sv[1]);
+    }
+    if (inds_out != nullptr) {
+      long long* io = inds_out + ray * Ni + NIT * lane;
+#pragma unroll
+      for (int i = 0; i < NIT; i += 2) *reinterpret_cast<longlong2*>(io + i) = make_longlong2(pos[i], pos[i + 1]);
+    }
+    // samples ascending and free of NaNs?
+    const float s_next = __shfl_down_sync(FULL, sv[0], 1);
+    bool asc = (lane == 31) || (sv[NIT - 1] <= s_next);
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      if (i + 1 < NIT) asc = asc && (sv[i] <= sv[i + 1]);
+      asc = asc && (sv[i] == sv[i]);
+    }
+    if (z_std != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int lo_ = __double2loint(sum), hi_ = __double2hiint(sum);
+        lo_ = __shfl_xor_sync(FULL, lo_, o);
+        hi_ = __shfl_xor_sync(FULL, hi_, o);
+        sum += __hiloint2double(hi_, lo_);
+      }
+      const double mean = sum / Ni;
+      double ss = 0.0;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const double dd = static_cast<double>(sv[i]) - mean;
+        ss += dd * dd;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int lo_ = __double2loint(ss), hi_ = __double2hiint(ss);
+        lo_ = __shfl_xor_sync(FULL, lo_, o);
+        hi_ = __shfl_xor_sync(FULL, hi_, o);
+        ss += __hiloint2double(hi_, lo_);
+      }
+      if (lane == 0) z_std[ray] = static_cast<float>(sqrt(ss / Ni));
+    }
+    float* const out = z_out + ray * NO;
+    if (z_asc && __all_sync(FULL, asc)) {
+      // stable rank merge, coarse depths first on ties: rank(s_k) = k + #{z <= s_k}, rank(z_i) = i + #{s < z_i}
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) out[NIT * lane + i + cle[i]] = sv[i];
+      const int c_next = __shfl_down_sync(FULL, cle[0], 1);
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int nxt = (i + 1 < NIT) ? cle[(i + 1) % NIT] : c_next;
+        if ((i == NIT - 1 && lane == 31) || cle[i] != nxt) s_c[cle[i]] = NIT * lane + i + 1;
+      }
+      __syncwarp();
+      const int2 mk = *reinterpret_cast<const int2*>(s_c + 2 * lane);
+      *reinterpret_cast<int2*>(s_c + 2 * lane) = make_int2(0, 0);
+      const int m1 = max(mk.x, mk.y);
+      int incl = m1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int q = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl = max(incl, q);
+      }
+      int ex = __shfl_up_sync(FULL, incl, 1);
+      if (lane == 0) ex = 0;
+      const float2 zz = *reinterpret_cast<const float2*>(s_z + 2 * lane);
+      out[2 * lane + max(ex, mk.x)] = zz.x;
+      out[2 * lane + 1 + max(ex, m1)] = zz.y;
+    } else {
+      // general path: bitonic sort of [samples, z, +inf padding] in shared memory (values only)
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) s_o[NIT * lane + i] = sv[i];
+      s_o[Ni + lane] = z0;
+      s_o[Ni + 32 + lane] = z1;
+      for (int j = NO + lane; j < PSORT; j += 32) s_o[j] = kInf;
+      __syncwarp();
+      for (int k = 2; k <= PSORT; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < PSORT; i += 32) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const float a = s_o[i], b = s_o[ixj];
+              const bool up = ((i & k) == 0);
+              if ((a > b) == up) {
+                s_o[i] = b;
+                s_o[ixj] = a;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      for (int j = lane; j < NO; j += 32) out[j] = s_o[j];
+    }
+    __syncwarp();
+  }
+}
+
 // z_out = sort(cat[z_a, z_b]) per ray (values only, ascending; main.py:730-732) and
 // z_std = std(z_b, unbiased=False) (main.py:750).  Warp-level bitonic sort in shared memory.
 __global__ void __launch_bounds__(kPdfWarps * 32)
@@ -627,10 +900,22 @@ int r2l_hier_sample(long long n_rays, int n_coarse, int Ni, const float* z_vals,
                 "r2l_sample_pdf + r2l_merge_sorted", n_coarse, Ni);
   if (n_rays == 0) return R2L_OK;
   R2L_CHECK_ARG(z_vals && weights && u && z_out, "r2l_hier_sample: null pointer");
+  R2L_CHECK_ARG(u_per_ray >= 0 && u_per_ray <= 2, "r2l_hier_sample: u_per_ray must be 0 (shared table), 1 (per ray) or "
+                "2 (shared ASCENDING table)");
   long long blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   auto st = static_cast<cudaStream_t>(stream);
+  if (u_per_ray == 2) {   // ONE ascending table shared by all rays (det=True): the search-free kernel
+    if (Ni == 128)
+      hier_sample_det_kernel<4><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, z_out,
+                                                                                    z_std, samples, inds_out);
+    else
+      hier_sample_det_kernel<2><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, z_out,
+                                                                                    z_std, samples, inds_out);
+    R2L_LAUNCH_CHECK();
+    return R2L_OK;
+  }
   if (Ni == 128)
     hier_sample_kernel<4><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, u_per_ray,
                                                                               z_out, z_std, samples, inds_out);

@@ -128,15 +128,17 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     debug = {}
     if N_importance > 0:
         rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
+        u_sorted = None
         if u is None:
             if perturb == 0. and not pytest:
                 u = _host_linspace_on(dev, N_importance)   # det=True table (helpers:292), cached on the device
+                u_sorted = True
             else:
                 u, _ = _make_u([N_rays], N_importance, det=(perturb == 0.), pytest=pytest)
         if hier_sample_supported(z_vals, weights, N_importance, u):
             # every deterministic render: mids, inverse-CDF sampling, sorted merge and z_std in one kernel
             z_all, z_std, z_samples, inds = hier_sample(z_vals, weights, N_importance, u, want_samples=return_debug,
-                                                        want_inds=return_debug)
+                                                        want_inds=return_debug, u_sorted=u_sorted)
             if return_debug:
                 debug.update(z_vals0=z_vals, weights0=weights, raw0=raw, inds=inds, z_samples=z_samples)
             z_vals = z_all

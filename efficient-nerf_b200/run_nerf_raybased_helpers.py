@@ -231,10 +231,13 @@ def hier_sample_supported(z_vals, weights, N_importance, u):
     return u.dim() == 2 and tuple(u.shape) == (z_vals.shape[0], N_importance)
 
 
-def hier_sample(z_vals, weights, N_importance, u, want_samples=False, want_inds=False):
+def hier_sample(z_vals, weights, N_importance, u, want_samples=False, want_inds=False, u_sorted=None):
     """Fused main.py:720-733,750: z_vals_mid -> sample_pdf(weights[..., 1:-1], u) -> sort(cat[z_vals, z_samples]) and
     std(z_samples), one launch.  Returns (z_all [N, 64+Ni], z_std [N], z_samples | None, inds | None); bit-identical to
-    sample_pdf + merge_sorted (tested)."""
+    sample_pdf + merge_sorted (tested).  `u_sorted`: a shared table [Ni] that is ascending (det=True's linspace) runs
+    the search-free kernel; None = look (host tables only — a device table is not read back, the caller says so)."""
+    if u.dim() == 1 and u_sorted is None:
+        u_sorted = (not u.is_cuda) and bool((u[1:] >= u[:-1]).all())
     z = z_vals.contiguous()
     w = weights.contiguous()
     dev = z.device
@@ -246,7 +249,8 @@ def hier_sample(z_vals, weights, N_importance, u, want_samples=False, want_inds=
     inds = torch.empty((N, N_importance), dtype=torch.int64, device=dev) if want_inds else None
     with torch.cuda.device(dev):
         _lib.call("r2l_hier_sample", N, 64, int(N_importance), _lib.ptr(z), _lib.ptr(w), _lib.ptr(ud),
-                  int(ud.dim() == 2), _lib.ptr(out), _lib.ptr(z_std), _lib.ptr(samples), _lib.ptr(inds),
+                  1 if ud.dim() == 2 else (2 if u_sorted else 0), _lib.ptr(out), _lib.ptr(z_std), _lib.ptr(samples),
+                  _lib.ptr(inds),
                   _lib.stream_ptr(dev))
     return out, z_std, samples, inds
 

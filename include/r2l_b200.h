@@ -97,8 +97,9 @@ int r2l_sample_pdf(long long n_rays, int nb, int Ni, const float* bins, long lon
 int r2l_merge_sorted(long long n_rays, int na, int nbv, const float* za, const float* zb, float* z_out,
                      float* z_std, void* stream);
 
-/* Fused hierarchical sampling for 64 coarse samples; u: shared table [Ni] (det=True) or [n,Ni] (u_per_ray=1);
- * Ni = 64 or 128:
+/* Fused hierarchical sampling for 64 coarse samples; u: shared table [Ni] (u_per_ray=0), per-ray variates [n,Ni]
+ * (u_per_ray=1), or a shared table the caller guarantees to be ASCENDING (u_per_ray=2: det=True's linspace, every
+ * render — the search-free kernel; same samples / inds / merged depths); Ni = 64 or 128:
  *   z_out [n, 64+Ni] = sort(cat[z_vals, sample_pdf(.5*(z[1:]+z[:-1]), weights[:,1:-1], Ni, u)]), z_std [n] (may be NULL)
  * = main.py:720-733 and :750 in one launch; optional samples [n,Ni] / inds int64 [n,Ni].  z_vals, weights: [n,64]
  * contiguous.  Bit-identical to r2l_sample_pdf followed by r2l_merge_sorted. */

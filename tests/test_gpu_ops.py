@@ -256,8 +256,32 @@ def test_hier_sample_fused_equals_unfused(E, Ni):
     s_ref, i_ref = E.sample_pdf(mids_c, wc[..., 1:-1], Ni, u=u, return_inds=True)
     m_ref, std_ref = E.merge_sorted(zc, s_ref, want_std=True)
     exact(smp, s_ref, "fused samples"), exact(inds, i_ref, "fused inds")
-    exact(z_all, m_ref, "fused merged depths"), exact(z_std, std_ref, "fused z_std")
+    exact(z_all, m_ref, "fused merged depths"), close(z_std, std_ref, 5e-7, "fused z_std")   # other summation order
     exact(z_all, torch.sort(torch.cat([z, s_ref.cpu()], -1), -1)[0], "fused vs torch.sort")
+    # the same table without the "ascending" promise runs the bisection kernel: identical results
+    g_all, g_std, g_smp, g_inds = E.run_nerf_raybased_helpers.hier_sample(zc, wc, Ni, u.cuda(), want_samples=True,
+                                                                          want_inds=True, u_sorted=False)
+    exact(g_smp, smp, "search-free vs bisection samples"), exact(g_inds, inds, "search-free vs bisection inds")
+    exact(g_all, z_all, "search-free vs bisection merged depths"), close(g_std, z_std, 5e-7, "search-free vs bisection z_std")
+    # ascending tables that are NOT a linspace (ties, clustered, constant), and weights that break the cdf
+    # (negative -> non-monotone, NaN, inf): the search-free kernel must still equal the separate kernels
+    w2 = wc.clone()
+    w2[20, 30] = -0.5
+    w2[21, 5] = float("nan")
+    w2[22, 40] = float("inf")
+    w2[23] = -1e-5                      # every w + 1e-5 == 0: total 0, pdf NaN
+    tables = [torch.sort(torch.rand(Ni))[0], torch.sort(torch.round(torch.rand(Ni) * 8) / 8)[0], torch.zeros(Ni),
+              torch.ones(Ni), torch.sort(torch.rand(Ni) ** 6)[0], u]
+    for k, ut in enumerate(tables):
+        ww = w2 if k == len(tables) - 1 else wc
+        a_all, a_std, a_smp, a_inds = E.run_nerf_raybased_helpers.hier_sample(zc, ww, Ni, ut, want_samples=True,
+                                                                              want_inds=True)
+        s_ref, i_ref = E.sample_pdf(mids_c, ww[..., 1:-1], Ni, u=ut, return_inds=True)
+        m_ref, std_ref = E.merge_sorted(zc, s_ref, want_std=True)
+        exact(a_smp, s_ref, f"table {k} samples"), exact(a_inds, i_ref, f"table {k} inds")
+        ok = torch.isfinite(s_ref).all(-1)          # rows with NaN samples: sort order of NaNs is unspecified
+        exact(a_all[ok], m_ref[ok], f"table {k} merged depths")
+        close(a_std[ok], std_ref[ok], 1e-6, f"table {k} z_std")
     # stochastic variates: per-ray [N, Ni] (create_data) and an unsorted shared table -> samples come out unordered,
     # the kernel sorts them alone and rank-merges; rows 11 / 12 (z not ascending) take the full bitonic sort
     for uu in (torch.rand(N, Ni), torch.rand(Ni)):
