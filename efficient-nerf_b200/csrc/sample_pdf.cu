@@ -38,6 +38,15 @@ __device__ __forceinline__ double shfl_idx_f64_(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
+// Correctly rounded num / denom that keeps a ZERO dividend off the IEEE-divide slow path (one lane with num == 0
+// otherwise drags the whole warp through ~50 extra instructions): det=True has u_0 = cdf_0 = 0 in every ray and
+// u_last = 1 = cdf_last in most.  +-0 / denom = +-0 exactly for a finite denom > 0; everything else divides normally.
+__device__ __forceinline__ float div_zero_fast(float num, float denom) {
+  const bool zero = (num == 0.0f) && (denom > 0.0f) && (denom < __int_as_float(0x7f800000));
+  const float t = __fdiv_rn(zero ? 1.0f : num, denom);
+  return zero ? num : t;
+}
+
 // Sum of w[0..n) in ATen-CPU order.  Executed by the whole warp; result valid on every lane.
 __device__ __forceinline__ float aten_row_sum(const float* w, int n, int lane) {
   float total = 0.0f;
@@ -246,7 +255,7 @@ sample_pdf_fast_kernel(long long n_rays, const float* __restrict__ bins, long lo
       const float2 lo = s_cb[below], hi = s_cb[above];
       float denom = __fsub_rn(hi.x, lo.x);
       if (denom < 1e-5f) denom = 1.0f;
-      const float t = __fdiv_rn(__fsub_rn(uk, lo.x), denom);
+      const float t = div_zero_fast(__fsub_rn(uk, lo.x), denom);
       samples[ray * Ni + it * 32 + lane] = __fadd_rn(lo.y, __fmul_rn(t, __fsub_rn(hi.y, lo.y)));
       if (inds_out != nullptr) inds_out[ray * Ni + it * 32 + lane] = pos;
     }
@@ -343,7 +352,7 @@ hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const flo
       const float2 lo = s_cb[below], hi = s_cb[above];
       float denom = __fsub_rn(hi.x, lo.x);
       if (denom < 1e-5f) denom = 1.0f;
-      const float t = __fdiv_rn(__fsub_rn(uk, lo.x), denom);
+      const float t = div_zero_fast(__fsub_rn(uk, lo.x), denom);
       const float sm_ = __fadd_rn(lo.y, __fmul_rn(t, __fsub_rn(hi.y, lo.y)));
       sv[it] = sm_;
       sum += static_cast<double>(sm_);
@@ -482,6 +491,152 @@ hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const flo
   }
 }
 
+// ---- sample_pdf for an ASCENDING shared u table (det=True), 63 bins: the search-free scheme of
+// hier_sample_det_kernel below (see its header) without the merge: inds from marks + a max-scan, NIT consecutive
+// samples per lane, 16-byte stores.  Same arithmetic as sample_pdf_fast_kernel: samples and inds are bit-identical.
+template <int NIT>
+__global__ void __launch_bounds__(kPdfWarps * 32)
+sample_pdf_det_kernel(long long n_rays, const float* __restrict__ bins, long long bins_stride,
+                      const float* __restrict__ weights, long long w_stride, const float* __restrict__ u,
+                      float* __restrict__ samples, long long* __restrict__ inds_out) {
+  constexpr int NB = 63, NW = 62, Ni = 32 * NIT, P2 = 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  const float kInf = __int_as_float(0x7f800000);
+  __shared__ __align__(16) float s_up[Ni + 4];               // [0] = -inf, [k + 1] = u_k, [Ni + 1..] = +inf
+  __shared__ __align__(16) float s_w_all[kPdfWarps][64];
+  __shared__ __align__(16) float2 s_cb_all[kPdfWarps][64];   // (cdf_j, bins_j), j < 63; [63] = (+inf, 0)
+  __shared__ __align__(16) int s_i_all[kPdfWarps][Ni + 4];   // marks for inds (index r in [0, Ni])
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float* const s_w = s_w_all[wib];
+  float2* const s_cb = s_cb_all[wib];
+  int* const s_i = s_i_all[wib];
+  for (int j = threadIdx.x; j < Ni; j += kPdfWarps * 32) s_up[j + 1] = __ldg(u + j);
+  if (threadIdx.x == 0) s_up[0] = -kInf;
+  if (threadIdx.x < 3) s_up[Ni + 1 + threadIdx.x] = kInf;
+  for (int j = lane; j < Ni + 4; j += 32) s_i[j] = 0;
+  if (lane == 0) s_cb[63] = make_float2(kInf, 0.f);
+  __syncthreads();
+  float ureg[NIT];
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) ureg[i] = s_up[NIT * lane + i + 1];
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kPdfWarps + wib;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kPdfWarps;
+  // the next ray's row is fetched while this one is processed (one ray per warp in flight otherwise)
+  float nb0 = 0.f, nb1 = 0.f, nw0 = 0.f, nw1 = 0.f;
+  if (warp0 < n_rays) {
+    nb0 = __ldg(bins + warp0 * bins_stride + lane);
+    if (lane + 32 < NB) nb1 = __ldg(bins + warp0 * bins_stride + lane + 32);
+    nw0 = __ldg(weights + warp0 * w_stride + lane);
+    if (lane + 32 < NW) nw1 = __ldg(weights + warp0 * w_stride + lane + 32);
+  }
+  for (long long ray = warp0; ray < n_rays; ray += nwarps) {
+    const float b0 = nb0, b1 = nb1;
+    s_w[lane] = __fadd_rn(nw0, 1e-5f);
+    if (lane + 32 < NW) s_w[lane + 32] = __fadd_rn(nw1, 1e-5f);
+    if (ray + nwarps < n_rays) {
+      const float* rb = bins + (ray + nwarps) * bins_stride;
+      const float* rw = weights + (ray + nwarps) * w_stride;
+      nb0 = __ldg(rb + lane);
+      if (lane + 32 < NB) nb1 = __ldg(rb + lane + 32);
+      nw0 = __ldg(rw + lane);
+      if (lane + 32 < NW) nw1 = __ldg(rw + lane + 32);
+    }
+    __syncwarp();
+    const float total = aten_row_sum_ct<NW>(s_w, lane);
+    const float2 wp = *reinterpret_cast<const float2*>(s_w + 2 * lane);
+    const double p0 = (2 * lane < NW) ? static_cast<double>(__fdiv_rn(wp.x, total)) : 0.0;
+    const double p1 = (2 * lane + 1 < NW) ? static_cast<double>(__fdiv_rn(wp.y, total)) : 0.0;
+    double p = p0 + p1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double q = shfl_up_f64_(p, o);
+      if (lane >= o) p += q;
+    }
+    double excl = shfl_up_f64_(p, 1);
+    if (lane == 0) excl = 0.0;
+    const float c1 = static_cast<float>(excl + p0);          // cdf[2 lane + 1]
+    const float c2 = static_cast<float>(excl + (p0 + p1));   // cdf[2 lane + 2]
+    const bool mono = __all_sync(FULL, (p0 >= 0.0) && (p1 >= 0.0) && (c2 < kInf));
+    __syncwarp();
+    s_cb[lane].y = b0;
+    if (lane + 32 < NB) s_cb[lane + 32].y = b1;
+    if (lane == 0) s_cb[0].x = 0.0f;
+    if (2 * lane < NW) s_cb[2 * lane + 1].x = c1;
+    if (2 * lane + 1 < NW) s_cb[2 * lane + 2].x = c2;
+    int pos[NIT];
+    if (mono) {
+      int gA = min(max(static_cast<int>(ceilf(c1 * static_cast<float>(Ni - 1))), 0), Ni);
+      int gB = min(max(static_cast<int>(ceilf(c2 * static_cast<float>(Ni - 1))), 0), Ni);
+      gA += (s_up[gA + 1] < c1 ? 1 : 0) - (s_up[gA] >= c1 ? 1 : 0);
+      gB += (s_up[gB + 1] < c2 ? 1 : 0) - (s_up[gB] >= c2 ? 1 : 0);
+      const bool off = !(s_up[gA] < c1) || !(s_up[gA + 1] >= c1) || !(s_up[gB] < c2) || !(s_up[gB + 1] >= c2);
+      if (__any_sync(FULL, off)) {   // not a linspace (ties, clusters): walk
+        while (gA > 0 && s_up[gA] >= c1) --gA;
+        while (gA < Ni && s_up[gA + 1] < c1) ++gA;
+        while (gB > 0 && s_up[gB] >= c2) --gB;
+        while (gB < Ni && s_up[gB + 1] < c2) ++gB;
+        __syncwarp();
+      }
+      const int rA = (lane < 31) ? gA : Ni, rB = (lane < 31) ? gB : Ni;
+      const int rN = __shfl_down_sync(FULL, rA, 1);          // lane 30 sees lane 31's Ni: "last entry"
+      if (lane == 0 && rA != 0) s_i[0] = 1;                  // cdf_0 = 0: r_0 = 0
+      if (rA != rB) s_i[rA] = 2 * lane + 2;
+      if (lane < 31 && rB != rN) s_i[rB] = 2 * lane + 3;
+      __syncwarp();
+      int m[NIT];
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        m[i] = s_i[NIT * lane + i];
+        if (i > 0) m[i] = max(m[i], m[i - 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) s_i[NIT * lane + i] = 0;
+      int incl = m[NIT - 1];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int q = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl = max(incl, q);
+      }
+      int ex = __shfl_up_sync(FULL, incl, 1);
+      if (lane == 0) ex = 0;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) pos[i] = max(m[i], ex);
+    } else {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        int q = 0;
+#pragma unroll
+        for (int st = P2; st > 0; st >>= 1) {
+          if (s_cb[q + st - 1].x <= ureg[i]) q += st;
+        }
+        pos[i] = q;
+      }
+    }
+    float sv[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int below = max(pos[i] - 1, 0);
+      const int above = min(pos[i], NB - 1);
+      const float2 lo = s_cb[below], hi = s_cb[above];
+      float denom = __fsub_rn(hi.x, lo.x);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = div_zero_fast(__fsub_rn(ureg[i], lo.x), denom);
+      sv[i] = __fadd_rn(lo.y, __fmul_rn(t, __fsub_rn(hi.y, lo.y)));
+    }
+    float* so = samples + ray * Ni + NIT * lane;
+    if constexpr (NIT == 4) *reinterpret_cast<float4*>(so) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+    else *reinterpret_cast<float2*>(so) = make_float2(sv[0], sv[1]);
+    if (inds_out != nullptr) {
+      long long* io = inds_out + ray * Ni + NIT * lane;
+#pragma unroll
+      for (int i = 0; i < NIT; i += 2) *reinterpret_cast<longlong2*>(io + i) = make_longlong2(pos[i], pos[i + 1]);
+    }
+    __syncwarp();
+  }
+}
+
 // ---- the same fused step for an ASCENDING shared u table (det=True: linspace(0,1,Ni) — every render) ---------------
 // hier_sample_kernel<4> executes 975 warp instructions per ray and is issue-bound (ncu r1g: issue slots 76 % busy at
 // 13 % of the DRAM roofline): 4 x 6-step bisections, divergent local scans for the merge positions and two 7-step
@@ -499,7 +654,7 @@ hier_sample_kernel(long long n_rays, const float* __restrict__ z_vals, const flo
 // non-monotone or non-finite cdf (negative / NaN weights) take the bisection; rows whose z or samples are not
 // ascending take the bitonic sort.
 template <int NIT>
-__global__ void __launch_bounds__(kPdfWarps * 32)
+__global__ void __launch_bounds__(kPdfWarps * 32, 5)
 hier_sample_det_kernel(long long n_rays, const float* __restrict__ z_vals, const float* __restrict__ weights,
                        const float* __restrict__ u, float* __restrict__ z_out, float* __restrict__ z_std,
                        float* __restrict__ samples_out, long long* __restrict__ inds_out) {
@@ -535,14 +690,25 @@ hier_sample_det_kernel(long long n_rays, const float* __restrict__ z_vals, const
   for (int i = 0; i < NIT; ++i) ureg[i] = s_up[NIT * lane + i + 1];
   const long long warp0 = static_cast<long long>(blockIdx.x) * kPdfWarps + wib;
   const long long nwarps = static_cast<long long>(gridDim.x) * kPdfWarps;
+  // the next ray's row is fetched while this one is processed (one ray per warp in flight otherwise)
+  float nz0 = 0.f, nz1 = 0.f, nw0 = 0.f, nw1 = 0.f;
+  if (warp0 < n_rays) {
+    nz0 = __ldg(z_vals + warp0 * NS + lane), nz1 = __ldg(z_vals + warp0 * NS + lane + 32);
+    nw0 = __ldg(weights + warp0 * NS + 1 + lane);
+    if (lane + 32 < NW) nw1 = __ldg(weights + warp0 * NS + 33 + lane);
+  }
   for (long long ray = warp0; ray < n_rays; ray += nwarps) {
-    const float* rz = z_vals + ray * NS;
-    const float* rw = weights + ray * NS + 1;   // weights[..., 1:-1]
-    const float z0 = __ldg(rz + lane), z1 = __ldg(rz + lane + 32);
+    const float z0 = nz0, z1 = nz1;
     s_z[lane] = z0;
     s_z[lane + 32] = z1;
-    s_w[lane] = __fadd_rn(__ldg(rw + lane), 1e-5f);
-    if (lane + 32 < NW) s_w[lane + 32] = __fadd_rn(__ldg(rw + lane + 32), 1e-5f);
+    s_w[lane] = __fadd_rn(nw0, 1e-5f);
+    if (lane + 32 < NW) s_w[lane + 32] = __fadd_rn(nw1, 1e-5f);
+    if (ray + nwarps < n_rays) {
+      const float* rz = z_vals + (ray + nwarps) * NS;
+      nz0 = __ldg(rz + lane), nz1 = __ldg(rz + lane + 32);
+      nw0 = __ldg(weights + (ray + nwarps) * NS + 1 + lane);   // weights[..., 1:-1]
+      if (lane + 32 < NW) nw1 = __ldg(weights + (ray + nwarps) * NS + 33 + lane);
+    }
     __syncwarp();
     const float zn0 = s_z[lane + 1], zn1 = s_z[lane + 33];   // [64] = +inf
     const float b0 = __fmul_rn(0.5f, __fadd_rn(zn0, z0));
@@ -635,12 +801,7 @@ hier_sample_det_kernel(long long n_rays, const float* __restrict__ z_vals, const
       const float2 lo = s_cb[below], hi = s_cb[above];
       float denom = __fsub_rn(hi.x, lo.x);
       if (denom < 1e-5f) denom = 1.0f;
-      // u_0 = cdf_0 = 0 and u_last = 1 = cdf_last make the numerator exactly 0 in most rays: a zero dividend sends
-      // the whole warp through the IEEE-divide slow path; +0 / denom = +0 for denom > 0 needs no divide
-      const float num = __fsub_rn(uk, lo.x);
-      const bool zero = (num == 0.0f) && (denom > 0.0f);
-      float t = __fdiv_rn(zero ? 1.0f : num, denom);
-      if (zero) t = num;
+      const float t = div_zero_fast(__fsub_rn(uk, lo.x), denom);
       const float sm_ = __fadd_rn(lo.y, __fmul_rn(t, __fsub_rn(hi.y, lo.y)));
       sv[i] = sm_;
       sum += static_cast<double>(sm_);
@@ -873,6 +1034,21 @@ int r2l_sample_pdf(long long n_rays, int nb, int Ni, const float* bins, long lon
   long long blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
+  R2L_CHECK_ARG(u_per_ray >= 0 && u_per_ray <= 2, "r2l_sample_pdf: u_per_ray must be 0 (shared table), 1 (per ray) or 2 "
+                "(shared ASCENDING table)");
+  if (nb == 63 && (Ni == 128 || Ni == 64) && u_per_ray == 2 && (reinterpret_cast<uintptr_t>(samples) & 15) == 0 &&
+      (inds_out == nullptr || (reinterpret_cast<uintptr_t>(inds_out) & 15) == 0)) {   // det=True: search-free kernel
+    auto st = static_cast<cudaStream_t>(stream);
+    if (Ni == 128)
+      sample_pdf_det_kernel<4><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, bins, bins_stride, weights,
+                                                                                   w_stride, u, samples, inds_out);
+    else
+      sample_pdf_det_kernel<2><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, bins, bins_stride, weights,
+                                                                                   w_stride, u, samples, inds_out);
+    R2L_LAUNCH_CHECK();
+    return R2L_OK;
+  }
+  if (u_per_ray == 2) u_per_ray = 0;   // other sizes: an ascending table is just a shared table
   if (nb == 63 && (Ni == 128 || Ni == 64)) {   // 64 coarse samples: every BASELINE config
     auto st = static_cast<cudaStream_t>(stream);
     if (Ni == 128)
@@ -906,6 +1082,8 @@ int r2l_hier_sample(long long n_rays, int n_coarse, int Ni, const float* z_vals,
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   auto st = static_cast<cudaStream_t>(stream);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(samples) | reinterpret_cast<uintptr_t>(inds_out)) & 15) == 0;
+  if (u_per_ray == 2 && !aligned) u_per_ray = 0;   // the search-free kernel stores 16 bytes per lane
   if (u_per_ray == 2) {   // ONE ascending table shared by all rays (det=True): the search-free kernel
     if (Ni == 128)
       hier_sample_det_kernel<4><<<static_cast<int>(blocks), kPdfWarps * 32, 0, st>>>(n_rays, z_vals, weights, u, z_out,

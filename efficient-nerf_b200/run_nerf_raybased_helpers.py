@@ -183,11 +183,13 @@ def _make_u(shape_prefix, N_samples, det, pytest):
     return u, per_ray
 
 
-def sample_pdf(bins, weights, N_samples, det=False, pytest=False, u=None, return_inds=False):
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False, u=None, return_inds=False, u_sorted=None):
     """Inverse-CDF sampling of the coarse weights (helpers:283-330).
 
     bins [N, nb], weights [N, nb-1] -> samples [N, N_samples]; searchsorted indices are bit-exact with
-    the reference's CPU path.  `u` may be injected ([N_samples] or [N, N_samples]).
+    the reference's CPU path.  `u` may be injected ([N_samples] or [N, N_samples]).  A shared table that is ascending
+    (det=True's linspace; `u_sorted`: None = look at host tables, a device table is taken at the caller's word) runs
+    the search-free kernel — same samples and indices.
     """
     on_host = isinstance(bins, torch.Tensor) and not bins.is_cuda
     dev = bins.device if isinstance(bins, torch.Tensor) and bins.is_cuda else _dev()
@@ -203,8 +205,12 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False, u=None, return
     N, nb = b.shape
     if u is None:
         u, per_ray = _make_u([N], N_samples, det, pytest)
+        if det and not pytest and u_sorted is None:
+            u_sorted = True
     else:
         per_ray = (u.dim() == 2)
+    if not per_ray and u_sorted is None:
+        u_sorted = isinstance(u, torch.Tensor) and (not u.is_cuda) and bool((u[1:] >= u[:-1]).all())
     u = _lib.as_f32_cuda(u, dev, "u")
     if per_ray and tuple(u.shape) != (N, N_samples):
         raise ValueError("per-ray u must be [N, N_samples]")
@@ -212,7 +218,8 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False, u=None, return
     inds = torch.empty((N, N_samples), dtype=torch.int64, device=dev) if return_inds else None
     with torch.cuda.device(dev):
         _lib.call("r2l_sample_pdf", N, nb, int(N_samples), _lib.ptr(b), b.stride(0), _lib.ptr(w), w.stride(0),
-                  _lib.ptr(u), int(per_ray), _lib.ptr(samples), _lib.ptr(inds), _lib.stream_ptr(dev))
+                  _lib.ptr(u), 1 if per_ray else (2 if u_sorted else 0), _lib.ptr(samples), _lib.ptr(inds),
+                  _lib.stream_ptr(dev))
     if on_host:
         samples = samples.cpu()
         inds = inds.cpu() if inds is not None else None

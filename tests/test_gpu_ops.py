@@ -253,7 +253,7 @@ def test_hier_sample_fused_equals_unfused(E, Ni):
     assert not E.run_nerf_raybased_helpers.hier_sample_supported(zc[:, :32], wc[:, :32], Ni, u)    # 32 coarse samples
     z_all, z_std, smp, inds = E.run_nerf_raybased_helpers.hier_sample(zc, wc, Ni, u, want_samples=True, want_inds=True)
     mids_c = (.5 * (zc[..., 1:] + zc[..., :-1])).contiguous()
-    s_ref, i_ref = E.sample_pdf(mids_c, wc[..., 1:-1], Ni, u=u, return_inds=True)
+    s_ref, i_ref = E.sample_pdf(mids_c, wc[..., 1:-1], Ni, u=u, return_inds=True, u_sorted=False)   # bisection kernel
     m_ref, std_ref = E.merge_sorted(zc, s_ref, want_std=True)
     exact(smp, s_ref, "fused samples"), exact(inds, i_ref, "fused inds")
     exact(z_all, m_ref, "fused merged depths"), close(z_std, std_ref, 5e-7, "fused z_std")   # other summation order
@@ -276,9 +276,15 @@ def test_hier_sample_fused_equals_unfused(E, Ni):
         ww = w2 if k == len(tables) - 1 else wc
         a_all, a_std, a_smp, a_inds = E.run_nerf_raybased_helpers.hier_sample(zc, ww, Ni, ut, want_samples=True,
                                                                               want_inds=True)
-        s_ref, i_ref = E.sample_pdf(mids_c, ww[..., 1:-1], Ni, u=ut, return_inds=True)
+        s_ref, i_ref = E.sample_pdf(mids_c, ww[..., 1:-1], Ni, u=ut, return_inds=True, u_sorted=False)
         m_ref, std_ref = E.merge_sorted(zc, s_ref, want_std=True)
         exact(a_smp, s_ref, f"table {k} samples"), exact(a_inds, i_ref, f"table {k} inds")
+        # the stand-alone sample_pdf takes the search-free kernel for an ascending host table: same bits
+        s_det, i_det = E.sample_pdf(mids_c, ww[..., 1:-1], Ni, u=ut, return_inds=True)
+        exact(s_det, s_ref, f"table {k} sample_pdf search-free samples")
+        exact(i_det, i_ref, f"table {k} sample_pdf search-free inds")
+        s_str = E.sample_pdf(mids_c, ww[:, 1:-1], Ni, u=ut)          # strided weights view, no inds
+        exact(s_str, s_ref, f"table {k} sample_pdf search-free, strided weights")
         ok = torch.isfinite(s_ref).all(-1)          # rows with NaN samples: sort order of NaNs is unspecified
         exact(a_all[ok], m_ref[ok], f"table {k} merged depths")
         close(a_std[ok], std_ref[ok], 1e-6, f"table {k} z_std")
