@@ -133,22 +133,32 @@ class R2LWorkload:
         self.rays_per_step = RAYS * self.P
         self.block = None
         self.graph = None
+        self.frames = None
         self.net = E.synthetic.seeded_r2l(0, precision)
         self.ps = E.PointSampler(H, W, E.synthetic.LEGO["focal"], 16, 2., 6.)
         self.E = E
         self.net.packed_handle()
         self.ev = None
 
+    def enable_fused_gather(self):
+        """--shard rays --gather fused: two symmetric-memory frame buffers (alternating), the MLP kernel stores its
+        tiles into every GPU's buffer by peer-to-peer stores; a barrier replaces the NCCL all-gather."""
+        self.frames = [self.E.sharding.PeerFrame(RAYS), self.E.sharding.PeerFrame(RAYS)]
+
     def enable_graph(self):
         """--graph: sampler + fused MLP captured once into a CUDA graph, one replay per step."""
-        self.graph = self.E.GraphedR2L(self.net, self.ps, self.P, rows=self.block)
+        if self.frames is not None:
+            self.graphs = [self.E.GraphedR2L(self.net, self.ps, 1, frame=f) for f in self.frames]
+            self.graph = self.graphs[0]
+        else:
+            self.graph = self.E.GraphedR2L(self.net, self.ps, self.P, rows=self.block)
 
-    def step(self, c2w_dev, mlp_events=None):
+    def step(self, c2w_dev, mlp_events=None, k=0):
         # c2w_dev: [P, 3, 4] — P consecutive test poses rendered by ONE sampler launch + ONE fused-MLP launch
         if self.graph is not None:
             if mlp_events is not None:      # no events inside a graph: the bracket is the whole replay
                 mlp_events[0].record()
-            out = self.graph(c2w_dev)
+            out = (self.graphs[k & 1] if self.frames is not None else self.graph)(c2w_dev)
             if mlp_events is not None:
                 mlp_events[1].record()
             return out
@@ -157,7 +167,10 @@ class R2LWorkload:
             pts = pts[self.block[0]:self.block[1]]
         if mlp_events is not None:
             mlp_events[0].record()
-        rgb = self.net.forward_points(pts)
+        if self.frames is not None:         # tiles stored straight into every GPU's frame buffer k & 1
+            rgb = self.net.forward_points_gather(pts, self.frames[k & 1])
+        else:
+            rgb = self.net.forward_points(pts)
         if mlp_events is not None:
             mlp_events[1].record()
         return rgb
@@ -178,6 +191,7 @@ class NerfWorkload:
     def __init__(self, E, precision, poses_per_launch=1):
         self.P, self.rays_per_step = 1, RAYS
         self.block = None
+        self.frames = None
         self.coarse, self.fine = E.synthetic.seeded_nerf_pair(0, precision)
         self.coarse.packed_handle(), self.fine.packed_handle()
         self.E, self.focal = E, E.synthetic.LEGO["focal"]
@@ -185,7 +199,7 @@ class NerfWorkload:
                        network_fn=self.coarse, use_viewdirs=True, white_bkgd=True, raw_noise_std=0., ndc=False,
                        near=2., far=6.)
 
-    def step(self, c2w_dev, mlp_events=None):
+    def step(self, c2w_dev, mlp_events=None, k=0):
         if c2w_dev.dim() == 3:
             c2w_dev = c2w_dev[0]
         if self.block is not None:          # --shard rays: render only this rank's block of the frame's rays
@@ -279,6 +293,10 @@ def main():
                     help="poses (default): rank r renders poses r, r+G, ... (weak scaling, no data-path collective); "
                          "rays: every frame is split into contiguous ray blocks over the ranks and the tiles are "
                          "all-gathered with NCCL (strong scaling: ms per frame)")
+    ap.add_argument("--gather", choices=["nccl", "fused"], default="nccl",
+                    help="--shard rays, R2L: nccl = one all_gather_into_tensor per frame after the MLP kernel; fused = the "
+                         "MLP kernel stores its tiles into every GPU's symmetric-memory frame buffer (peer-to-peer "
+                         "stores over NVLink) and a cross-GPU barrier publishes the frame")
     ap.add_argument("--graph", action="store_true",
                     help="R2L: replay the step (sampler + fused MLP) as one CUDA graph instead of launching it from Python")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -310,6 +328,11 @@ def main():
         if P != 1:
             raise SystemExit("--shard rays renders one frame per step")
         wl.block = E.sharding.shard_rays(RAYS, rank, world)
+    fused = args.gather == "fused"
+    if fused:
+        if not (by_rays and args.workload == "r2l" and world > 1):
+            raise SystemExit("--gather fused applies to --shard rays with the R2L workload on more than one GPU")
+        wl.enable_fused_gather()
     if args.graph:
         if args.workload != "r2l":
             raise SystemExit("--graph is implemented for the R2L workload")
@@ -324,9 +347,13 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     frame_buf = torch.empty((RAYS, 3), dtype=torch.float32, device="cuda") if by_rays else None
 
-    def run_step(pose, mev=None):
-        out = wl.step(pose, mev)
-        if by_rays:     # NCCL all-gather of the finished tiles: the whole frame on every rank
+    def run_step(pose, mev=None, k=0, before_publish=None):
+        out = wl.step(pose, mev, k)
+        if fused:       # the tiles are already in every GPU's buffer k & 1: a cross-GPU barrier publishes the frame
+            if before_publish is not None:
+                before_publish()
+            out = wl.frames[k & 1].publish()
+        elif by_rays:   # NCCL all-gather of the finished tiles: the whole frame on every rank
             out = E.sharding.gather_rays_into(out.contiguous(), frame_buf, RAYS)
         return out
     peaks = measured_peaks()
@@ -344,7 +371,7 @@ def main():
             for k, pose in enumerate(pose_list):
                 flush.zero_()                              # L2 flush, outside the event bracket
                 evs[k][0].record()
-                run_step(pose, mevs[k] if with_mlp_events else None)
+                run_step(pose, mevs[k] if with_mlp_events else None, k)
                 evs[k][1].record()
             return evs, mevs
 
@@ -394,16 +421,23 @@ def main():
         e0.record()
         # the frame read-back runs on its own stream (double-buffered pinned host frames), so the D2H copy of step i
         # overlaps the kernels of step i+1 — what a caller that streams frames to the host does
+        copied = [None, None]
         for i in range(e2e_steps):
             c2w_buf.copy_(pose_host[warmup + i], non_blocking=True)          # H2D of this step's input
-            out = run_step(c2w_buf)
+            # fused gather: peers overwrite symmetric buffer (i + 1) & 1 once they pass publish(i); the read-back of
+            # the frame it still holds (step i - 1) must be over before this rank joins that barrier
+            wait_prev = (lambda: main_stream.wait_event(copied[(i + 1) & 1])) if fused and copied[(i + 1) & 1] else None
+            out = run_step(c2w_buf, None, i, wait_prev)
             if not by_rays or rank == 0:
                 done = torch.cuda.Event()
                 done.record(main_stream)
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(done)
                     frame_host2[i & 1].copy_(out, non_blocking=True)          # D2H of this step's result
-                    out.record_stream(copy_stream)
+                    if not fused:      # (symmetric-memory buffers are not the caching allocator's)
+                        out.record_stream(copy_stream)
+                    copied[i & 1] = torch.cuda.Event()
+                    copied[i & 1].record(copy_stream)
         main_stream.wait_stream(copy_stream)
         e1.record()
         barrier()
@@ -426,8 +460,12 @@ def main():
                 "scaling": "strong" if by_rays else "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": dict(wl.describe(),
-                               sharding=("contiguous ray blocks of every frame (multiples of 128 rays) + one NCCL "
-                                         "all_gather_into_tensor of the rgb tiles per frame, inside the timed region"
+                               sharding=(("contiguous ray blocks of every frame (multiples of 128 rays); the MLP kernel "
+                                          "stores its rgb tiles into every GPU's symmetric-memory frame buffer "
+                                          "(peer-to-peer stores) + one cross-GPU barrier per frame, inside the timed "
+                                          "region" if fused else
+                                          "contiguous ray blocks of every frame (multiples of 128 rays) + one NCCL "
+                                          "all_gather_into_tensor of the rgb tiles per frame, inside the timed region")
                                          if by_rays else "pose round-robin, no data-path collective"),
                                l2="flushed between steps (256 MiB memset outside the event brackets)",
                                timing="sum of per-step CUDA-event durations, max over ranks"),

@@ -424,7 +424,7 @@ using namespace r2l;
 extern "C" {
 
 const char* r2l_last_error(void) { return g_last_error.c_str(); }
-int r2l_abi_version(void) { return 3; }
+int r2l_abi_version(void) { return 4; }
 
 // Number of CUDA kernels this library has launched so far in this process (all entry points, all streams).
 long long r2l_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
@@ -867,8 +867,12 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
 
 static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_stride, const float* embedded,
                       long long emb_stride, float* rgb, cudaStream_t st, float* dbg_acc = nullptr,
-                      float* dbg_x0 = nullptr, void* dbg_a = nullptr, long long* prof = nullptr) {
+                      float* dbg_x0 = nullptr, void* dbg_a = nullptr, long long* prof = nullptr,
+                      float* const* peers = nullptr, int n_peer = 0, long long peer_row0 = 0) {
   R2lParams p{};
+  for (int g = 0; g < n_peer; ++g) p.rgb_peer[g] = peers[g];
+  p.n_peer = n_peer;
+  p.peer_row0 = peer_row0;
   p.wstream = m->wstream;
   p.w_tail = m->aux;
   for (int i = 0; i < 3; ++i) p.b_tail[i] = m->b_tail[i];
@@ -912,6 +916,27 @@ int r2l_resmlp_forward(void* handle, long long n_rays, const float* pts, long lo
   int rc = check_dbg(m, "r2l_resmlp_forward");
   if (rc != R2L_OK) return rc;
   return resmlp_run(m, n_rays, pts, pts_stride, nullptr, 0, rgb, static_cast<cudaStream_t>(stream));
+}
+
+// r2l_resmlp_forward whose tail stores this rank's rows [row0, row0 + n_rays) into EVERY peer's frame buffer
+// (peer_frames: HOST array of n_peers device pointers to [>= row0 + n_rays][3] fp32 buffers mapped for peer access,
+// this GPU's own included): the compute step and the all-gather of the ray-sharded frame in one kernel.
+int r2l_resmlp_forward_gather(void* handle, long long n_rays, const float* pts, long long pts_stride,
+                              float* const* peer_frames, int n_peers, long long row0, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 1, "r2l_resmlp_forward_gather: not an R2L handle");
+  R2L_CHECK_ARG(n_rays >= 0 && pts_stride >= 3LL * m->n_points && row0 >= 0, "r2l_resmlp_forward_gather: bad sizes");
+  R2L_CHECK_ARG(n_peers >= 1 && n_peers <= kMaxPeers, "r2l_resmlp_forward_gather: 1..%d peers (got %d)", kMaxPeers,
+                n_peers);
+  R2L_CHECK_ARG(peer_frames != nullptr, "r2l_resmlp_forward_gather: null pointer");
+  for (int g = 0; g < n_peers; ++g)
+    R2L_CHECK_ARG(peer_frames[g] != nullptr, "r2l_resmlp_forward_gather: peer %d has no frame buffer", g);
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(pts, "r2l_resmlp_forward_gather: null pointer");
+  int rc = check_dbg(m, "r2l_resmlp_forward_gather");
+  if (rc != R2L_OK) return rc;
+  return resmlp_run(m, n_rays, pts, pts_stride, nullptr, 0, nullptr, static_cast<cudaStream_t>(stream), nullptr, nullptr,
+                    nullptr, nullptr, peer_frames, n_peers, row0);
 }
 
 // NeRF_v3_2.forward(x) API path: x [n_rays, ldx] is the reference-layout embedding (n_points*63 features).

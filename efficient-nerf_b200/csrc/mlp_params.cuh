@@ -37,6 +37,8 @@ struct NerfPpMaps {
   CUtensorMap m16, m8, m4;
 };
 
+constexpr int kMaxPeers = 8;   // GPUs of one box
+
 struct R2lParams {
   const uint8_t* wstream;
   const float* w_tail;      // [3][256]
@@ -56,6 +58,12 @@ struct R2lParams {
   long long* prof;          // optional [gridDim.x][8] cycle counters (see r2l_resmlp_profile)
   float* dbg_head_acc;      // optional debug dump [n_tiles*128][256]: head accumulators (bias included)
   float* dbg_head_x0;       // optional debug dump [n_tiles*128][256]: x0 = relu(acc)
+  // fused tile gather (ray-sharded frames): when n_peer > 0 the tail stores row `ray` of this launch to
+  // rgb_peer[g] + 3 * (peer_row0 + ray) for every g — the same frame buffer on every GPU of the box, reached by
+  // peer-to-peer stores over NVLink (symmetric memory) — instead of p.rgb: the all-gather needs no kernel of its own
+  float* rgb_peer[kMaxPeers];
+  int n_peer;
+  long long peer_row0;
 };
 
 int nerf_mlp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st);

@@ -407,9 +407,23 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           o2 = 1.0f / (1.0f + expf(-o2));
         }
         if (valid) {
-          p.rgb[3 * ray + 0] = o0;
-          p.rgb[3 * ray + 1] = o1;
-          p.rgb[3 * ray + 2] = o2;
+          if (p.n_peer == 0) {
+            p.rgb[3 * ray + 0] = o0;
+            p.rgb[3 * ray + 1] = o1;
+            p.rgb[3 * ray + 2] = o2;
+          } else {
+            // fused gather: this rank's rows go straight into every GPU's frame buffer (P2P stores over NVLink; a
+            // tile is 1.5 KB per peer).  Kernel completion + the symmetric-memory barrier that follows on the stream
+            // publish them; the fence orders them before this CTA's exit at system scope.
+#pragma unroll 1
+            for (int g = 0; g < p.n_peer; ++g) {
+              float* o = p.rgb_peer[g] + 3 * (p.peer_row0 + ray);
+              o[0] = o0;
+              o[1] = o1;
+              o[2] = o2;
+            }
+            __threadfence_system();
+          }
         }
       }
     }

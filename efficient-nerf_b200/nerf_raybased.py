@@ -484,6 +484,22 @@ class NeRF_v3_2(nn.Module):
             _lib.call("r2l_resmlp_forward", h.h, N, _lib.ptr(p), p.stride(0), _lib.ptr(rgb), _lib.stream_ptr(p.device))
         return rgb
 
+    def forward_points_gather(self, pts, frame):
+        """forward_points for ONE RANK'S ray block of a sharded frame, with the tile gather fused into the kernel:
+        rgb rows land in `frame` (sharding.PeerFrame: the same [n_rays, 3] symmetric-memory buffer on every GPU of the
+        box) at this rank's row offset ON EVERY RANK by peer-to-peer stores.  Call frame.publish() afterwards (the
+        cross-GPU barrier that replaces the NCCL all-gather); returns the local view of the whole frame."""
+        _check_infer_input(pts, "pts")
+        h = self.packed_handle()
+        p = _lib.as_f32_cuda(pts).reshape(-1, pts.shape[-1])
+        N = p.shape[0]
+        if N != frame.row1 - frame.row0:
+            raise ValueError(f"this rank owns rows [{frame.row0}, {frame.row1}) of the frame, got {N} rays")
+        with torch.cuda.device(p.device):
+            _lib.call("r2l_resmlp_forward_gather", h.h, N, _lib.ptr(p), p.stride(0), frame.ptrs, frame.world_size,
+                      frame.row0, _lib.stream_ptr(p.device))
+        return frame.buf
+
     # -- nn.Module API ---------------------------------------------------------------------
     def forward(self, x):  # x: embedded position coordinates
         tc = self.precision != "fp32" and self.supports_tensor_core_path()

@@ -255,10 +255,15 @@ class GraphedR2L:
     microseconds.  `g(c2w)` copies the pose(s) into the graph's static input and replays; the returned tensor is the
     graph's static output [n_poses*H*W, 3] (overwritten by the next call)."""
 
-    def __init__(self, model, point_sampler, n_poses=1, positional_embedder=None, rows=None):
+    def __init__(self, model, point_sampler, n_poses=1, positional_embedder=None, rows=None, frame=None):
         dev = point_sampler.z_vals.device
         self.n_poses = int(n_poses)
         self.rows = rows
+        self.frame = frame      # sharding.PeerFrame: the MLP kernel stores its tiles into every GPU's frame buffer
+        if frame is not None:
+            if self.n_poses != 1:
+                raise ValueError("a PeerFrame holds one frame")
+            self.rows = rows = (frame.row0, frame.row1)
         self.c2w = torch.zeros((self.n_poses, 3, 4), dtype=torch.float32, device=dev)
         self.c2w[:, 0, 0] = self.c2w[:, 1, 1] = self.c2w[:, 2, 2] = 1.
         model.packed_handle() if getattr(model, "precision", "fp32") != "fp32" else None
@@ -268,6 +273,8 @@ class GraphedR2L:
                 return render_r2l(model, point_sampler, self.c2w if self.n_poses > 1 else self.c2w[0],
                                   positional_embedder)
             pts = point_sampler.sample_test(self.c2w[0])[self.rows[0]:self.rows[1]]   # one rank's ray block
+            if self.frame is not None:
+                return model.forward_points_gather(pts, self.frame)   # caller: frame.publish() after the replay
             return model.forward_points(pts)
 
         with torch.no_grad():

@@ -66,6 +66,37 @@ def gather_rays_into(local, out, n_rays, multiple=128, group=None):
     return out
 
 
+class PeerFrame:
+    """One frame buffer [n_rays, channels] fp32 per GPU, allocated in symmetric memory and mapped into every rank of
+    the box (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once at construction), for the fused tile
+    gather of ray-sharded frames: every rank's MLP kernel stores its rows [row0, row1) into ALL buffers by peer-to-peer
+    stores over NVLink (NeRF_v3_2.forward_points_gather), `publish()` is the cross-GPU barrier after which `buf` holds
+    the whole frame on every rank.  Replaces kernel + NCCL all_gather_into_tensor (gather_rays_into) by ONE kernel +
+    a ~7 us barrier.  A buffer may be rewritten by a peer as soon as that peer has passed the NEXT publish(): alternate
+    two PeerFrames (or consume the frame before the next publish) when frames are rendered back to back."""
+
+    def __init__(self, n_rays, channels=3, multiple=128, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerFrame needs an initialised process group (one process per GPU)")
+        self.rank, self.world_size = world()
+        if self.world_size > 8:
+            raise ValueError("peer-to-peer frames cover the GPUs of one box (<= 8 ranks)")
+        grp = group if group is not None else dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.n_rays = int(n_rays)
+        self.buf = symm_mem.empty((self.n_rays, int(channels)), dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, group=grp.group_name)
+        self.ptrs = (ctypes.c_void_p * self.world_size)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self.row0, self.row1 = shard_rays(self.n_rays, self.rank, self.world_size, multiple)
+
+    def publish(self):
+        """Cross-GPU barrier on the current stream: every rank's stores of this frame have landed everywhere."""
+        self.hdl.barrier()
+        return self.buf
+
+
 def gather_frames(local_frames, n_poses, group=None):
     """local_frames: list of [H*W, C] tensors for shard_poses(n_poses).  Returns the list of all
     n_poses frames in pose order on every rank (one all_gather per round of G poses)."""

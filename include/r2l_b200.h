@@ -164,6 +164,14 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
 int r2l_resmlp_forward(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
                        void* stream);
 
+/* Ray-sharded frame (the reference's nn.DataParallel gather, main.py:37-42): r2l_resmlp_forward whose tail
+ * stores this rank's rows [row0, row0+n_rays) into EVERY GPU's frame buffer by peer-to-peer stores — compute and
+ * all-gather in one kernel.  peer_frames: HOST array of n_peers (<= 8) device pointers to [>= row0+n_rays][3] fp32
+ * buffers mapped for peer access (symmetric memory), this GPU's own included.  The caller publishes the frame with a
+ * cross-GPU barrier on the same stream. */
+int r2l_resmlp_forward_gather(void* handle, long long n_rays, const float* pts, long long pts_stride,
+                              float* const* peer_frames, int n_peers, long long row0, void* stream);
+
 /* NeRF_v3_2.forward(x [n_rays, n_points*63]) -> [n_rays,3]   (model/nerf_raybased.py:539-544). */
 int r2l_resmlp_forward_embedded(void* handle, long long n_rays, const float* x, long long ldx, float* rgb,
                                 void* stream);
