@@ -94,3 +94,47 @@ def sample_pdf_np(bins: np.ndarray, weights: np.ndarray, u: np.ndarray):
     t = ((u - c0).astype(F32) / denom).astype(F32)                               # helpers:327
     samples = (b0 + (t * (b1 - b0).astype(F32)).astype(F32)).astype(F32)         # helpers:328
     return samples, inds, cdf
+
+
+# ---- the search-free scheme of hier_sample_det_kernel / sample_pdf_det_kernel (csrc/sample_pdf.cu), restated ----------
+# Test infrastructure like the rest of oracle/: it pins the IDENTITIES the kernels rely on (for an ascending u table
+# and an ascending cdf) against plain searchsorted / sort on the CPU, so a -m "not gpu" run covers the algorithm.
+def inds_by_marks(cdf: np.ndarray, u: np.ndarray) -> np.ndarray:
+    """searchsorted(cdf, u, right=True) = #{j : cdf_j <= u_k} without searching u per sample:
+    r_j = #{k : u_k < cdf_j}; the LAST j of every run of equal r writes mark[r_j] = j + 1; inds = running max of the
+    marks over k.  Needs u and cdf ascending (helpers:287-292 with det=True)."""
+    N, nb = cdf.shape
+    Ni = u.shape[0]
+    out = np.zeros((N, Ni), dtype=np.int64)
+    for n in range(N):
+        r = np.searchsorted(u, cdf[n], side="left")            # #{k : u_k < cdf_j}; the kernel: ceil(cdf (Ni-1)) + fix-up
+        mark = np.zeros(Ni + 1, dtype=np.int64)
+        for j in range(nb):
+            if j == nb - 1 or r[j] != r[j + 1]:
+                mark[r[j]] = j + 1
+        out[n] = np.maximum.accumulate(mark[:Ni])
+    return out
+
+
+def merge_by_ranks(z: np.ndarray, s: np.ndarray, inds: np.ndarray) -> np.ndarray:
+    """sort(cat[z, s]) for ascending z [N, nz] and ascending samples s [N, Ni] drawn from bins `inds` (main.py:730-732):
+    rank(s_k) = k + cle_k with cle_k = #{z <= s_k} = below + 1 + (z[below+1] <= s_k) (+ the kernel's verification);
+    rank(z_i) = i + #{k : cle_k <= i}, again marks (last k of every run of equal cle writes k + 1) + a running max."""
+    N, nz = z.shape
+    Ni = s.shape[1]
+    out = np.full((N, nz + Ni), np.nan, dtype=z.dtype)
+    for n in range(N):
+        below = np.maximum(inds[n] - 1, 0)
+        zp = np.concatenate([z[n], [np.inf, np.inf, np.inf]])
+        cle = below + 1 + (zp[below + 1] <= s[n])
+        bad = ~(zp[below] <= s[n]) | (zp[below + 2] <= s[n])
+        if bad.any():                                           # the kernel's scan fallback
+            cle = np.searchsorted(z[n], s[n], side="right")
+        out[n, np.arange(Ni) + cle] = s[n]
+        mark = np.zeros(nz + 2, dtype=np.int64)
+        for k in range(Ni):
+            if k == Ni - 1 or cle[k] != cle[k + 1]:
+                mark[cle[k]] = k + 1
+        cnt = np.maximum.accumulate(mark[:nz])
+        out[n, np.arange(nz) + cnt] = z[n]
+    return out

@@ -135,3 +135,32 @@ def test_sampler_extra_forms(golden, O):
     assert torch.equal(O.plucker(ro.reshape(-1, 3), rd.reshape(-1, 3)), t(g["plucker_train"]))
     assert torch.equal(O.sample_test_plucker(H, W, focal, t(g["c2w"])), t(g["plucker_test"]))
     assert torch.equal(O.embed_cnnstyle(t(g["x"]), 5), t(g["embed_L5"]))
+
+
+def test_search_free_identities_of_the_det_kernels():
+    """The counting identities behind hier_sample_det_kernel / sample_pdf_det_kernel (marks + running max instead of
+    per-sample bisections, rank merge instead of a sort), restated in numpy, against searchsorted / sort — on the
+    golden weights, on sparse / flat / tied pdfs and on ascending tables that are not a linspace."""
+    from oracle.sample_pdf_np import sample_pdf_np, inds_by_marks, merge_by_ranks
+    rng = np.random.RandomState(0)
+    N = 300
+    t_vals = np.linspace(0., 1., 64, dtype=np.float32)
+    z = np.broadcast_to(2. * (1. - t_vals) + 6. * t_vals, (N, 64)).astype(np.float32).copy()
+    z[N // 2:] = np.sort(rng.uniform(2., 6., (N - N // 2, 64)).astype(np.float32), -1)
+    z[3, 10:20] = z[3, 10]                                       # tied coarse depths
+    mids = (.5 * (z[:, 1:] + z[:, :-1])).astype(np.float32)
+    w = (rng.rand(N, 62) ** 8).astype(np.float32)
+    w[::3] = rng.rand(N, 62)[::3]
+    w[5] = 0.                                                    # flat pdf
+    w[7, 10:50] = 0.                                             # long run of equal cdf entries
+    w[9] = 0.
+    w[9, 31] = 1.                                                # all mass in one bin: samples pile up
+    tables = [np.linspace(0., 1., 128, dtype=np.float32), np.linspace(0., 1., 64, dtype=np.float32),
+              np.sort(rng.rand(128)).astype(np.float32), np.sort(np.round(rng.rand(128) * 8) / 8).astype(np.float32),
+              np.zeros(64, np.float32), np.ones(128, np.float32)]
+    for u in tables:
+        s, inds, cdf = sample_pdf_np(mids, w, u)
+        assert np.array_equal(inds_by_marks(cdf, u), inds)
+        assert (np.diff(s, axis=-1) >= 0).all()                  # ascending u -> ascending samples
+        merged = merge_by_ranks(z, s, inds)
+        assert np.array_equal(merged, np.sort(np.concatenate([z, s], -1), -1))
