@@ -468,6 +468,19 @@ def load_script(script, argv=(), fused=True, stubs=True, patch=True):
     exec(code, mod.__dict__)
     if patch:
         mod.__dropin_patched__ = patch_glue(mod, create_data_flavour=(stem == "create_data"))
+        a = getattr(mod, "args", None)
+        if stem == "create_data" and a is not None and (getattr(a, "trans_origin", "") or
+                                                          float(getattr(a, "focal_scale", 1.) or 1.) != 1.):
+            # create_data.py:35-38 wraps get_rays in a partial carrying these two options; the fused render() builds
+            # its rays itself and would silently drop them
+            raise NotImplementedError("--trans_origin / --focal_scale are outside the rendering hot path (DESIGN.md §7)")
+    # `--benchmark` (main.py:1125-1132) times `render_func` through `from __main__ import render_func`: the script's
+    # functions are also reachable from the real __main__ (this launcher), without overwriting anything there
+    real_main = sys.modules.get("__main__")
+    if real_main is not None and real_main is not mod:
+        for name, obj in list(vars(mod).items()):
+            if isinstance(obj, types.FunctionType) and obj.__module__ == stem and not hasattr(real_main, name):
+                setattr(real_main, name, obj)
     return mod
 
 
