@@ -5,8 +5,8 @@
 
 Workload (config.workload):
   r2l  (default, BASELINE configs[1]): R2L lego_noview resmlp W256 D88, n_sample_per_ray=16, 400x400
-       synthetic test poses; one STEP = one pose = one 160 000-ray frame through
-       PointSampler -> fused (PositionalEmbedder + 88-layer ResMLP) kernel.
+       synthetic test poses; one STEP = one launch of the fused kernel (PointSampler ray generation +
+       PositionalEmbedder + 88-layer ResMLP) over the step's poses.
   nerf (BASELINE configs[0]): NeRF lego W256 D8, 64 coarse + 128 fine samples, one STEP = one 400x400 frame
        through get_rays -> fused encode+MLP (coarse) -> raw2outputs -> sample_pdf -> merge -> fused
        encode+MLP (fine) -> raw2outputs.
@@ -126,7 +126,7 @@ def make_poses(E, n, offset=0, stride=1):
 
 class R2LWorkload:
     name = "r2l"
-    kernels_per_step = 2   # point_sample_kernel + r2l_mlp_kernel
+    kernels_per_step = 1   # r2l_mlp_kernel (ray generation fused)
 
     def __init__(self, E, precision, poses_per_launch=1):
         self.P = int(poses_per_launch)
@@ -162,15 +162,12 @@ class R2LWorkload:
             if mlp_events is not None:
                 mlp_events[1].record()
             return out
-        pts = self.ps.sample_test_batch(c2w_dev) if c2w_dev.dim() == 3 else self.ps.sample_test(c2w_dev)
-        if self.block is not None:          # --shard rays: this rank's contiguous block of the frame's rays
-            pts = pts[self.block[0]:self.block[1]]
         if mlp_events is not None:
             mlp_events[0].record()
-        if self.frames is not None:         # tiles stored straight into every GPU's frame buffer k & 1
-            rgb = self.net.forward_points_gather(pts, self.frames[k & 1])
-        else:
-            rgb = self.net.forward_points(pts)
+        # ONE kernel: rays from pixel index + pose, stratified points, encoding, 88-layer ResMLP.  --shard rays: this
+        # rank's contiguous block of the frame's rays; --gather fused: tiles stored into every GPU's frame buffer k & 1
+        rgb = self.net.render_poses(self.ps, c2w_dev, rows=self.block,
+                                    frame=self.frames[k & 1] if self.frames is not None else None)
         if mlp_events is not None:
             mlp_events[1].record()
         return rgb
@@ -536,7 +533,7 @@ def extras(E, peaks, precision, main_workload):
             r2l = R2LWorkload(E, precision, 1)
             ps8 = E.PointSampler(cam8["H"], cam8["W"], cam8["focal"], 16, 2., 6.)
             n8 = cam8["H"] * cam8["W"]
-            ms = timeit(lambda: r2l.net.forward_points(ps8.sample_test(pose)), n=20)
+            ms = timeit(lambda: r2l.net.render_poses(ps8, pose), n=20)
             out["r2l_800x800"] = {"ms_per_frame": ms, "Mrays_per_s": n8 / ms / 1e3,
                                   "tensor_TFLOPs": FLOP_PER_RAY["r2l"] * n8 / ms / 1e9}
             nw = wl if other == "nerf" else NerfWorkload(E, precision)

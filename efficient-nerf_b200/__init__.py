@@ -21,7 +21,7 @@ from . import synthetic
 from . import dropin
 from .run_nerf_raybased_helpers import (get_rays, ndc_rays, Embedder, get_embedder, raw2outputs, sample_pdf,
                                         normalize_dirs, merge_sorted)
-from .nerf_raybased import NeRF, ResMLP, NeRF_v3_2, PointSampler, PositionalEmbedder, LazyEmbedding, get_activation
+from .nerf_raybased import NeRF, ResMLP, NeRF_v3_2, PointSampler, PositionalEmbedder, LazyEmbedding, LazyPoints, get_activation
 from .render import render_rays, render_rays_create_data, batchify_rays, batchify, run_network, render_r2l, render_path, GraphedR2L
 from .render import render as render_image
 

@@ -54,6 +54,8 @@ SIGNATURES = {
                           _c_f32p, _c_int, _c_int, _c_vp],
     "r2l_resmlp_forward": [_c_vp, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_vp],
     "r2l_resmlp_forward_embedded": [_c_vp, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_vp],
+    "r2l_resmlp_render": [_c_vp, _c_int, _c_int, _c_int, _c_dbl, _c_f32p, _c_f32p, _c_int, _c_ll, _c_ll, _c_f32p,
+                          ctypes.POINTER(_c_vp), _c_int, _c_ll, _c_vp],
     "r2l_resmlp_forward_gather": [_c_vp, _c_ll, _c_f32p, _c_ll, ctypes.POINTER(_c_vp), _c_int, _c_ll, _c_vp],
     "r2l_resmlp_debug_head": [_c_vp, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_f32p, _c_f32p, _c_vp, _c_vp],
     "r2l_resmlp_profile": [_c_vp, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_vp, _c_vp],

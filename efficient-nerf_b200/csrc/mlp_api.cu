@@ -424,7 +424,7 @@ using namespace r2l;
 extern "C" {
 
 const char* r2l_last_error(void) { return g_last_error.c_str(); }
-int r2l_abi_version(void) { return 4; }
+int r2l_abi_version(void) { return 5; }
 
 // Number of CUDA kernels this library has launched so far in this process (all entry points, all streams).
 long long r2l_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
@@ -868,8 +868,13 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
 static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_stride, const float* embedded,
                       long long emb_stride, float* rgb, cudaStream_t st, float* dbg_acc = nullptr,
                       float* dbg_x0 = nullptr, void* dbg_a = nullptr, long long* prof = nullptr,
-                      float* const* peers = nullptr, int n_peer = 0, long long peer_row0 = 0) {
+                      float* const* peers = nullptr, int n_peer = 0, long long peer_row0 = 0,
+                      const R2lParams* cam = nullptr) {
   R2lParams p{};
+  if (cam != nullptr) {
+    p.cam = cam->cam, p.cam_z = cam->cam_z, p.cam_H = cam->cam_H, p.cam_W = cam->cam_W;
+    p.cam_focal = cam->cam_focal, p.cam_ray0 = cam->cam_ray0;
+  }
   for (int g = 0; g < n_peer; ++g) p.rgb_peer[g] = peers[g];
   p.n_peer = n_peer;
   p.peer_row0 = peer_row0;
@@ -916,6 +921,39 @@ int r2l_resmlp_forward(void* handle, long long n_rays, const float* pts, long lo
   int rc = check_dbg(m, "r2l_resmlp_forward");
   if (rc != R2L_OK) return rc;
   return resmlp_run(m, n_rays, pts, pts_stride, nullptr, 0, rgb, static_cast<cudaStream_t>(stream));
+}
+
+// PointSampler.sample_test + PositionalEmbedder + NeRF_v3_2 in ONE kernel (main.py:297-309): the head generates its
+// rays from the pixel index (c2w [n_poses][3][4] device, z_vals [n_sample] device = PointSampler.z_vals) — no pts
+// tensor.  Renders rays [ray0, ray0 + n_rays) of the pose-major range [n_poses][H*W] into rgb [n_rays][3], or, when
+// peer_frames != NULL, into every peer's frame buffer at rows row0.. (see r2l_resmlp_forward_gather).
+int r2l_resmlp_render(void* handle, int n_poses, int H, int W, double focal, const float* c2w, const float* z_vals,
+                      int n_sample, long long ray0, long long n_rays, float* rgb, float* const* peer_frames,
+                      int n_peers, long long row0, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 1, "r2l_resmlp_render: not an R2L handle");
+  R2L_CHECK_ARG(n_poses >= 1 && H > 0 && W > 0 && focal != 0.0, "r2l_resmlp_render: bad camera");
+  R2L_CHECK_ARG(n_sample == m->n_points, "r2l_resmlp_render: the sampler draws %d points per ray, the model takes %d",
+                n_sample, m->n_points);
+  R2L_CHECK_ARG(ray0 >= 0 && n_rays >= 0 && ray0 + n_rays <= static_cast<long long>(n_poses) * H * W,
+                "r2l_resmlp_render: rays [%lld, %lld) outside %d x %d x %d", ray0, ray0 + n_rays, n_poses, H, W);
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(c2w && z_vals, "r2l_resmlp_render: null pointer");
+  if (peer_frames != nullptr) {
+    R2L_CHECK_ARG(n_peers >= 1 && n_peers <= kMaxPeers && row0 >= 0, "r2l_resmlp_render: 1..%d peers", kMaxPeers);
+    for (int g = 0; g < n_peers; ++g)
+      R2L_CHECK_ARG(peer_frames[g] != nullptr, "r2l_resmlp_render: peer %d has no frame buffer", g);
+  } else {
+    R2L_CHECK_ARG(rgb != nullptr, "r2l_resmlp_render: null pointer");
+    n_peers = 0;
+  }
+  int rc = check_dbg(m, "r2l_resmlp_render");
+  if (rc != R2L_OK) return rc;
+  R2lParams cam{};
+  cam.cam = c2w, cam.cam_z = z_vals, cam.cam_H = H, cam.cam_W = W;
+  cam.cam_focal = static_cast<float>(focal), cam.cam_ray0 = ray0;
+  return resmlp_run(m, n_rays, nullptr, 0, nullptr, 0, rgb, static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr,
+                    nullptr, peer_frames, n_peers, row0, &cam);
 }
 
 // r2l_resmlp_forward whose tail stores this rank's rows [row0, row0 + n_rays) into EVERY peer's frame buffer

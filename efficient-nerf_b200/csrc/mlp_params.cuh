@@ -64,6 +64,15 @@ struct R2lParams {
   float* rgb_peer[kMaxPeers];
   int n_peer;
   long long peer_row0;
+  // fused ray generation + point sampling (PointSampler.sample_test, model/nerf_raybased.py:94-102): when cam != nullptr
+  // the head computes its points from the pixel index instead of reading p.pts — row r of this launch is ray
+  // cam_ray0 + r of the pose-major range [n_poses][H*W]; cam = c2w [n_poses][3][4], cam_z = the sampler's z_vals
+  // [n_points]; the same rounded operations, in the same order, as point_sample_kernel (rays.cu)
+  const float* cam;
+  const float* cam_z;
+  int cam_H, cam_W;
+  float cam_focal;
+  long long cam_ray0;
 };
 
 int nerf_mlp_launch(bool bf16, const NerfParams& p, int grid, cudaStream_t st);

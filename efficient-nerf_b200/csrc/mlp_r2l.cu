@@ -276,6 +276,24 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       const long long ray_c = valid ? ray : (p.n_rays - 1);
       const float* prow = (p.pts != nullptr) ? p.pts + ray_c * p.pts_stride : nullptr;
       const float* erow = (p.embedded != nullptr) ? p.embedded + ray_c * p.emb_stride : nullptr;
+      // fused ray generation: this row's ray from its pixel index and pose (point_sample_kernel's arithmetic)
+      float rox = 0.f, roy = 0.f, roz = 0.f, rdx = 0.f, rdy = 0.f, rdz = 0.f;
+      if (p.cam != nullptr) {
+        const long long g = p.cam_ray0 + ray_c;
+        const long long hw = static_cast<long long>(p.cam_H) * p.cam_W;
+        const float* c = p.cam + 12 * (g / hw);
+        const int pix = static_cast<int>(g % hw);
+        const int h = pix / p.cam_W, w = pix % p.cam_W;
+        const float dx = __fdiv_rn(__fsub_rn(static_cast<float>(w), static_cast<float>(p.cam_W * 0.5)), p.cam_focal);
+        const float dy = -__fdiv_rn(__fsub_rn(static_cast<float>(h), static_cast<float>(p.cam_H * 0.5)), p.cam_focal);
+        rdx = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(dx, __ldg(c + 0))), __fmul_rn(dy, __ldg(c + 1))),
+                        __fmul_rn(-1.0f, __ldg(c + 2)));
+        rdy = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(dx, __ldg(c + 4))), __fmul_rn(dy, __ldg(c + 5))),
+                        __fmul_rn(-1.0f, __ldg(c + 6)));
+        rdz = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(dx, __ldg(c + 8))), __fmul_rn(dy, __ldg(c + 9))),
+                        __fmul_rn(-1.0f, __ldg(c + 10)));
+        rox = __ldg(c + 3), roy = __ldg(c + 7), roz = __ldg(c + 11);
+      }
       // ---- head: chunks of 4 points (K = 256); this WG encodes blocks j = wg and wg+2 of every chunk
       const long long ce = prof ? clock64() : 0;
       for (int c = 0; c < n_chunks; ++c) {
@@ -284,7 +302,12 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           const int j = wg + 2 * bi;
           const int pt = c * 4 + j;
           float px = 0.f, py = 0.f, pz = 0.f;
-          if (erow == nullptr) {
+          if (p.cam != nullptr) {
+            const float zz = __ldg(p.cam_z + pt);
+            px = __fadd_rn(rox, __fmul_rn(rdx, zz));
+            py = __fadd_rn(roy, __fmul_rn(rdy, zz));
+            pz = __fadd_rn(roz, __fmul_rn(rdz, zz));
+          } else if (erow == nullptr) {
             px = __ldg(prow + 3 * pt);
             py = __ldg(prow + 3 * pt + 1);
             pz = __ldg(prow + 3 * pt + 2);

@@ -10,8 +10,8 @@ What the launcher does, in this order (no file of the reference is edited or cop
 1. `install()` registers stand-in modules under the two import paths the reference binds its hot path from —
    `model.nerf_raybased` (main.py:12, create_data.py:10) and `utils.run_nerf_raybased_helpers` (main.py:18-20,
    create_data.py:11, dataset/load_blender.py:8, load_llff.py:4) — that export this package's mirrors under the
-   reference's names.  `PositionalEmbedder` is the lazy form there, so main.py:297-309
-   `model(positional_embedder(point_sampler.sample_test(c2w)))` runs the fused encode+ResMLP kernel.
+   reference's names.  `PointSampler` and `PositionalEmbedder` are the lazy forms there, so main.py:297-309
+   `model(positional_embedder(point_sampler.sample_test(c2w)))` is ONE kernel (ray generation + encoding + ResMLP).
 2. Packages the reference imports but this image does not have are stubbed IF absent (`smilelogging`, `imageio`,
    `lpips`, `matplotlib` is simply not needed): see `install_stubs`.  A real installation always wins.  The LPIPS
    stub returns NaN — a pretrained perceptual network is out of scope, PSNR / SSIM / FLIP are real.
@@ -89,6 +89,14 @@ class _LazyPositionalEmbedder(nerf_raybased.PositionalEmbedder):
         super().__init__(L, include_input=include_input, lazy=lazy)
 
 
+class _LazyPointSampler(nerf_raybased.PointSampler):
+    """main.py:1017 builds `PointSampler(H, W, focal, n_sample, near, far)`; here sample_test hands out the lazy handle,
+    so `model(positional_embedder(point_sampler.sample_test(c2w)))` is ONE kernel (rays generated inside it)."""
+
+    def __init__(self, H, W, focal, n_sample, near, far, lazy=True):
+        super().__init__(H, W, focal, n_sample, near, far, lazy=lazy)
+
+
 def _public(mod):
     return {k: v for k, v in vars(mod).items() if not k.startswith("_")}
 
@@ -109,6 +117,7 @@ def _standin_modules(fused):
             mm.__dict__.setdefault(name, getattr(hm, name))
     if fused:
         mm.PositionalEmbedder = _LazyPositionalEmbedder
+        mm.PointSampler = _LazyPointSampler
     hm.__doc__ = mm.__doc__ = "efficient_nerf_b200 stand-in (dropin.install)"
     return mm, hm
 

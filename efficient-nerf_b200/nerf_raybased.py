@@ -325,6 +325,51 @@ def get_activation(act):
     return func
 
 
+class LazyPoints:
+    """Deferred PointSampler.sample_test output (PointSampler(..., lazy=True)): remembers sampler and pose(s) so that
+    NeRF_v3_2 can generate the rays INSIDE the fused kernel (r2l_resmlp_render: no [H*W, n_sample*3] tensor at all);
+    anything else that touches it gets the materialised points."""
+
+    def __init__(self, sampler, c2ws):
+        self.sampler, self.c2ws = sampler, c2ws      # c2ws: [P, 3, 4] on the sampler's device
+        self._mat = None
+
+    @property
+    def shape(self):
+        return torch.Size((self.c2ws.shape[0] * self.sampler.H * self.sampler.W, self.sampler.n_sample * 3))
+
+    def dim(self):
+        return 2
+
+    @property
+    def device(self):
+        return self.c2ws.device
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    @property
+    def requires_grad(self):
+        return False
+
+    def materialize(self):
+        if self._mat is None:
+            self._mat = self.sampler.sample_test_batch(self.c2ws, lazy=False)
+        return self._mat
+
+    def __getattr__(self, name):
+        return getattr(self.materialize(), name)
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        conv = lambda a: a.materialize() if isinstance(a, LazyPoints) else a
+        return func(*[conv(a) for a in args], **{k: conv(v) for k, v in (kwargs or {}).items()})
+
+
 class LazyEmbedding:
     """Deferred PositionalEmbedder output: remembers the sampled points so that NeRF_v3_2 can run the
     fused encode+MLP kernel; anything else that touches it gets the materialised [N, dim*(2L+1)] tensor."""
@@ -348,7 +393,8 @@ class LazyEmbedding:
 
     def materialize(self):
         if self._mat is None:
-            self._mat = _embed(self.pts, self.L, self.include_input, 1)
+            pts = self.pts.materialize() if isinstance(self.pts, LazyPoints) else self.pts
+            self._mat = _embed(pts, self.L, self.include_input, 1)
         return self._mat
 
     def __getattr__(self, name):
@@ -484,6 +530,35 @@ class NeRF_v3_2(nn.Module):
             _lib.call("r2l_resmlp_forward", h.h, N, _lib.ptr(p), p.stride(0), _lib.ptr(rgb), _lib.stream_ptr(p.device))
         return rgb
 
+    def render_poses(self, sampler, c2ws, rows=None, frame=None):
+        """PointSampler.sample_test + PositionalEmbedder(L=10) + network in ONE kernel (main.py:297-309): the head
+        generates its rays from pixel index and pose, no points tensor.  c2ws [3|4, 4] or [P, 3|4, 4]; `rows` =
+        (start, stop) of the pose-major ray range [P*H*W] to render (default: all).  With `frame`
+        (sharding.PeerFrame, one pose) this rank's rows are stored into every GPU's frame buffer (call
+        frame.publish() afterwards).  Bit-identical to forward_points(sampler.sample_test(c2w))."""
+        if sampler.n_sample * 63 != self.input_dim:
+            raise ValueError(f"the sampler draws {sampler.n_sample} points per ray, the model takes {self.input_dim // 63}")
+        h = self.packed_handle()
+        dev = sampler.z_vals.device
+        c = _lib.as_f32_cuda(c2ws, dev, "c2w")
+        c = c.reshape(-1, c.shape[-2], 4)[:, :3, :4].contiguous()
+        P, n_all = c.shape[0], c.shape[0] * sampler.H * sampler.W
+        if frame is not None:
+            if P != 1 or frame.n_rays != n_all:
+                raise ValueError("a PeerFrame holds one frame of this sampler's size")
+            rows = (frame.row0, frame.row1)
+        r0, r1 = (0, n_all) if rows is None else (int(rows[0]), int(rows[1]))
+        if not (0 <= r0 <= r1 <= n_all):
+            raise ValueError(f"rows {rows} outside [0, {n_all}]")
+        z = sampler.z_vals.contiguous()
+        rgb = None if frame is not None else torch.empty((r1 - r0, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("r2l_resmlp_render", h.h, P, sampler.H, sampler.W, sampler.focal, _lib.ptr(c), _lib.ptr(z),
+                      sampler.n_sample, r0, r1 - r0, _lib.ptr(rgb), frame.ptrs if frame is not None else None,
+                      frame.world_size if frame is not None else 0, r0 if frame is not None else 0,
+                      _lib.stream_ptr(dev))
+        return frame.buf if frame is not None else rgb
+
     def forward_points_gather(self, pts, frame):
         """forward_points for ONE RANK'S ray block of a sharded frame, with the tile gather fused into the kernel:
         rgb rows land in `frame` (sharding.PeerFrame: the same [n_rays, 3] symmetric-memory buffer on every GPU of the
@@ -505,6 +580,8 @@ class NeRF_v3_2(nn.Module):
         tc = self.precision != "fp32" and self.supports_tensor_core_path()
         if isinstance(x, LazyEmbedding):
             if tc and x.L == 10 and x.include_input and x.pts.shape[-1] * 21 == self.input_dim:
+                if isinstance(x.pts, LazyPoints):      # rays generated inside the kernel
+                    return self.render_poses(x.pts.sampler, x.pts.c2ws)
                 return self.forward_points(x.pts)
             x = x.materialize()
         _check_infer_input(x, "x")
@@ -533,10 +610,11 @@ class NeRF_v3_2(nn.Module):
 # ----------------------------------------------------------------------------- R2L input pipeline
 class PointSampler():
 
-    def __init__(self, H, W, focal, n_sample, near, far):
+    def __init__(self, H, W, focal, n_sample, near, far, lazy=False):
         _lib.require_cuda()
         self.H, self.W, self.focal = int(H), int(W), float(focal)
         self.n_sample = int(n_sample)
+        self.lazy = lazy        # sample_test returns a LazyPoints handle (rays generated inside the fused kernel)
         dev = torch.device("cuda", torch.cuda.current_device())
         t_vals = torch.linspace(0., 1., steps=n_sample).to(dev)  # host linspace, like the reference (model:88-89)
         self.z_vals = near * (1 - t_vals) + far * (t_vals)       # [n_sample]
@@ -553,9 +631,12 @@ class PointSampler():
         return pts
 
     def sample_test(self, c2w):  # c2w: [3, 4]
+        if self.lazy:
+            c = _lib.as_f32_cuda(c2w, self.z_vals.device, "c2w")
+            return LazyPoints(self, c[:3, :4].reshape(1, 3, 4).contiguous())
         return self._sample(c2w)  # [H*W, n_sample*3]
 
-    def sample_test_batch(self, c2ws):
+    def sample_test_batch(self, c2ws, lazy=None):
         """sample_test for P poses in one launch: c2ws [P, 3|4, 4] -> [P*H*W, n_sample*3] (pose-major), so that one
         fused-MLP launch renders P frames (full waves of 128-ray tiles instead of a ragged last wave per frame)."""
         dev = self.z_vals.device
@@ -563,6 +644,8 @@ class PointSampler():
         if c.dim() != 3 or c.shape[-1] != 4 or c.shape[-2] < 3:
             raise ValueError(f"c2ws must be [P, 3, 4] or [P, 4, 4], got {tuple(c.shape)}")
         c = c[:, :3, :4].contiguous()
+        if self.lazy if lazy is None else lazy:
+            return LazyPoints(self, c)
         P = c.shape[0]
         pts = torch.empty((P * self.H * self.W, self.n_sample * 3), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -668,7 +751,9 @@ class PositionalEmbedder():
 
     def __call__(self, x):
         if self.lazy and x.dim() == 2:
-            return LazyEmbedding(_lib.as_f32_cuda(x), self.L, self.include_input)
+            return LazyEmbedding(x if isinstance(x, LazyPoints) else _lib.as_f32_cuda(x), self.L, self.include_input)
+        if isinstance(x, LazyPoints):
+            x = x.materialize()
         return _embed(x, self.L, self.include_input, 1)  # [n_ray, dim_pts*(2L+1)]
 
     def embed_cnnstyle(self, x):

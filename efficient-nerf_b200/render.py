@@ -237,21 +237,21 @@ def render_r2l(model, point_sampler, c2w, positional_embedder=None):
     """R2L branch of render_path (main.py:285-325): one frame = one un-chunked forward.
     Uses the fused encode+MLP kernel when the model supports it; returns rgb [H*W, 3]."""
     c = c2w if isinstance(c2w, torch.Tensor) else torch.as_tensor(c2w)
-    # a stack of poses [P, 3, 4] renders P frames with ONE launch each of the sampler and the fused MLP -> [P*H*W, 3]
-    pts = point_sampler.sample_test_batch(c) if c.dim() == 3 else point_sampler.sample_test(c2w)
+    # a stack of poses [P, 3, 4] renders P frames with ONE launch -> [P*H*W, 3]
     if model.precision != "fp32" and model.supports_tensor_core_path():
         L = positional_embedder.L if positional_embedder is not None else 10
-        if L == 10 and pts.shape[-1] * 21 == model.input_dim:
-            return model.forward_points(pts)
+        if L == 10 and point_sampler.n_sample * 63 == model.input_dim:
+            return model.render_poses(point_sampler, c)      # rays generated inside the fused kernel
+    pts = point_sampler.sample_test_batch(c, lazy=False) if c.dim() == 3 else point_sampler._sample(c)
     if positional_embedder is None:
         raise ValueError("positional_embedder is required for the non-fused path")
     return model(positional_embedder(pts))
 
 
 class GraphedR2L:
-    """The R2L frame (PointSampler kernel + fused encode/MLP kernel) captured ONCE into a CUDA graph and replayed per
-    pose: one graph launch per frame (or per stack of `n_poses` frames) instead of two kernel launches plus the
-    Python glue around them — what matters when a frame is sharded over many GPUs and takes a few hundred
+    """The R2L frame (ray generation + encode + MLP: one kernel) captured ONCE into a CUDA graph and replayed per
+    pose: one graph launch per frame (or per stack of `n_poses` frames) instead of the kernel launch plus the
+    Python glue around it — what matters when a frame is sharded over many GPUs and takes a few hundred
     microseconds.  `g(c2w)` copies the pose(s) into the graph's static input and replays; the returned tensor is the
     graph's static output [n_poses*H*W, 3] (overwritten by the next call)."""
 
@@ -272,10 +272,8 @@ class GraphedR2L:
             if self.rows is None:
                 return render_r2l(model, point_sampler, self.c2w if self.n_poses > 1 else self.c2w[0],
                                   positional_embedder)
-            pts = point_sampler.sample_test(self.c2w[0])[self.rows[0]:self.rows[1]]   # one rank's ray block
-            if self.frame is not None:
-                return model.forward_points_gather(pts, self.frame)   # caller: frame.publish() after the replay
-            return model.forward_points(pts)
+            # one rank's ray block; with a frame the tiles go to every GPU (caller: frame.publish() after the replay)
+            return model.render_poses(point_sampler, self.c2w, rows=self.rows, frame=self.frame)
 
         with torch.no_grad():
             side = torch.cuda.Stream(dev)

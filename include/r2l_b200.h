@@ -164,6 +164,15 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
 int r2l_resmlp_forward(void* handle, long long n_rays, const float* pts, long long pts_stride, float* rgb,
                        void* stream);
 
+/* The whole R2L frame in ONE kernel: PointSampler.sample_test (model/nerf_raybased.py:94-102) + PositionalEmbedder +
+ * NeRF_v3_2 (main.py:297-309).  The head generates its rays from the pixel index: c2w [n_poses][3][4] (device),
+ * z_vals [n_sample] (device; PointSampler's linspace(near, far)); renders rays [ray0, ray0+n_rays) of the pose-major
+ * range [n_poses][H*W] into rgb [n_rays][3] — or, with peer_frames != NULL (n_peers <= 8), into every GPU's frame
+ * buffer at rows row0.. like r2l_resmlp_forward_gather.  Bit-identical to r2l_point_sample + r2l_resmlp_forward. */
+int r2l_resmlp_render(void* handle, int n_poses, int H, int W, double focal, const float* c2w, const float* z_vals,
+                      int n_sample, long long ray0, long long n_rays, float* rgb, float* const* peer_frames,
+                      int n_peers, long long row0, void* stream);
+
 /* Ray-sharded frame (the reference's nn.DataParallel gather, main.py:37-42): r2l_resmlp_forward whose tail
  * stores this rank's rows [row0, row0+n_rays) into EVERY GPU's frame buffer by peer-to-peer stores — compute and
  * all-gather in one kernel.  peer_frames: HOST array of n_peers (<= 8) device pointers to [>= row0+n_rays][3] fp32

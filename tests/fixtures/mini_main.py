@@ -82,5 +82,6 @@ def train():
     assert torch.equal(render_func(model, pose44).view(H, W, 3), rgb_r2l)
     logger.info(f'render_func: {timed.mean * 1e3:.3f} ms')
     np.savez(args.out, r2l=rgb_r2l.cpu().numpy(), nerf=rgb.cpu().numpy(), frame8=to8b(rgb_r2l),
-             lazy=type(positional_embedder(point_sampler.sample_test(c2w))).__name__, calls=np.array(CALLS, dtype=str),
+             lazy=type(positional_embedder(point_sampler.sample_test(c2w))).__name__,
+             lazy_pts=type(point_sampler.sample_test(c2w)).__name__, calls=np.array(CALLS, dtype=str),
              trial=args.trial.body_arch)

@@ -123,7 +123,7 @@ def test_launcher_renders_what_direct_calls_render(tmp_path, E):
                        env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     got = np.load(out)
-    assert str(got["lazy"]) == "LazyEmbedding" and got["calls"].size == 0 and str(got["trial"]) == "resmlp"
+    assert str(got["lazy"]) == "LazyEmbedding" and str(got["lazy_pts"]) == "LazyPoints" and got["calls"].size == 0 and str(got["trial"]) == "resmlp"
     # the same frames from direct package calls with the same seed and construction order
     H = W = 40
     focal = 555.5555155968841 * W / 400.

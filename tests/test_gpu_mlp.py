@@ -512,3 +512,42 @@ def test_r2l_cuda_graph_replay_equals_eager(E, O):
         with pytest.raises(ValueError):
             g3(poses[0])
 
+
+
+def test_r2l_ray_generation_fused_into_the_kernel(E, O):
+    """r2l_resmlp_render (rays from pixel index + pose inside the MLP kernel, no points tensor) against
+    r2l_point_sample + r2l_resmlp_forward, bit for bit: whole frames whose size is not a multiple of the 128-ray tile,
+    pose stacks, arbitrary row ranges, 4x4 poses, and the reference call pattern through the lazy handles."""
+    sd = O.r2l_state_dict(0)
+    net = load_r2l(E, O, sd, "fp16")
+    Hh, Ww = 37, 41
+    ps = E.PointSampler(Hh, Ww, 55., 16, 2., 6.)
+    poses = torch.stack([O.pose_spherical(th, -30., 4.)[:3, :4] for th in (-120., -10., 75.)], 0).cuda()
+    n = Hh * Ww
+    with torch.no_grad():
+        for p in poses:
+            want = net.forward_points(ps.sample_test(p))
+            assert torch.equal(net.render_poses(ps, p), want)
+            p44 = torch.cat([p, torch.tensor([[0., 0., 0., 1.]], device="cuda")], 0)
+            assert torch.equal(net.render_poses(ps, p44), want)
+        want3 = net.forward_points(ps.sample_test_batch(poses))
+        assert torch.equal(net.render_poses(ps, poses), want3)
+        for r0, r1 in ((0, 1), (1000, 1517), (n - 5, n + 300), (2 * n + 7, 3 * n), (5, 5)):
+            assert torch.equal(net.render_poses(ps, poses, rows=(r0, r1)), want3[r0:r1])
+        with pytest.raises(ValueError):
+            net.render_poses(ps, poses, rows=(0, 3 * n + 1))
+        with pytest.raises(ValueError):
+            net.render_poses(E.PointSampler(Hh, Ww, 55., 8, 2., 6.), poses)
+        # main.py:297-309 through the lazy sampler / embedder: one kernel, same bits; the handles still behave like tensors
+        lps = E.PointSampler(Hh, Ww, 55., 16, 2., 6., lazy=True)
+        emb = E.PositionalEmbedder(10, lazy=True)
+        lp = lps.sample_test(poses[1])
+        assert type(lp).__name__ == "LazyPoints" and tuple(lp.shape) == (n, 48)
+        k0 = E._lib.kernel_launches()
+        out = net(emb(lp))
+        assert E._lib.kernel_launches() - k0 == 1
+        assert torch.equal(out, net.forward_points(ps.sample_test(poses[1])))
+        assert torch.equal(torch.add(lp, 0.), ps.sample_test(poses[1])) and torch.equal(lp[5:9], ps.sample_test(poses[1])[5:9])
+        assert torch.equal(lp.view(n, 16, 3), ps.sample_test2(poses[1]))
+        assert torch.equal(E.PositionalEmbedder(10)(lps.sample_test(poses[1])), E.PositionalEmbedder(10)(ps.sample_test(poses[1])))
+        assert torch.equal(emb(lps.sample_test(poses[1])).materialize(), E.PositionalEmbedder(10)(ps.sample_test(poses[1])))

@@ -63,6 +63,13 @@ with torch.no_grad():
         pf[0].publish()
         torch.cuda.synchronize()
         assert torch.equal(pf[0].buf, want), "graphed fused gather != single-GPU frame"
+    # ray generation fused as well: one kernel per rank from pose to every GPU's frame buffer
+    pf[1].buf.fill_(-1.)
+    pf[1].publish()
+    net.render_poses(ps, c2, frame=pf[1])
+    pf[1].publish()
+    torch.cuda.synchronize()
+    assert torch.equal(pf[1].buf, want), "render_poses(frame=) != single-GPU frame"
     try:
         net.forward_points_gather(ps.sample_test(c2)[:128], pf[0])
         raise SystemExit("a wrong-sized block must be rejected")
