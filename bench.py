@@ -40,9 +40,9 @@ H = W = 400
 RAYS = H * W
 FLOP_PER_RAY = {"r2l": 11789824, "nerf": 303824896}   # BASELINE.md §2 (unpadded MACs x2)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1g_ncu_r2l_mlp.txt: one launch = 4 frames; profiles/r1g_ncu_nerf_mlp.txt: coarse + fine launch of one frame).  The MLP
-# kernels are tensor-bound: the traffic is the packed weights once (L2 resident afterwards) + points in, rgb / raw out.
-NCU_TRAFFIC_BYTES = {"r2l": 135548416 + 8448000, "nerf": (132556032 + 121996800) + (217386496 + 442190592)}
+# (profiles/r1h_ncu_r2l_mlp.txt: one launch = 4 frames, ray generation fused: the DRAM traffic is the 12.6 MB of packed weights,
+# the 7.7 MB of rgb are still in L2 when the kernel ends; profiles/r1g_ncu_nerf_mlp.txt: coarse + fine launch of one frame).
+NCU_TRAFFIC_BYTES = {"r2l": 12640000 + 0, "nerf": (132556032 + 121996800) + (217386496 + 442190592)}
 
 
 def dist_env():
@@ -480,7 +480,7 @@ def main():
                                 "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step; "
                                                f"burst {peaks['tf_burst']})",
                                 "kernel_ms": mlp_ms, "algorithmic_flop_per_launch": flops,
-                                "traffic": NCU_TRAFFIC_BYTES["r2l"] * P // 4, "traffic_unit": "B/launch (ncu, profiles/r1g: 4 poses per launch)"}
+                                "traffic": NCU_TRAFFIC_BYTES["r2l"] * P // 4, "traffic_unit": "B/launch (ncu, profiles/r1h: 4 poses per launch)"}
         else:
             ach = flops / (dev_ms / steps * 1e-3) / 1e12
             line["roofline"] = {"bound": "tensor", "kernel": "nerf_mlp_pp_kernel (coarse+fine, whole frame)",
