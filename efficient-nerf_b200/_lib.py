@@ -67,6 +67,8 @@ SIGNATURES = {
 }
 _RESTYPES = {"r2l_last_error": ctypes.c_char_p, "r2l_kernel_launches": ctypes.c_longlong}
 
+ABI_VERSION = 5   # r2l_abi_version() of the library this binding was written for (include/r2l_b200.h)
+
 _lock = threading.Lock()
 _lib = None
 launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it)
@@ -89,6 +91,10 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        lib.r2l_abi_version.restype = ctypes.c_int
+        if lib.r2l_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} has ABI version {lib.r2l_abi_version()}, this package needs {ABI_VERSION}: "
+                               "rebuild it with `python efficient-nerf_b200/build.py`")
         _lib = lib
     return _lib
 
