@@ -57,3 +57,10 @@ def test_no_cpu_fallback(E):
     with pytest.raises(RuntimeError, match="CUDA only"):
         with torch.no_grad():
             net(torch.zeros(2, 90))
+
+
+def test_graft_entry_build_passes_its_own_checks():
+    """The driver's 'does it build' entry: compiles (a no-op when the sources are unchanged), imports the package and
+    checks the ABI version against the binding's constant."""
+    import __graft_entry__
+    __graft_entry__.build()
