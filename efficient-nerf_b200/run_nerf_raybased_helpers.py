@@ -10,7 +10,6 @@ Outputs live on the CUDA device of the inputs.  Inputs given on the host (the re
 render_rays calls sample_pdf with `.cpu()` tensors, main.py:723-727) are uploaded, computed on
 the GPU and the result is returned on the host again, so call sites keep working unchanged.
 """
-import ctypes
 
 import numpy as np
 import torch

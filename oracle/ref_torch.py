@@ -15,7 +15,6 @@ oracle/sample_pdf_np.py additionally restates sample_pdf at the level of individ
 Parity pinning: the reference ships no tests or golden vectors, so the fixtures under
 tests/golden/ are outputs of the reference's own code run in the build container.
 """
-import math
 from types import SimpleNamespace
 
 import numpy as np
