@@ -241,6 +241,7 @@ def _smilelogging_stub():
     parser.add_argument("--note", type=str, default="")
     parser.add_argument("--experiments_dir", type=str, default="Experiments")
     pkg.argparser = parser
+    pkg.__dropin_stub__ = True
 
     class _Printer:
         def __call__(self, *msgs, **k):
@@ -467,6 +468,12 @@ def load_script(script, argv=(), fused=True, stubs=True, patch=True):
     for p in (os.getcwd(), root):
         if p not in sys.path:
             sys.path.insert(0, p)
+    # a second load in the same process must re-parse argv: option.py parses at import and registers its options on
+    # the (stub) smilelogging parser, which therefore has to be a fresh one
+    for name in ("option", stem):
+        sys.modules.pop(name, None)
+    if getattr(sys.modules.get("smilelogging"), "__dropin_stub__", False):
+        sys.modules.pop("smilelogging", None), sys.modules.pop("smilelogging.utils", None)
     install(fused=fused, stubs=stubs)
     sys.argv = [script] + list(argv)
     with open(script) as f:

@@ -141,3 +141,36 @@ def test_launcher_renders_what_direct_calls_render(tmp_path, E):
     assert np.array_equal(got["r2l"], r2l.cpu().numpy())
     assert np.array_equal(got["nerf"], rgb.cpu().numpy())
     assert got["frame8"].dtype == np.uint8 and got["frame8"].shape == (H, W, 3)
+
+
+PROBE_CD = r'''
+import json, sys
+sys.path.insert(0, {root!r})
+from efficient_nerf_b200 import dropin
+dropin.make_synthetic_blender({tmp!r} + "/scene", res=32)
+argv = ("--create_data rand --config {ref}/configs/lego.txt --n_pose_kd 100 --datadir {tmp}/scene "
+        "--experiments_dir {tmp}/Experiments --project cd").split()
+mod = dropin.load_script("{ref}/utils/create_data.py", argv)
+out = dict(patched=mod.__dropin_patched__, render_rays=mod.render_rays.__name__, nerf=mod.NeRF.__module__,
+           get_rays=mod.get_rays1.__module__, create_data=mod.args.create_data, n_pose_kd=mod.args.n_pose_kd)
+try:
+    dropin.load_script("{ref}/utils/create_data.py", argv + ["--focal_scale", "2"])
+    out["focal_scale"] = "accepted"
+except NotImplementedError as e:
+    out["focal_scale"] = "rejected"
+print("PROBE" + json.dumps(out, default=str))
+'''
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "utils", "create_data.py")), reason="the reference checkout is not present")
+def test_unmodified_create_data_binds_to_the_package(tmp_path):
+    code = PROBE_CD.format(root=ROOT, tmp=str(tmp_path), ref=REF)
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("PROBE")]
+    assert line, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(line[0][5:])
+    assert out["patched"] == ["batchify", "run_network", "batchify_rays", "render", "raw2outputs", "render_rays"]
+    assert out["render_rays"] == "render_rays_create_data"           # the flavour that also returns depth_map
+    assert out["nerf"].startswith("efficient_nerf_b200") and out["get_rays"].startswith("efficient_nerf_b200")
+    assert out["create_data"] == "rand" and int(out["n_pose_kd"]) == 100
+    assert out["focal_scale"] == "rejected"                          # options the fused render would silently drop
