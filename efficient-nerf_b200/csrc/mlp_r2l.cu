@@ -14,6 +14,11 @@
 //          residual add is free and exact fp32; b1/b2 ride along as the folded bias step.
 //   tail : rgb = sigmoid(W_t (x_43 + x0) + b_t)   (outer skip, use_residual) on CUDA cores in fp32:
 //          W_t x0 is accumulated at the head epilogue, W_t x_43 at the last epilogue.
+// Inputs of the head, one of three (R2lParams): the sampled points `pts` (PointSampler output), the caller's embedding
+// `embedded` (API path), or NOTHING but camera and pose (`cam`: r2l_resmlp_render) — then each row generates its ray
+// from pixel index and c2w with point_sample_kernel's arithmetic (rays.cu) and the frame is one kernel from pose to rgb.
+// Output: `rgb`, or — fused tile gather of a ray-sharded frame — the same rows of every GPU's frame buffer
+// (`rgb_peer`, peer-to-peer stores; the caller's cross-GPU barrier publishes them).
 // Weight stream per tile: per layer one 8 KiB bias stage + K/64 stages of 32 KiB (P = 16: 12.4 MB, L2 resident).
 #include "common.cuh"
 #include "mlp_params.cuh"
