@@ -163,9 +163,22 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
     written = []
     rng_global = np.random  # the reference's global stream
 
+    query_fn = None
+    if render_fn is None:
+        # a teacher that is not on the fused tensor-core path (other widths / depths, precision='fp32') is queried like
+        # the reference does (create_data.py:283-293): embed + batchified forward
+        from .render import _fused_ok, run_network
+        if not all(_fused_ok(n, True if use_viewdirs else None) for n in (teacher_fn, teacher_fine) if n is not None):
+            from .run_nerf_raybased_helpers import get_embedder
+            embed_fn, _ = get_embedder(10, 0)
+            embeddirs_fn = get_embedder(4, 0)[0] if use_viewdirs else None
+
+            def query_fn(inputs, viewdirs, network_fn):
+                return run_network(inputs, viewdirs, network_fn, embed_fn, embeddirs_fn, netchunk=1024 * 64)
+
     def render_pose(focal_, c2w):
         rays_o, rays_d = get_rays(H, W, focal_, c2w)  # [H, W, 3] on the device
-        kw = dict(network_fn=teacher_fn, network_fine=teacher_fine, network_query_fn=None, N_samples=N_samples,
+        kw = dict(network_fn=teacher_fn, network_fine=teacher_fine, network_query_fn=query_fn, N_samples=N_samples,
                   N_importance=N_importance, perturb=perturb, raw_noise_std=raw_noise_std, white_bkgd=white_bkgd,
                   use_viewdirs=use_viewdirs, lindisp=lindisp, ndc=False, near=near, far=far, return_depth=True)
         if fast_rng and perturb > 0.:
@@ -192,8 +205,8 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
                 if stream == "per_group":
                     if not mine:
                         continue
-                    if resume and os.path.exists(os.path.join(datadir, f"data_{first + F - 1}.npy")):
-                        continue   # this group's last file exists: already done
+                    if resume and os.path.exists(_group_marker(datadir, first, F)):
+                        continue   # the marker is written after ALL of the group's files are on disk
                     rng = np.random.RandomState(seed + g)
                 else:
                     rng = rng_global
@@ -256,6 +269,7 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
                     saver.submit(datadir, first, host[:F * split_size], split_size, n_parts=max(1, writer_threads),
                                  barrier=done)
                     done.wait()
+                    _mark_group_done(datadir, first, F)
                     host_free.put(b)
             except Exception as e:
                 fin_err.append(e)
@@ -329,7 +343,11 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
                 data = data[ix.to(data.device)]
                 host = data.cpu().numpy() if data.is_cuda else data.numpy()
                 assert host.dtype == np.float32 and host.shape[1] == C
-                saver.submit(datadir, first, host[:F * split_size], split_size, n_parts=max(1, writer_threads))
+                done = _AsyncNpySaver.Barrier(max(1, writer_threads))
+                saver.submit(datadir, first, host[:F * split_size], split_size, n_parts=max(1, writer_threads),
+                             barrier=done)
+                done.wait()
+                _mark_group_done(datadir, first, F)
             written.extend(range(first, first + F))
             n_done += 1
         if finisher is not None:
@@ -344,6 +362,19 @@ def create_data_rand(teacher_fn, teacher_fine, datadir, n_pose_kd, H, W, focal, 
             finisher.join()
         saver.close()
     return written
+
+
+def _group_marker(datadir, first, F):
+    """Completion marker of the group whose files are data_{first} .. data_{first+F-1}.  A group's files are written
+    by several threads over disjoint ranges, so 'the last file exists' does not mean 'the group is complete'; the
+    marker is created only after every writer of the group has finished.  (Not a .npy: the reference's own resume
+    counts the .npy files of the directory, create_data.py:790-796.)"""
+    return os.path.join(datadir, f".group_{first}_{first + F - 1}.done")
+
+
+def _mark_group_done(datadir, first, F):
+    with open(_group_marker(datadir, first, F), "w") as f:
+        f.write("ok\n")
 
 
 def _host_rays(H, W, focal, c2w):

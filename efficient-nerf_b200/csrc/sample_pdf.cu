@@ -7,7 +7,12 @@
 //   w      = weights + 1e-5f                      one fp32 add
 //   total  = sum(w) in ATen `vectorized_inner_sum` order: 8 vector lanes x 4 interleaved
 //            accumulators, folded 0+=1,2,3; scalar tail summed first, then the 8 lanes
-//            added left to right (rows shorter than 8: the same 4-accumulator scheme on scalars)
+//            added left to right (rows shorter than 8: the same 4-accumulator scheme on scalars).
+//            ASSUMPTION: this is ATen's AVX2 kernel (8 fp32 lanes).  torch 2.11 dispatches it for `sum` on AVX-512
+//            hosts as well (measured here and on the GPU boxes, SURVEY 8a-8: torch.backends.cpu.get_cpu_capability()
+//            says AVX512 but the fp32 row sums match the 8-lane order on 200 k rows); a build whose `sum` used 16
+//            lanes would round `total` differently, and the bit-exact claim would then hold against goldens made
+//            with ATEN_CPU_CAPABILITY=avx2 (tests/golden/sample_pdf.npz records the capability it was made with).
 //   pdf    = w / total                            correctly rounded fp32 divide
 //   cdf    = [0, cumsum(pdf)] accumulated in DOUBLE, each entry rounded to fp32.  All partial
 //            sums of these fp32 values are exact in double (values >= ~1e-7, sum <= ~1, < 53

@@ -188,10 +188,18 @@ class NeRF(nn.Module):
         return d
 
     def __setstate__(self, state):
-        # also reached when a module pickled by the REFERENCE class is loaded through compat's aliases
-        self.__dict__.update(state)
+        # also reached when a module pickled by the REFERENCE class is loaded through compat's aliases; the base
+        # method back-fills the hook dicts that torch-1.x pickles (the released checkpoints) do not carry
+        super(NeRF, self).__setstate__(state)
         self.__dict__.setdefault('precision', DEFAULT_PRECISION)
         self.__dict__['_packed'] = {}
+
+    def _replicate_for_data_parallel(self):
+        # nn.DataParallel shallow-copies __dict__: without this every replica would share (and evict, from concurrent
+        # threads) one dict of packed-weight handles keyed by ITS OWN parameter copies
+        replica = super()._replicate_for_data_parallel()
+        replica._packed = {}
+        return replica
 
     # -- tensor-core path -------------------------------------------------------------------
     def supports_tensor_core_path(self):
@@ -456,12 +464,20 @@ class NeRF_v3_2(nn.Module):
         return d
 
     def __setstate__(self, state):
-        # also reached when a module pickled by the REFERENCE class (main.py:1534-1536) is loaded through compat
-        self.__dict__.update(state)
+        # also reached when a module pickled by the REFERENCE class (main.py:1534-1536) is loaded through compat; the
+        # base method back-fills the hook dicts that torch-1.x pickles (the released R2L checkpoints) do not carry
+        super(NeRF_v3_2, self).__setstate__(state)
         self.__dict__.setdefault('precision', DEFAULT_PRECISION)
         self.__dict__['_packed'] = {}
         if 'input_dim' not in self.__dict__:
             self.__dict__['input_dim'] = self.head[0].in_features
+
+    def _replicate_for_data_parallel(self):
+        # nn.DataParallel shallow-copies __dict__: without this every replica would share (and evict, from concurrent
+        # threads) one dict of packed-weight handles keyed by ITS OWN parameter copies
+        replica = super()._replicate_for_data_parallel()
+        replica._packed = {}
+        return replica
 
     # -- tensor-core path -------------------------------------------------------------------
     def _tc_config(self):

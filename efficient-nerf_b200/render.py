@@ -76,7 +76,15 @@ def _points(rays_o, rays_d, z_vals):
     return pts
 
 
+def _unwrap(net):
+    """nn.DataParallel / main.py's MyDataParallel -> the wrapped module.  The reference wraps its models whenever it is
+    not --render_only (main.py:472-479) and create_data.py always does (:298-299); here one process drives one GPU,
+    so the wrapper's scatter / replicate / gather is bypassed and the fused kernels see the real module."""
+    return net.module if isinstance(net, torch.nn.DataParallel) else net
+
+
 def _fused_ok(net, viewdirs):
+    net = _unwrap(net)
     return (isinstance(net, NeRF) and viewdirs is not None and net.precision != "fp32"
             and net.supports_tensor_core_path())
 
@@ -114,6 +122,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         else:
             t_rand = torch.rand((N_rays, N_samples))  # CPU generator (main.py:691)
     z_vals = _z_vals(near, far, t_vals, lindisp, t_rand if perturb > 0. else None)
+
+    network_fn, network_fine = _unwrap(network_fn), _unwrap(network_fine)
 
     def query(z, net):
         if _fused_ok(net, viewdirs):

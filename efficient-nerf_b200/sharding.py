@@ -72,8 +72,14 @@ class PeerFrame:
     gather of ray-sharded frames: every rank's MLP kernel stores its rows [row0, row1) into ALL buffers by peer-to-peer
     stores over NVLink (NeRF_v3_2.forward_points_gather), `publish()` is the cross-GPU barrier after which `buf` holds
     the whole frame on every rank.  Replaces kernel + NCCL all_gather_into_tensor (gather_rays_into) by ONE kernel +
-    a ~7 us barrier.  A buffer may be rewritten by a peer as soon as that peer has passed the NEXT publish(): alternate
-    two PeerFrames (or consume the frame before the next publish) when frames are rendered back to back."""
+    a ~7 us barrier.
+
+    Reuse contract: a peer that has left THIS publish() may launch its next frame at once, and that kernel stores into
+    this rank's buffer — possibly while this rank is still reading the frame just published.  A single PeerFrame
+    rendered back to back is therefore a cross-GPU data race.  Either alternate TWO PeerFrames (frame k+1 goes to the
+    other buffer) and consume frame k, stream-ordered, before joining publish() k+1 — a peer can only reach the
+    kernel of frame k+2 (same buffer as k) after that barrier — or, with one PeerFrame, call `release()` (a second
+    barrier) once the frame has been consumed and before any rank renders into it again."""
 
     def __init__(self, n_rays, channels=3, multiple=128, group=None):
         import ctypes
@@ -95,6 +101,11 @@ class PeerFrame:
         """Cross-GPU barrier on the current stream: every rank's stores of this frame have landed everywhere."""
         self.hdl.barrier()
         return self.buf
+
+    def release(self):
+        """Second barrier for single-buffer use: every rank has finished reading the frame (reads enqueued on the
+        current stream before this call), so peers may overwrite it."""
+        self.hdl.barrier()
 
 
 def gather_frames(local_frames, n_poses, group=None):

@@ -69,3 +69,28 @@ def test_reference_checkpoint_renders_through_the_fused_kernels(E, golden):
     with torch.no_grad():
         out = nerf(t(g["nerf_x"]).cuda())
     assert float((out.cpu() - t(g["nerf_out"])).abs().max()) <= 2e-3
+
+
+_TORCH2_HOOK_ATTRS = ("_forward_hooks_with_kwargs", "_forward_hooks_always_called", "_forward_pre_hooks_with_kwargs",
+                      "_backward_pre_hooks", "_state_dict_pre_hooks", "_load_state_dict_post_hooks",
+                      "_load_state_dict_pre_hooks", "_non_persistent_buffers_set", "_is_full_backward_hook")
+
+
+def test_torch1_pickles_load(E, O):
+    """the released R2L / NeRF checkpoints were pickled by torch 1.x, whose modules lack the hook
+    dicts torch 2.x expects; nn.Module.__setstate__ back-fills them, so the overrides must call it.  Simulated by
+    stripping those attributes from every module's state before pickling."""
+    import copy
+    import pickle
+    for net in (E.NeRF_v3_2(O.r2l_args(netdepth=6), 252, 3), E.NeRF(8, 256, 63, 27, 5, [4], True)):
+        old = copy.deepcopy(net)
+        for m in old.modules():
+            for a in _TORCH2_HOOK_ATTRS:
+                m.__dict__.pop(a, None)
+        for a in ("precision", "_packed"):          # a module pickled by the reference class has neither
+            old.__dict__.pop(a, None)
+        new = pickle.loads(pickle.dumps(old))
+        assert new.precision in ("fp16", "bf16", "fp32") and new._packed == {}
+        new.load_state_dict(net.state_dict())       # AttributeError before the fix
+        assert all(torch.equal(v, net.state_dict()[k]) for k, v in new.state_dict().items())
+        new.register_forward_hook(lambda *a: None)

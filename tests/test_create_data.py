@@ -43,7 +43,7 @@ def test_wire_format_shuffle_and_reference_stream(E, tmp_path):
     CD, written = run(E, tmp_path / "a")
     F = CD.files_per_group(8, 8, 2, 32)                       # 2 poses * 64 rays / 32 = 4 files per group
     assert F == 4 and written == list(range(1, 9))
-    files = sorted(os.listdir(tmp_path / "a"), key=lambda x: int(x[5:-4]))
+    files = sorted((x for x in os.listdir(tmp_path / "a") if x.endswith(".npy")), key=lambda x: int(x[5:-4]))
     assert files == [f"data_{k}.npy" for k in range(1, 9)]
     arr = np.load(tmp_path / "a" / "data_1.npy")
     assert arr.dtype == np.float32 and arr.shape == (32, 9)
@@ -99,6 +99,17 @@ def test_rank_sharding_is_disjoint_complete_and_rank_count_independent(E, tmp_pa
     # resume in per_group mode: finished groups are skipped
     CD, again = run(E, tmp_path / "two", n_pose_kd=8, rank=0, world_size=2, seed=11)
     assert again == []
+    # a crash can leave a group's LAST file complete while earlier ranges are missing (parallel writers): only the
+    # completion marker, written after every writer has finished, makes a group "done" 
+    import glob
+    import os
+    marks = sorted(glob.glob(str(tmp_path / "two" / ".group_1_4.done")))
+    assert len(marks) == 1
+    os.remove(marks[0])
+    os.remove(str(tmp_path / "two" / "data_2.npy"))
+    CD, again = run(E, tmp_path / "two", n_pose_kd=8, rank=0, world_size=2, seed=11)
+    assert again == [1, 2, 3, 4]
+    assert np.array_equal(CD.load_shards(str(tmp_path / "one")), CD.load_shards(str(tmp_path / "two")))
     # the reference stream on two ranks: every rank replays the global np.random stream
     np.random.seed(5)
     CD, r_all = run(E, tmp_path / "ref1", n_pose_kd=8)
