@@ -30,11 +30,15 @@ import sys
 import threading
 import time
 
-import numpy as np
-import torch
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"] or "--impl=reference" in sys.argv:
+    # the reference arm times the reference's CPU path: its modules pick `device` at import (model/nerf_raybased.py:10,
+    # utils/run_nerf_raybased_helpers.py:13), so this process must not see a GPU (set before torch is imported)
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 H = W = 400
 RAYS = H * W
@@ -216,18 +220,35 @@ class NerfWorkload:
 
 # ------------------------------------------------------------------------------------ CPU arm
 def cpu_reference(workload, steps, warmup, sample_rays):
-    """The reference's algorithm (oracle port, torch CPU kernels = what the reference runs on CPU) on a bounded
-    sample of the same frame, all host threads.  The ONLY place bench.py imports oracle/ (the checker is timed as the
-    CPU baseline; the GPU arm never touches it)."""
+    """The reference's OWN code on a bounded sample of the same frame, all host threads: the unmodified
+    model/nerf_raybased.py, utils/run_nerf_raybased_helpers.py and main.py render functions from baseline/_ref
+    (staged by baseline/stage_reference.py, hashes pinned; kind = "reference").  Only if no staged tree exists does it
+    fall back to the oracle port (kind = "port": the same torch-CPU ops, pinned bit-exact to the reference).  The ONLY
+    place bench.py touches oracle/ (the checker's loader is used to time the CPU baseline; the GPU arm never does)."""
     from oracle import ref_torch as O
+    from oracle import ref_real as R
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     cam = O.LEGO
     c2w = O.pose_spherical(-180., -30., 4.)[:3, :4]
     idx = torch.linspace(0, RAYS - 1, sample_rays).long()
     times = []
+    root = R.reference_root(required=False)
+    kind = "reference" if root is not None else "port"
     with torch.no_grad():
-        if workload == "r2l":
+        if root is not None:
+            ref = R.load(root, device="cpu")
+            if workload == "r2l":
+                # main.py:297-309: model(positional_embedder(point_sampler.sample_test(c2w))), on the sampled rows
+                model, pe, ps = R.build_r2l(ref, 0, H, W, cam["focal"], 16, 2., 6.)
+                fn = lambda: model(pe(ps.sample_test(c2w)[idx]))
+            else:
+                # main.py:283-290: render(H, W, focal, chunk, rays=...) with create_nerf's render_kwargs_test
+                coarse, fine, kw = R.build_nerf(ref, 0)
+                ro, rd = ref.Hh.get_rays(H, W, cam["focal"], c2w)
+                rays = (ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx])
+                fn = lambda: ref.main["render"](H, W, cam["focal"], chunk=1024 * 32, rays=rays, **kw)[0]
+        elif workload == "r2l":
             sd = O.r2l_state_dict(0)
             fn = lambda: O.render_r2l(sd, H, W, cam["focal"], 2., 6., c2w, rows=idx)
         else:
@@ -242,10 +263,12 @@ def cpu_reference(workload, steps, warmup, sample_rays):
             if i >= warmup:
                 times.append(dt)
     mean = float(np.mean(times))
-    return dict(value=sample_rays / mean / 1e6, unit="Mrays/s", cores=cores, kind="port",
+    what = ("the unmodified reference from baseline/_ref: model/nerf_raybased.py + utils/run_nerf_raybased_helpers.py + "
+            "main.py render functions" if kind == "reference" else
+            "oracle/ref_torch.py = the reference's torch-CPU path (no staged reference tree found)")
+    return dict(value=sample_rays / mean / 1e6, unit="Mrays/s", cores=cores, kind=kind,
                 sample=f"{sample_rays} evenly spaced rays of one 400x400 frame per step, {len(times)} timed steps "
-                       f"(oracle/ref_torch.py = the reference's torch-CPU path); ms/frame extrapolated = "
-                       f"{mean / sample_rays * RAYS * 1e3:.0f}"), mean
+                       f"({what}); ms/frame extrapolated = {mean / sample_rays * RAYS * 1e3:.0f}"), mean
 
 
 def run_reference_arm(args):
