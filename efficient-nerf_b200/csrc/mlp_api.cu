@@ -149,6 +149,12 @@ struct Mlp {
   float* vb_ws = nullptr;          // workspace: per-ray view-branch bias [vb_cap rays][128]
   long long vb_cap = 0;
   NerfPpMaps* pp_maps = nullptr;   // tensor maps over wstream_pp
+  // far-sample sigma fix-up (nerf_far.cu): fp32 transposed point layers, the flagged-ray list and its counters
+  float* far_wt = nullptr;
+  int* far_ws = nullptr;           // [0] count of this forward, [1] count of the last finished forward, [2..] ray list
+  long long far_cap = 0;
+  int far_mode = 1;                // 0: off (raw sigma of the 16-bit kernels), 1: flag + fp32 fix-up
+  float far_abs = 1e-4f, far_rel = 9.765625e-4f;   // guard band: |sigma| < max(far_abs, far_rel * sum |w_a| relu(h7))
   R2lPairMaps* r2l_maps = nullptr; // R2L pair mode: tensor maps over wstream
   // R2L
   int n_points = 0, n_blocks = 0, sigmoid_out = 1, outer_skip = 1;
@@ -231,6 +237,8 @@ static void destroy(Mlp* m) {
   if (m->wstream_pp) cudaFree(m->wstream_pp);
   if (m->view_tab) cudaFree(m->view_tab);
   if (m->vb_ws) cudaFree(m->vb_ws);
+  if (m->far_wt) cudaFree(m->far_wt);
+  if (m->far_ws) cudaFree(m->far_ws);
   if (m->aux) cudaFree(m->aux);
   if (m->dbg_host) cudaFreeHost(m->dbg_host);
   delete m->pp_maps;
@@ -424,7 +432,7 @@ using namespace r2l;
 extern "C" {
 
 const char* r2l_last_error(void) { return g_last_error.c_str(); }
-int r2l_abi_version(void) { return 5; }
+int r2l_abi_version(void) { return 6; }
 
 // Number of CUDA kernels this library has launched so far in this process (all entry points, all streams).
 long long r2l_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
@@ -639,6 +647,10 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
     if (rc == R2L_OK) rc = encode_rows_map(&m->pp_maps->m4, m->wstream_pp, elems_pp * 2, 8);
     if (rc != R2L_OK) return cleanup(rc);
   }
+  if (cudaMalloc(reinterpret_cast<void**>(&m->far_wt), nerf_far_weight_bytes()) != cudaSuccess)
+    return cleanup(fail(R2L_ERR_CUDA, "r2l_nerf_create: cudaMalloc failed"));
+  rc = nerf_far_pack(pts_w, pts_b, alpha_w, m->far_wt, st);
+  if (rc != R2L_OK) return cleanup(rc);
   cudaError_t e = cudaMemcpyAsync(m->aux + kNerfAuxAlphaW, alpha_w, 256 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxRgbW, rgb_w, 384 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&m->alpha_b, alpha_b, 4, cudaMemcpyDeviceToHost, st);
@@ -656,7 +668,36 @@ static int check_dbg(Mlp* m, const char* who) {
   return R2L_OK;
 }
 
+static int nerf_run_mlp(Mlp* m, NerfParams& p, cudaStream_t st);
+
+// The MLP kernel, then (ray-sample calls with the fix-up enabled) the fp32 re-evaluation of the flagged far samples.
 static int nerf_run(Mlp* m, NerfParams& p, cudaStream_t st) {
+  const bool far = m->far_mode != 0 && p.embedded == nullptr && p.S > 0;
+  if (far) {
+    const long long n_rays = p.n_rows / p.S;
+    R2L_CHECK_ARG(n_rays < (1LL << 31), "r2l_nerf_forward: too many rays for one call");
+    if (n_rays > m->far_cap) {   // workspace grown on demand, like the view-bias workspace
+      R2L_CUDA(cudaStreamSynchronize(st));
+      if (m->far_ws) cudaFree(m->far_ws);
+      m->far_ws = nullptr;
+      m->far_cap = 0;
+      R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->far_ws), sizeof(int) * (2 + static_cast<size_t>(n_rays))));
+      R2L_CUDA(cudaMemsetAsync(m->far_ws, 0, 2 * sizeof(int), st));
+      m->far_cap = n_rays;
+    }
+    R2L_CUDA(cudaMemsetAsync(m->far_ws, 0, sizeof(int), st));
+    p.far_list = m->far_ws + 2;
+    p.far_count = m->far_ws;
+    p.far_cap = static_cast<int>(m->far_cap);
+    p.far_abs = m->far_abs;
+    p.far_rel = m->far_rel;
+  }
+  int rc = nerf_run_mlp(m, p, st);
+  if (rc != R2L_OK || !far) return rc;
+  return nerf_far_fixup_launch(m->far_wt, m->alpha_b, p.far_list, p.far_count, p.far_cap, m->far_ws + 1, p, st);
+}
+
+static int nerf_run_mlp(Mlp* m, NerfParams& p, cudaStream_t st) {
   p.wstream = m->wstream;
   p.alpha_w = m->aux + kNerfAuxAlphaW;
   p.rgb_w = m->aux + kNerfAuxRgbW;
@@ -743,6 +784,32 @@ int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long lo
     rc = nerf_run(m, p, static_cast<cudaStream_t>(stream));
     if (rc != R2L_OK) return rc;
   }
+  return R2L_OK;
+}
+
+// Far-sample sigma fix-up control (nerf_far.cu).  mode 0: off — raw holds the 16-bit kernels' own sigma everywhere;
+// mode 1 (default): r2l_nerf_forward flags the rays whose last sample has |sigma| < max(abs_band, rel_band * sum |w_a|
+// relu(h7)) and re-evaluates those points in fp32.  abs_band / rel_band < 0 keep the current values.
+int r2l_nerf_far_fixup(void* handle, int mode, double abs_band, double rel_band) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_far_fixup: not a NeRF handle");
+  R2L_CHECK_ARG(mode == 0 || mode == 1, "r2l_nerf_far_fixup: mode must be 0 or 1");
+  m->far_mode = mode;
+  if (abs_band >= 0.0) m->far_abs = static_cast<float>(abs_band);
+  if (rel_band >= 0.0) m->far_rel = static_cast<float>(rel_band);
+  return R2L_OK;
+}
+
+// Number of rays the last r2l_nerf_forward on `stream` flagged (synchronises the stream): diagnostics / tests.
+int r2l_nerf_far_count(void* handle, long long* out_count, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 0 && out_count != nullptr, "r2l_nerf_far_count: bad arguments");
+  *out_count = 0;
+  if (m->far_ws == nullptr) return R2L_OK;
+  int v = 0;
+  R2L_CUDA(cudaMemcpyAsync(&v, m->far_ws + 1, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  R2L_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  *out_count = v;
   return R2L_OK;
 }
 

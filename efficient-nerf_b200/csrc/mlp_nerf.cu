@@ -37,7 +37,8 @@ constexpr int kNerfOffBiasRing = kNerfOffRing + kNerfRing * kStageBytes;
 constexpr int kNerfOffAlphaW = kNerfOffBiasRing + kNerfBiasRing * kBiasStageBytes;   // 256 floats
 constexpr int kNerfOffRgbW = kNerfOffAlphaW + 256 * 4;                // 3*128 floats
 constexpr int kNerfOffPart = kNerfOffRgbW + 384 * 4;                  // 128 x float4
-constexpr int kNerfOffBars = kNerfOffPart + 128 * 16;
+constexpr int kNerfOffAbs = kNerfOffPart + 128 * 16;                  // 128 floats
+constexpr int kNerfOffBars = kNerfOffAbs + 128 * 4;
 constexpr int kNerfNumBars = 2 * kNerfRing + 2 * kNerfBiasRing + 4 + 2 + 2 + 2 + 1;
 constexpr int kNerfOffTmem = kNerfOffBars + kNerfNumBars * 8;
 constexpr int kNerfSmemBytes = kNerfOffTmem + 16;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
   float* const sAlphaW = reinterpret_cast<float*>(smem + kNerfOffAlphaW);
   float* const sRgbW = reinterpret_cast<float*>(smem + kNerfOffRgbW);
   float4* const sPart = reinterpret_cast<float4*>(smem + kNerfOffPart);
+  float* const sAbs = reinterpret_cast<float*>(smem + kNerfOffAbs);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kNerfOffBars);
   uint64_t* const w_full = bars;
   uint64_t* const w_empty = bars + kNerfRing;
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
       const long long g_row = static_cast<long long>(tile) * kTileM + row;
       const bool valid = g_row < p.n_rows;
       float sigma_part = 0.0f;
+      float abs_part = 0.0f;   // sum |w_a| relu(h7): scale of the far-sample guard band (nerf_far.cu)
       for (int step = 0; step <= 8; ++step) {
         const int db = step & 1;
         wait_d(db, 300 + step);
@@ -373,8 +376,11 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
               [&](uint32_t col0, uint32_t (&v)[32]) {
                 store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  sigma_part = fmaf(sAlphaW[col0 + i], fmaxf(__uint_as_float(v[i]), 0.0f), sigma_part);
+                for (int i = 0; i < 32; ++i) {
+                  const float w = sAlphaW[col0 + i], h = fmaxf(__uint_as_float(v[i]), 0.0f);
+                  sigma_part = fmaf(w, h, sigma_part);
+                  abs_part = fmaf(fabsf(w), h, abs_part);
+                }
               },
               signal);
         } else if (step == 8) {
@@ -417,11 +423,13 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
       }
       if (wg == 1) {
         sPart[row] = make_float4(r, gch, b, sigma_part);
+        sAbs[row] = abs_part;
         named_bar_arrive(1, 256);
         named_bar_sync(2, 256);   // WG0 has consumed sPart
       } else {
         named_bar_sync(1, 256);
         const float4 o1 = sPart[row];
+        const float a1 = sAbs[row];
         named_bar_arrive(2, 256);
         if (valid) {
           float4 o;
@@ -430,6 +438,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
           o.z = b + o1.z + p.rgb_b[2];
           o.w = sigma_part + o1.w + p.alpha_b;
           reinterpret_cast<float4*>(p.raw)[g_row] = o;
+          nerf_far_flag(p, g_row, g_row / p.S, o.w, abs_part + a1);
         }
       }
     }

@@ -77,7 +77,8 @@ constexpr int kPpOffBiasRing = kPpOffRing + kPpRing * kPpStageB;
 constexpr int kPpOffAlphaW = kPpOffBiasRing + kPpBiasRing * kPpBiasB;   // 256 floats
 constexpr int kPpOffRgbW = kPpOffAlphaW + 256 * 4;                    // 3*128 floats
 constexpr int kPpOffPart = kPpOffRgbW + 384 * 4;                      // 128 x float4
-constexpr int kPpOffBars = kPpOffPart + 128 * 16;
+constexpr int kPpOffAbs = kPpOffPart + 128 * 16;                      // 128 floats: WG1's half of sum |w_a| relu(h7)
+constexpr int kPpOffBars = kPpOffAbs + 128 * 4;
 constexpr int kPpNumBars = 2 * kPpRing + 2 * kPpBiasRing + 2 + 2 + 2 + 2 + 2;
 constexpr int kPpOffTmem = kPpOffBars + kPpNumBars * 8;
 constexpr int kPpSmemBytes = kPpOffTmem + 16;
@@ -98,6 +99,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
   float* const sAlphaW = reinterpret_cast<float*>(smem + kPpOffAlphaW);
   float* const sRgbW = reinterpret_cast<float*>(smem + kPpOffRgbW);
   float4* const sPart = reinterpret_cast<float4*>(smem + kPpOffPart);
+  float* const sAbs = reinterpret_cast<float*>(smem + kPpOffAbs);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kPpOffBars);
   uint64_t* const w_full = bars;                    // leader: own producer + the peer's relay
   uint64_t* const w_empty = w_full + kPpRing;       // both issuers have committed the stage (2 arrivals, both CTAs)
@@ -451,6 +453,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
     };
     for (int unit = unit0; unit < n_units; unit += unit_step, ++eit) {
       float sigma_part[2] = {0.0f, 0.0f};
+      float abs_part[2] = {0.0f, 0.0f};   // sum |w_a| relu(h7): scale of the far-sample guard band (nerf_far.cu)
       for (int step = 0; step < 10; ++step) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -459,13 +462,18 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
           if (threadIdx.x == 0) trace(eit, 300000 + t * 10000 + step * 100);   // epilogue of (t, step) starts
           if (step < 9) {
             if (step == 7) {
-              float sp = 0.0f;
+              float sp = 0.0f, sa = 0.0f;
               for_pieces(t, [&](uint32_t col0, uint32_t (&v)[32]) {
                 store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) sp = fmaf(sAlphaW[col0 + i], fmaxf(__uint_as_float(v[i]), 0.0f), sp);
+                for (int i = 0; i < 32; ++i) {
+                  const float w = sAlphaW[col0 + i], h = fmaxf(__uint_as_float(v[i]), 0.0f);
+                  sp = fmaf(w, h, sp);
+                  sa = fmaf(fabsf(w), h, sa);
+                }
               });
               sigma_part[t] = sp;
+              abs_part[t] = sa;
             } else if (step == 8) {
               for_pieces(t, [&](uint32_t col0, uint32_t (&v)[32]) {
                 store_sub<BF16, false>(v, a_row + (col0 >> 5) * kSubBytes);
@@ -520,11 +528,13 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
             }
             if (wg == 1) {
               sPart[row] = make_float4(r, gch, b, sigma_part[t]);
+              sAbs[row] = abs_part[t];
               named_bar_arrive(1, 256);
               named_bar_sync(2, 256);   // WG0 has consumed sPart
             } else {
               named_bar_sync(1, 256);
               const float4 o1 = sPart[row];
+              const float a1 = sAbs[row];
               named_bar_arrive(2, 256);
               if (valid) {
                 float4 o;
@@ -533,6 +543,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
                 o.z = b + o1.z + p.rgb_b[2];
                 o.w = sigma_part[t] + o1.w + p.alpha_b;
                 reinterpret_cast<float4*>(p.raw)[g_row] = o;
+                nerf_far_flag(p, g_row, ray, o.w, abs_part[t] + a1);
               }
             }
           }

@@ -29,7 +29,28 @@ struct NerfParams {
   long long* prof;          // optional [gridDim.x][8] cycle counters (see r2l_nerf_profile)
   int prof_mode;            // ping-pong kernel: 1 = report ring turnaround instead of the wait split
   const float* vb;          // ping-pong kernel only: per-ray view-branch bias [n_rays][128] (nerf_view_bias_kernel)
+  // far-sample guard band (nerf_far.cu): rays whose LAST sample has |sigma| < max(far_abs, far_rel * sum|w_a| relu(h7))
+  // are appended to far_list (atomicAdd on far_count; entries beyond far_cap are dropped, the count keeps growing)
+  int* far_list;            // nullptr: no flagging
+  int* far_count;
+  int far_cap;
+  float far_abs, far_rel;
 };
+
+// far-sample sigma fix-up (nerf_far.cu)
+size_t nerf_far_weight_bytes();
+int nerf_far_pack(const float* const* pts_w, const float* const* pts_b, const float* alpha_w, float* Wt, cudaStream_t st);
+int nerf_far_fixup_launch(const float* Wt, float alpha_b, const int* list, const int* count, int cap, int* stats,
+                          const NerfParams& p, cudaStream_t st);
+
+// The epilogue's test: is row g_row the far sample of its ray, and is its sigma inside the guard band?
+__device__ __forceinline__ void nerf_far_flag(const NerfParams& p, long long g_row, long long ray, float sigma,
+                                              float abs_sum) {
+  if (p.far_list != nullptr && g_row - ray * p.S == p.S - 1 && fabsf(sigma) < fmaxf(p.far_abs, p.far_rel * abs_sum)) {
+    const int idx = atomicAdd(p.far_count, 1);
+    if (idx < p.far_cap) p.far_list[idx] = static_cast<int>(ray);
+  }
+}
 
 // Tensor maps over the ping-pong kernel's stage stream seen as rows of 256 x 16-bit (512 bytes): boxes of 32 / 16 / 8
 // rows = one CTA's half of a K=64 stage (N 256), of a K=64 stage (N 128), of a bias stage

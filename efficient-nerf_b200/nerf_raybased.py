@@ -230,7 +230,31 @@ class NeRF(nn.Module):
                       _lib.ptr_array(pb), *[_lib.ptr(t) for t in others], _lib.stream_ptr(dev))
         h = _Handle(out)
         self._packed[precision] = (key, h)
+        self._apply_far(h)
         return h
+
+    # -- far-sample sigma fix-up (csrc/nerf_far.cu) ------------------------------------------
+    def set_far_fixup(self, enabled=True, abs_band=None, rel_band=None):
+        """raw2outputs gives a ray's LAST sample a 1e10 interval (main.py:579-581), so its alpha is a step function of
+        sign(sigma).  With the fix-up on (default) forward_samples re-evaluates, in fp32, the far samples whose 16-bit
+        sigma lies inside the guard band |sigma| < max(abs_band, rel_band * sum |w_a| relu(h7)) — bit-identical to the
+        precision='fp32' path there.  `enabled=False` returns the tensor-core kernels' own sigma everywhere."""
+        self.__dict__['_far'] = (bool(enabled), abs_band, rel_band)
+        for _, h in self._packed.values():
+            self._apply_far(h)
+
+    def _apply_far(self, h):
+        en, a, r = self.__dict__.get('_far', (True, None, None))
+        _lib.call("r2l_nerf_far_fixup", h.h, 1 if en else 0, -1.0 if a is None else float(a), -1.0 if r is None else float(r))
+
+    def far_flagged(self):
+        """Rays the last forward_samples flagged for the fp32 far-sample fix-up (synchronises the stream)."""
+        n = ctypes.c_longlong(0)
+        h = self.packed_handle()
+        dev = self.alpha_linear.weight.device
+        with torch.cuda.device(dev):
+            _lib.call("r2l_nerf_far_count", h.h, ctypes.byref(n), _lib.stream_ptr(dev))
+        return int(n.value)
 
     def forward_samples(self, rays_o, rays_d, viewdirs, z_vals):
         """Fused encode + MLP: raw [N, S, 4] for points o + d*z (main.py:65-87 + model:377-401)."""

@@ -144,6 +144,15 @@ int r2l_nerf_forward(void* handle, long long n_rays, int S, const float* rays_o,
                      const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
                      const float* z_vals, float* raw, void* stream);
 
+/* Far-sample sigma fix-up (main.py:578-581, 598: the last sample's 1e10 interval makes its alpha a step function of
+ * sign(sigma)).  mode 1 (default): r2l_nerf_forward flags the rays whose last sample has
+ * |sigma| < max(abs_band, rel_band * sum_i |alpha_w_i| relu(h7_i)) and re-evaluates those points in fp32 (bit-identical
+ * to the precision="fp32" path) before returning raw; mode 0: off.  Negative bands keep the current values
+ * (defaults 1e-4, 2^-10). */
+int r2l_nerf_far_fixup(void* handle, int mode, double abs_band, double rel_band);
+/* Rays flagged by the last r2l_nerf_forward enqueued on `stream` (synchronises it). */
+int r2l_nerf_far_count(void* handle, long long* out_count, void* stream);
+
 /* NeRF.forward(x [M, >=90]) -> [M,4]   (model/nerf_raybased.py:377-401). */
 int r2l_nerf_forward_embedded(void* handle, long long M, const float* x, long long ldx, float* out, void* stream);
 

@@ -105,14 +105,16 @@ def test_precision_argument_validation(E):
 
 
 def test_bench_reference_arm_prints_contract_line():
-    """bench.py --impl reference runs the oracle port on the host cores and prints one JSON line."""
+    """bench.py --impl reference runs the reference's own files (baseline/_ref, staged by baseline/stage_reference.py;
+    the oracle port only when no staged tree exists) on the host cores and prints one JSON line."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                         "--warmup", "0", "--workload", "r2l"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "Mrays/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "main.py")) or os.path.exists("/root/reference/main.py")
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0
 
 
