@@ -167,6 +167,6 @@ def test_synthetic_workloads_equal_the_oracle_seeds(E, O):
 def test_bench_gpu_arm_does_not_import_the_oracle():
     """Only the CPU legs of bench.py (cpu_baseline / --impl reference) may execute oracle/."""
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
-    assert src.count("from oracle") == 1
     body = src.split("def cpu_reference", 1)[1].split("\ndef ", 1)[0]
-    assert "from oracle import ref_torch" in body
+    assert "from oracle import ref_torch" in body and "from oracle import ref_real" in body
+    assert src.count("from oracle") == body.count("from oracle") == 2      # nowhere else
