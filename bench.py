@@ -8,13 +8,16 @@ Workload (config.workload):
        synthetic test poses; one STEP = one launch of the fused kernel (PointSampler ray generation +
        PositionalEmbedder + 88-layer ResMLP) over the step's poses.
   nerf (BASELINE configs[0]): NeRF lego W256 D8, 64 coarse + 128 fine samples, one STEP = one 400x400 frame
-       through get_rays -> fused encode+MLP (coarse) -> raw2outputs -> sample_pdf -> merge -> fused
-       encode+MLP (fine) -> raw2outputs.
+       through get_rays -> fused encode+MLP (coarse) -> raw2outputs -> hier_sample -> fused encode+MLP (fine) ->
+       raw2outputs.  At N = 1 the default run reports it as a full record of its own under `extras.nerf`
+       (roofline with event-timed MLP launches, e2e with declared copies, cpu_baseline, parity census).
 Random-init weights (torch.manual_seed(0), the reference's construction order), synthetic poses
 pose_spherical(theta_k, -30, 4): data = "synthetic".
 
 Multi-GPU: one process per GPU (torchrun), poses sharded round-robin, NO data-path collective (weak
-scaling: every rank renders K poses); time = max over ranks; value = all rays / that time.
+scaling: every rank renders K poses); time = max over ranks; value = all rays / that time.  For N > 1 a short
+second phase renders single frames RAY-sharded over the ranks (strong scaling: the gather of the rgb tiles is the
+one collective of the path; R2L fuses it into the MLP kernel over peer memory) and reports `extras.ray_sharded`.
 
 Timing: W >= 3 warm-up steps, then K steps; every step is bracketed by CUDA events on the launching
 stream (torch's current stream, which is the stream the C ABI launches on); an L2 flush (256 MiB
@@ -43,10 +46,16 @@ import torch  # noqa: E402
 H = W = 400
 RAYS = H * W
 FLOP_PER_RAY = {"r2l": 11789824, "nerf": 303824896}   # BASELINE.md §2 (unpadded MACs x2)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1h_ncu_r2l_mlp.txt: one launch = 4 frames, ray generation fused: the DRAM traffic is the 12.6 MB of packed weights,
-# the 7.7 MB of rgb are still in L2 when the kernel ends; profiles/r1g_ncu_nerf_mlp.txt: coarse + fine launch of one frame).
-NCU_TRAFFIC_BYTES = {"r2l": 12640000 + 0, "nerf": (132556032 + 121996800) + (217386496 + 442190592)}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed `ncu --set
+    full` captures (profiles/traffic.json names the capture each figure was read from)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def dist_env():
@@ -67,20 +76,23 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the GPU is under load.  Reported: the samples of
+    the timed region plus the last 0.5 s of the (identical) warm-up loop before it — a 20-step timed region lasts
+    ~0.13 s, less than nvidia-smi's own latency."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
-        self.n0 = 0
+        self.t_mark = None
+        self.t_end = None
 
     def start(self):
         """Start sampling (before the warm-up: nvidia-smi needs ~0.5 s to deliver its first line)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -91,36 +103,50 @@ class ClockSampler:
             self.proc = None
 
     def mark(self):
-        """The timed region starts now: only samples taken from here on are reported."""
-        self.n0 = len(self.lines)
+        """The timed region starts now."""
+        self.t_mark = time.time()
+
+    def end(self):
+        """The timed region has ended (samples that arrive within 0.15 s still describe it)."""
+        self.t_end = time.time()
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        if self.t_end is not None:
+            time.sleep(max(0.0, self.t_end + 0.15 - time.time()))
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines[self.n0:]:
+        lo = (self.t_mark or 0.0) - 0.5
+        hi = (self.t_end or time.time()) + 0.15
+        n_timed = 0
+        for ts, ln in self.lines:
+            if ts < lo or ts > hi:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])), mx.append(float(f[1]))
+                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
             except ValueError:
                 continue
+            n_timed += ts >= (self.t_mark or 0.0)
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_in_timed_region": int(n_timed),
+                "window": "timed region + the last 0.5 s of the identical warm-up loop, 50 ms period"}
 
 
 # ------------------------------------------------------------------------------------ workloads
@@ -158,7 +184,7 @@ class R2LWorkload:
             self.graph = self.E.GraphedR2L(self.net, self.ps, self.P, rows=self.block)
 
     def step(self, c2w_dev, mlp_events=None, k=0):
-        # c2w_dev: [P, 3, 4] — P consecutive test poses rendered by ONE sampler launch + ONE fused-MLP launch
+        # c2w_dev: [P, 3, 4] — P consecutive test poses rendered by ONE fused launch
         if self.graph is not None:
             if mlp_events is not None:      # no events inside a graph: the bracket is the whole replay
                 mlp_events[0].record()
@@ -176,6 +202,9 @@ class R2LWorkload:
             mlp_events[1].record()
         return rgb
 
+    def mlp_ms(self, mev, steps):
+        return sum(a.elapsed_time(b) for a, b in mev) / steps
+
     def describe(self):
         return {"workload": "R2L lego_noview resmlp W256 D88, n_sample_per_ray=16, 400x400 synthetic poses "
                             f"(BASELINE configs[1]); step = one launch of {self.P} consecutive test pose(s) = "
@@ -187,18 +216,21 @@ class R2LWorkload:
 
 class NerfWorkload:
     name = "nerf"
-    kernels_per_step = 13
+    kernels_per_step = 15
 
     def __init__(self, E, precision, poses_per_launch=1):
         self.P, self.rays_per_step = 1, RAYS
         self.block = None
         self.frames = None
+        self.graph = None
         self.coarse, self.fine = E.synthetic.seeded_nerf_pair(0, precision)
         self.coarse.packed_handle(), self.fine.packed_handle()
         self.E, self.focal = E, E.synthetic.LEGO["focal"]
         self.kw = dict(network_query_fn=None, perturb=0., N_importance=128, network_fine=self.fine, N_samples=64,
                        network_fn=self.coarse, use_viewdirs=True, white_bkgd=True, raw_noise_std=0., ndc=False,
                        near=2., far=6.)
+        self.mlp_events = []
+        self.coarse._mlp_events = self.fine._mlp_events = self.mlp_events   # events around the MLP launches
 
     def step(self, c2w_dev, mlp_events=None, k=0):
         if c2w_dev.dim() == 3:
@@ -212,10 +244,18 @@ class NerfWorkload:
         rgb, disp, acc, _ = self.E.render_image(H, W, self.focal, chunk=32768, c2w=c2w_dev, **self.kw)
         return rgb.reshape(-1, 3)
 
+    def mlp_ms(self, mev, steps):
+        """CUDA-event time of the MLP launches (coarse + fine: view bias, fused MLP, far-sample fix-up) per step, over
+        the LAST `steps` steps recorded."""
+        evs = self.mlp_events[-2 * steps:]
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        del self.mlp_events[:]
+        return ms
+
     def describe(self):
         return {"workload": "NeRF lego W256 D8, 64 coarse + 128 fine samples, 400x400 synthetic poses "
                             "(BASELINE configs[0]); step = 1 frame = 160000 rays",
-                "rays_per_step": RAYS, "operands": self.coarse.precision, "accumulate": "fp32"}
+                "rays_per_step": RAYS, "operands": self.coarse.precision, "accumulate": "fp32", "cuda_graph": False}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -275,7 +315,7 @@ def run_reference_arm(args):
     rank, local, world = dist_env()
     if rank != 0:
         return 0
-    sample = 8192 if args.workload == "r2l" else 512
+    sample = 65536 if args.workload == "r2l" else 4096
     steps = max(1, min(args.steps, 3))
     warmup = min(args.warmup, 1)
     cb, mean = cpu_reference(args.workload, steps, warmup, sample)
@@ -299,6 +339,102 @@ WORKLOAD_DESC = {
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def roofline_block(workload, rays_per_launch, kernel_ms, peaks, P=1):
+    flops = FLOP_PER_RAY[workload] * rays_per_launch
+    ach = flops / (kernel_ms * 1e-3) / 1e12
+    tr = ncu_traffic().get(workload, {})
+    traffic = tr.get("bytes_per_frame")
+    if workload == "r2l" and "bytes_weights" in tr:
+        # the weights are read once per launch, the rgb rows scale with the poses of the launch
+        traffic = tr.get("bytes_weights", 0) + tr.get("bytes_per_pose", 0) * P
+    return {"bound": "tensor",
+            "kernel": "r2l_mlp_kernel" if workload == "r2l" else
+                      "nerf_mlp_pp_kernel, coarse + fine launch of one frame (+ view bias and far-sample fix-up)",
+            "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
+            "frac_of_burst": ach / peaks["tf_burst"],
+            "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step; burst "
+                           f"{peaks['tf_burst']})",
+            "kernel_ms": kernel_ms, "algorithmic_flop_per_launch": flops, "traffic": traffic,
+            "traffic_unit": f"B per step (dram__bytes_read.sum + dram__bytes_write.sum, {tr.get('source', 'no capture')})"}
+
+
+def timed_run(wl, poses_dev, warmup, steps, run_step, flush, barrier, sampler=None, on_start=None):
+    """Device-resident timing: W warm-up steps (+ 0.6 s more of the identical loop), then K event-bracketed steps with
+    an L2 flush before each; returns (per-step ms, MLP events, extra warm-up steps, wall seconds)."""
+    def timed_pass(pose_list, with_mlp_events):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in pose_list]
+        mevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in pose_list]
+        for k, pose in enumerate(pose_list):
+            flush.zero_()                              # L2 flush, outside the event bracket
+            evs[k][0].record()
+            run_step(pose, mevs[k] if with_mlp_events else None, k)
+            evs[k][1].record()
+        return evs, mevs
+
+    # Warm-up = the SAME loop (same allocation pattern, same kernels, host running ahead): W steps, then more until
+    # 0.6 s have passed.  Two start-up transients otherwise land in the K timed steps: the power-cap controller
+    # throttles hard ~0.3 s after a cold GPU starts a tensor-heavy kernel (one 60-70 ms NeRF step among 42 ms
+    # ones), and the first pass through the un-synchronised loop contains one step with a ~90 ms host-side stall.
+    timed_pass(poses_dev[:warmup], True)
+    torch.cuda.synchronize()
+    t_warm = time.perf_counter()
+    extra_warm = 0
+    while time.perf_counter() - t_warm < 0.6 and extra_warm < 400:
+        n_more = max(warmup, 4)
+        timed_pass([poses_dev[k % warmup] for k in range(n_more)], True)
+        torch.cuda.synchronize()
+        extra_warm += n_more
+    barrier()
+    if on_start is not None:
+        on_start()
+    if sampler is not None:
+        sampler.mark()
+    t_wall0 = time.perf_counter()
+    ev, mev = timed_pass(poses_dev[warmup:warmup + steps], True)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    if sampler is not None:
+        sampler.end()
+    return [a.elapsed_time(b) for a, b in ev], mev, extra_warm, t_wall
+
+
+def e2e_run(wl, poses, warmup, steps, run_step, barrier, rank, by_rays=False, fused=False):
+    """End to end through the public API with HOST buffers: every step copies its pose(s) from pinned host memory
+    (H2D) and its finished frame(s) back to pinned host memory (D2H, on a second stream, double-buffered, so the copy
+    of step i overlaps the kernels of step i+1 — what a caller streaming frames does).  Returns total ms."""
+    P = wl.P
+    pose_host = [p.pin_memory() for p in poses]
+    frame_host2 = [torch.empty((wl.rays_per_step if not by_rays else RAYS, 3), dtype=torch.float32).pin_memory()
+                   for _ in range(2)]
+    c2w_buf = torch.empty((P, 3, 4), dtype=torch.float32, device="cuda")
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    copied = [None, None]
+    for i in range(steps):
+        c2w_buf.copy_(pose_host[warmup + i], non_blocking=True)          # H2D of this step's input
+        # fused gather: peers overwrite symmetric buffer (i + 1) & 1 once they pass publish(i); the read-back of
+        # the frame it still holds (step i - 1) must be over before this rank joins that barrier
+        wait_prev = (lambda: main_stream.wait_event(copied[(i + 1) & 1])) if fused and copied[(i + 1) & 1] else None
+        out = run_step(c2w_buf, None, i, wait_prev)
+        if not by_rays or rank == 0:
+            done = torch.cuda.Event()
+            done.record(main_stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                frame_host2[i & 1].copy_(out, non_blocking=True)          # D2H of this step's result
+                if not fused:      # (symmetric-memory buffers are not the caching allocator's)
+                    out.record_stream(copy_stream)
+                copied[i & 1] = torch.cuda.Event()
+                copied[i & 1].record(copy_stream)
+    main_stream.wait_stream(copy_stream)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,90 +514,31 @@ def main():
         return out
     peaks = measured_peaks()
 
-    # ---------------- device-resident timing
     with torch.no_grad():
         sampler = ClockSampler(local)
         if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
             sampler.start()
-        def timed_pass(pose_list, with_mlp_events):
-            """The timed loop: L2 flush, then one event-bracketed step, for every pose of the list; the host does not
-            synchronise inside (it runs ahead of the device, as a caller streaming frames would)."""
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in pose_list]
-            mevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in pose_list]
-            for k, pose in enumerate(pose_list):
-                flush.zero_()                              # L2 flush, outside the event bracket
-                evs[k][0].record()
-                run_step(pose, mevs[k] if with_mlp_events else None, k)
-                evs[k][1].record()
-            return evs, mevs
+        counts = {}
 
-        # Warm-up = the SAME loop (same allocation pattern, same kernels, host running ahead): W steps, then more until
-        # 0.6 s have passed.  Two start-up transients otherwise land in the K timed steps: the power-cap controller
-        # throttles hard ~0.3 s after a cold GPU starts a tensor-heavy kernel (one 60-70 ms NeRF step among 42 ms
-        # ones), and the first pass through the un-synchronised loop contains one step with a ~90 ms host-side stall.
-        timed_pass(poses_dev[:warmup], True)
-        torch.cuda.synchronize()
-        t_warm = time.perf_counter()
-        extra_warm = 0
-        while time.perf_counter() - t_warm < 0.6 and extra_warm < 400:
-            n_more = max(warmup, 4)
-            timed_pass([poses_dev[k % warmup] for k in range(n_more)], True)
-            torch.cuda.synchronize()
-            extra_warm += n_more
-        barrier()
-        launches0 = E._lib.launch_count
-        kernels0 = E._lib.kernel_launches()
-        barrier()
-        sampler.mark()
-        t_wall0 = time.perf_counter()
-        ev, mev = timed_pass(poses_dev[warmup:warmup + steps], True)
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-        launches = E._lib.launch_count - launches0
-        kernels = E._lib.kernel_launches() - kernels0
+        def on_start():      # the library's launch counters are read around the timed pass only
+            counts["abi"], counts["kernels"] = E._lib.launch_count, E._lib.kernel_launches()
+
+        # ---------------- device-resident timing
+        step_ms, mev, extra_warm, t_wall = timed_run(wl, poses_dev, warmup, steps, run_step, flush, barrier, sampler,
+                                                     on_start)
+        launches = E._lib.launch_count - counts["abi"]
+        kernels = E._lib.kernel_launches() - counts["kernels"]
         if getattr(wl, "graph", None) is not None:     # replays do not pass through the library's launch counter
             kernels += wl.graph.kernels_per_replay * steps
         clocks = sampler.stop() if rank == 0 else None
-        step_ms = [a.elapsed_time(b) for a, b in ev]
         dev_ms = sum(step_ms)
         if os.environ.get("BENCH_VERBOSE"):
             print("per-step ms:", " ".join(f"{x:.2f}" for x in step_ms[:40]), file=sys.stderr)
-        mlp_ms = sum(a.elapsed_time(b) for a, b in mev) / steps if args.workload == "r2l" else None
+        mlp_ms = wl.mlp_ms(mev, steps)
 
         # ---------------- end-to-end timing through the public API with host buffers
-        pose_host = [p.pin_memory() for p in poses]
-        frame_host = torch.empty((RAYS_STEP, 3), dtype=torch.float32).pin_memory()
-        c2w_buf = torch.empty((P, 3, 4), dtype=torch.float32, device="cuda")
         e2e_steps = steps
-        copy_stream = torch.cuda.Stream()
-        main_stream = torch.cuda.current_stream()
-        frame_host2 = [frame_host, torch.empty_like(frame_host).pin_memory()]
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        # the frame read-back runs on its own stream (double-buffered pinned host frames), so the D2H copy of step i
-        # overlaps the kernels of step i+1 — what a caller that streams frames to the host does
-        copied = [None, None]
-        for i in range(e2e_steps):
-            c2w_buf.copy_(pose_host[warmup + i], non_blocking=True)          # H2D of this step's input
-            # fused gather: peers overwrite symmetric buffer (i + 1) & 1 once they pass publish(i); the read-back of
-            # the frame it still holds (step i - 1) must be over before this rank joins that barrier
-            wait_prev = (lambda: main_stream.wait_event(copied[(i + 1) & 1])) if fused and copied[(i + 1) & 1] else None
-            out = run_step(c2w_buf, None, i, wait_prev)
-            if not by_rays or rank == 0:
-                done = torch.cuda.Event()
-                done.record(main_stream)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(done)
-                    frame_host2[i & 1].copy_(out, non_blocking=True)          # D2H of this step's result
-                    if not fused:      # (symmetric-memory buffers are not the caching allocator's)
-                        out.record_stream(copy_stream)
-                    copied[i & 1] = torch.cuda.Event()
-                    copied[i & 1].record(copy_stream)
-        main_stream.wait_stream(copy_stream)
-        e1.record()
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
+        e2e_ms = e2e_run(wl, poses, warmup, e2e_steps, run_step, barrier, rank, by_rays, fused)
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -472,6 +549,7 @@ def main():
     value = total_rays / (dev_ms * 1e-3) / 1e6
     e2e_value = RAYS_STEP * e2e_steps * n_jobs / (e2e_ms * 1e-3) / 1e6
 
+    line = None
     if rank == 0:
         line = {"metric": "render_throughput", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
                 "warmup": warmup, "warmup_extra_steps": extra_warm, "ms_per_step": dev_ms / steps,
@@ -495,36 +573,107 @@ def main():
                         "d2h_bytes_per_step": RAYS_STEP * 3 * 4, "ms_per_step": e2e_ms / e2e_steps},
                 "gpu_launches": int(kernels), "abi_calls": int(launches),
                 "clocks": clocks}
-        flops = FLOP_PER_RAY[args.workload] * RAYS_STEP / (world if by_rays else 1)   # per rank and launch
-        if args.workload == "r2l":
-            ach = flops / (mlp_ms * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "r2l_mlp_kernel", "achieved": ach,
-                                "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
-                                "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step; "
-                                               f"burst {peaks['tf_burst']})",
-                                "kernel_ms": mlp_ms, "algorithmic_flop_per_launch": flops,
-                                "traffic": NCU_TRAFFIC_BYTES["r2l"] * P // 4, "traffic_unit": "B/launch (ncu, profiles/r1h: 4 poses per launch)"}
-        else:
-            ach = flops / (dev_ms / steps * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "nerf_mlp_pp_kernel (coarse+fine, whole frame)",
-                                "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                                "frac": ach / peaks["tf_sust"], "peak_source": f"{peaks['src']} bf16_tflops_sustained",
-                                "kernel_ms": dev_ms / steps, "algorithmic_flop_per_launch": flops,
-                                "traffic": NCU_TRAFFIC_BYTES["nerf"],
-                                "traffic_unit": "B/frame = coarse + fine launch (ncu, profiles/r1g)"}
+        line["roofline"] = roofline_block(args.workload, RAYS_STEP // (world if by_rays else 1), mlp_ms, peaks, P)
         if world == 1 and not args.no_cpu_baseline:
             sample = 16384 if args.workload == "r2l" else 1024
             line["cpu_baseline"], _ = cpu_reference(args.workload, 2, 1, sample)
-        if world == 1 and not args.no_extras:
-            line["extras"] = extras(E, peaks, args.precision, args.workload)
+    if world == 1 and not args.no_extras:
+        line["extras"] = extras(E, peaks, args.precision, args.workload, flush, no_cpu=args.no_cpu_baseline)
+    if world > 1 and not args.no_extras and not by_rays:
+        # strong scaling of ONE frame, driver-visible: rays of every frame sharded over the ranks
+        try:
+            rs = ray_sharded_phase(E, dist, args.precision, rank, world, barrier)
+        except Exception as e:      # the headline line must survive a failure of the secondary phase
+            rs = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            line.setdefault("extras", {})["ray_sharded"] = rs
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def extras(E, peaks, precision, main_workload):
-    """Short secondary measurements reported beside the headline: the other model and the two HBM-bound kernels."""
+def ray_sharded_phase(E, dist, precision, rank, world, barrier):
+    """One 400x400 frame split into contiguous ray blocks over the ranks: R2L with the tile gather fused
+    into the MLP kernel (peer-to-peer stores into every GPU's symmetric-memory frame buffer + one cross-GPU barrier) and
+    the rank's kernel replayed as a CUDA graph; NeRF with one NCCL all_gather_into_tensor per frame.  Reports ms per
+    frame (device, max over ranks), e2e (pose from pinned host memory, frame back to rank 0's host memory) and whether
+    the gathered frame is bit-identical to the same frame rendered by ONE GPU."""
+    out = {}
+    with torch.no_grad():
+        def measure(wl, run_step, fused, frames):
+            poses1 = [p.reshape(1, 3, 4).contiguous() for p in make_poses(E, frames + 4)]
+            poses_dev = [p.cuda() for p in poses1]
+            for k in range(4):
+                run_step(poses_dev[k], None, k)
+            barrier()
+            evs = []
+            for k in range(frames):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                run_step(poses_dev[4 + k], None, k)
+                b.record()
+                evs.append((a, b))
+            barrier()
+            ms = sum(a.elapsed_time(b) for a, b in evs)
+            e2e = e2e_run(wl, poses1, 4, frames, run_step, barrier, rank, True, fused)
+            t = torch.tensor([ms, e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0]) / frames, float(t[1]) / frames, poses_dev[0]
+
+        def all_same(a, b):
+            same = torch.tensor([int(torch.equal(a, b))], device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            return bool(int(same[0]))
+
+        # ---- R2L: fused gather + graph replay
+        wl = R2LWorkload(E, precision, 1)
+        wl.block = E.sharding.shard_rays(RAYS, rank, world)
+        wl.enable_fused_gather()
+        wl.enable_graph()
+
+        def step_r2l(pose, mev=None, k=0, before_publish=None):
+            wl.step(pose, None, k)
+            if before_publish is not None:
+                before_publish()
+            return wl.frames[k & 1].publish()
+        ms, e2e, pose0 = measure(wl, step_r2l, True, 60)
+        got = step_r2l(pose0, None, 0).clone()
+        whole = wl.net.render_poses(wl.ps, pose0)           # the same frame on this GPU alone
+        out["r2l"] = {"ms_per_frame_400x400": ms, "Mrays_per_s": RAYS / ms / 1e3,
+                      "e2e": {"ms_per_frame": e2e, "Mrays_per_s": RAYS / e2e / 1e3, "h2d_bytes_per_step": 48,
+                              "d2h_bytes_per_step": RAYS * 12},
+                      "bit_identical_to_single_gpu": all_same(got, whole),
+                      "gather": "fused into r2l_mlp_kernel: rgb tiles stored to every GPU's frame buffer over NVLink + "
+                                "one symmetric-memory barrier per frame; CUDA-graph replay",
+                      "tiles_per_gpu": (wl.block[1] - wl.block[0] + 127) // 128}
+        barrier()
+        # ---- NeRF: NCCL gather of the rgb tiles
+        wn = NerfWorkload(E, precision)
+        wn.block = E.sharding.shard_rays(RAYS, rank, world)
+        frame_buf = torch.empty((RAYS, 3), dtype=torch.float32, device="cuda")
+
+        def step_nerf(pose, mev=None, k=0, before_publish=None):
+            return E.sharding.gather_rays_into(wn.step(pose).contiguous(), frame_buf, RAYS)
+        ms, e2e, pose0 = measure(wn, step_nerf, False, 12)
+        got = step_nerf(pose0).clone()
+        wn.block = None
+        whole = wn.step(pose0)
+        out["nerf"] = {"ms_per_frame_400x400": ms, "Mrays_per_s": RAYS / ms / 1e3,
+                       "e2e": {"ms_per_frame": e2e, "Mrays_per_s": RAYS / e2e / 1e3, "h2d_bytes_per_step": 48,
+                               "d2h_bytes_per_step": RAYS * 12},
+                       "bit_identical_to_single_gpu": all_same(got, whole),
+                       "gather": "one NCCL all_gather_into_tensor of the rgb tiles per frame"}
+    out["scaling"] = "strong"
+    out["timing"] = "sum of per-frame CUDA-event durations (gather / barrier inside), max over ranks"
+    return out
+
+
+def extras(E, peaks, precision, main_workload, flush, no_cpu=False):
+    """Secondary measurements reported beside the headline: the OTHER model as a full record of its own (roofline with
+    event-timed MLP launches, e2e with declared copies, cpu_baseline, parity census), single-pose R2L, the other BASELINE
+    configs and the HBM-bound kernels."""
     out = {}
     with torch.no_grad():
         def timeit(fn, n=10, warm=3):
@@ -539,17 +688,41 @@ def extras(E, peaks, precision, main_workload):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / n
 
+        def full_record(wl, name, steps, warmup=3):
+            """The same measurement the headline gets (timed_run + e2e_run), for another workload."""
+            P = wl.P
+            flat = make_poses(E, (steps + warmup) * P)
+            poses = [torch.stack(flat[i * P:(i + 1) * P], 0).contiguous() for i in range(steps + warmup)]
+            poses_dev = [p.cuda() for p in poses]
+            run_step = lambda pose, mev=None, k=0, before_publish=None: wl.step(pose, mev, k)
+            sync = torch.cuda.synchronize
+            step_ms, mev, extra_warm, _ = timed_run(wl, poses_dev, warmup, steps, run_step, flush, sync)
+            mlp_ms = wl.mlp_ms(mev, steps)
+            e2e_ms = e2e_run(wl, poses, warmup, steps, run_step, sync, 0)
+            ms = sum(step_ms) / steps
+            rec = {"workload": wl.describe()["workload"], "steps": steps, "ms_per_step": ms,
+                   "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(max(step_ms)),
+                   "ms_per_frame_400x400": ms / P, "Mrays_per_s": wl.rays_per_step / ms / 1e3,
+                   "e2e": {"value": wl.rays_per_step * steps / e2e_ms / 1e3, "unit": "Mrays/s",
+                           "ms_per_step": e2e_ms / steps, "h2d_bytes_per_step": 48 * P,
+                           "d2h_bytes_per_step": wl.rays_per_step * 12},
+                   "roofline": roofline_block(name, wl.rays_per_step, mlp_ms, peaks, P),
+                   "l2": "flushed between steps", "timing": "sum of per-step CUDA-event durations"}
+            rec["tensor_TFLOPs"] = FLOP_PER_RAY[name] * wl.rays_per_step / ms / 1e9
+            rec["frac_of_sustained_peak"] = rec["tensor_TFLOPs"] / peaks["tf_sust"]
+            return rec
+
         other = "nerf" if main_workload == "r2l" else "r2l"
-        wl = (R2LWorkload if other == "r2l" else NerfWorkload)(E, precision)
+        wl = (R2LWorkload if other == "r2l" else NerfWorkload)(E, precision, 4 if other == "r2l" else 1)
+        out[other] = full_record(wl, other, 12 if other == "nerf" else 100)
+        if not no_cpu:
+            out[other]["cpu_baseline"], _ = cpu_reference(other, 2, 1, 1024 if other == "nerf" else 16384)
         pose = make_poses(E, 1)[0].cuda()
-        if main_workload == "r2l":   # the same R2L frame rendered one pose per launch (ragged last wave of tiles)
+        if main_workload == "r2l":   # the reference's own step: ONE pose per forward (main.py:297-309)
             w1 = R2LWorkload(E, precision, 1)
-            ms1 = timeit(lambda: w1.step(pose), n=50)
-            out["r2l_one_pose_per_launch"] = {"ms_per_frame_400x400": ms1, "Mrays_per_s": RAYS / ms1 / 1e3}
-        ms = timeit(lambda: wl.step(pose), n=5 if other == "nerf" else 20)
-        fl = FLOP_PER_RAY[other] * RAYS
-        out[other] = {"ms_per_frame_400x400": ms, "Mrays_per_s": RAYS / ms / 1e3,
-                      "tensor_TFLOPs": fl / ms / 1e9, "frac_of_sustained_peak": fl / ms / 1e9 / peaks["tf_sust"]}
+            out["r2l_one_pose_per_launch"] = full_record(w1, "r2l", 100)
+        nw = wl if other == "nerf" else NerfWorkload(E, precision)
+        out["parity"] = parity_block(E, nw, precision)
         # the other BASELINE configs, one frame each (configs[3]: 800x800; configs[4]: LLFF fern 504x378, NDC, 64+64)
         if main_workload == "r2l":
             cam8 = E.synthetic.LEGO_800
@@ -559,7 +732,6 @@ def extras(E, peaks, precision, main_workload):
             ms = timeit(lambda: r2l.net.render_poses(ps8, pose), n=20)
             out["r2l_800x800"] = {"ms_per_frame": ms, "Mrays_per_s": n8 / ms / 1e3,
                                   "tensor_TFLOPs": FLOP_PER_RAY["r2l"] * n8 / ms / 1e9}
-            nw = wl if other == "nerf" else NerfWorkload(E, precision)
             kw8 = dict(nw.kw)
             ms = timeit(lambda: E.render_image(cam8["H"], cam8["W"], cam8["focal"], chunk=32768, c2w=pose, **kw8), n=3, warm=1)
             out["nerf_800x800"] = {"ms_per_frame": ms, "Mrays_per_s": n8 / ms / 1e3,
@@ -570,7 +742,7 @@ def extras(E, peaks, precision, main_workload):
             ms = timeit(lambda: E.render_image(fern["H"], fern["W"], fern["focal"], chunk=32768, c2w=pose, **kwf), n=3, warm=1)
             out["nerf_fern_504x378_ndc_64+64"] = {"ms_per_frame": ms, "Mrays_per_s": nf / ms / 1e3,
                                                   "tensor_TFLOPs": 227868672 * nf / ms / 1e9}
-        # HBM-bound kernels on 4x the frame (inputs > L2): raw2outputs S=192, sample_pdf Ni=128
+        # HBM-bound kernels on 4x the frame (inputs > L2): raw2outputs S=192 / S=64, sample_pdf Ni=128, hier_sample
         N = 4 * RAYS
         raw = torch.randn(N, 192, 4, device="cuda")
         z = torch.sort(torch.rand(N, 192, device="cuda") * 4 + 2, -1)[0]
@@ -578,20 +750,65 @@ def extras(E, peaks, precision, main_workload):
         ms = timeit(lambda: E.raw2outputs(raw, z, d, 0, True))
         gbs = N * (24 * 192 + 36) / ms / 1e6
         out["raw2outputs_S192"] = {"ms": ms, "GB_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm"], "rays": N}
-        del raw
+        raw64, z64 = raw[:, :64].contiguous(), z[:, :64].contiguous()
+        ms = timeit(lambda: E.raw2outputs(raw64, z64, d, 0, True))
+        gbs = N * (24 * 64 + 36) / ms / 1e6
+        out["raw2outputs_S64"] = {"ms": ms, "GB_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm"], "rays": N}
+        del raw, raw64
         bins = z[:, :63].contiguous()
         w = torch.rand(N, 62, device="cuda")
         ms = timeit(lambda: E.sample_pdf(bins, w, 128, det=True))
         gbs = N * 1012 / ms / 1e6
         out["sample_pdf_Ni128"] = {"ms": ms, "GB_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm"], "rays": N}
         # the fused form render_rays uses (mids + sample_pdf + sorted merge + z_std): 512 B in, 772 B out per ray
-        zc = z[:, :64].contiguous()
         wc = torch.rand(N, 64, device="cuda")
         ut = torch.linspace(0., 1., 128)
-        ms = timeit(lambda: E.run_nerf_raybased_helpers.hier_sample(zc, wc, 128, ut))
+        ms = timeit(lambda: E.run_nerf_raybased_helpers.hier_sample(z64, wc, 128, ut))
         gbs = N * 1284 / ms / 1e6
         out["hier_sample_64+128"] = {"ms": ms, "GB_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm"], "rays": N,
                                      "note": "the unfused kernels move 2548 B/ray for the same result"}
+    return out
+
+
+def parity_block(E, nerf_wl, precision):
+    """Whole-view parity of the bench pose, on the device: the fused tensor-core path against the precision='fp32'
+    CUDA-core path (pinned <= 1e-5 to the torch-CPU goldens in tests/).  NeRF: rays beyond the 2e-3 gate in rgb_map /
+    rgb0 with and without the far-sample fix-up, rays flagged; R2L: max |rgb - fp32| over the frame."""
+    out = {}
+    pose = make_poses(E, 1)[0].cuda()
+    focal = E.synthetic.LEGO["focal"]
+    with torch.no_grad():
+        c32, f32 = E.synthetic.seeded_nerf_pair(0, "fp32")
+        embed_fn, _ = E.get_embedder(10, 0)
+        embeddirs_fn, _ = E.get_embedder(4, 0)
+        qfn = lambda inputs, viewdirs, fn: E.run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, 1024 * 64)
+        kw32 = dict(nerf_wl.kw, network_fn=c32, network_fine=f32, network_query_fn=qfn)
+        rgb32, _, _, ex32 = E.render_image(H, W, focal, chunk=8192, c2w=pose, **kw32)
+        res = {}
+        for name, on in (("with_far_fixup", True), ("without_far_fixup", False)):
+            nerf_wl.coarse.set_far_fixup(on), nerf_wl.fine.set_far_fixup(on)
+            rgb, _, _, ex = E.render_image(H, W, focal, chunk=32768, c2w=pose, **nerf_wl.kw)
+            d = (rgb - rgb32).abs().reshape(-1, 3).max(-1)[0]
+            d0 = (ex["rgb0"] - ex32["rgb0"]).abs().reshape(-1, 3).max(-1)[0]
+            mse = float(((rgb - rgb32).double() ** 2).mean())
+            res[name] = {"rays_beyond_2e-3_rgb_map": int((d > 2e-3).sum()), "rays_beyond_2e-3_rgb0": int((d0 > 2e-3).sum()),
+                         "max_abs_rgb_map": float(d.max()), "max_abs_rgb0": float(d0.max()),
+                         "psnr_vs_fp32_dB": float(-10. * np.log10(max(mse, 1e-30)))}
+            if on:
+                res[name]["rays_flagged_fine_pass"] = nerf_wl.fine.far_flagged()
+        nerf_wl.coarse.set_far_fixup(True), nerf_wl.fine.set_far_fixup(True)
+        out["nerf_400x400_vs_fp32_path"] = dict(res, operands=precision, rays=RAYS,
+                                                gate="rgb within 2e-3 max-abs per view (north_star)")
+        net = E.synthetic.seeded_r2l(0, precision)
+        net32 = E.synthetic.seeded_r2l(0, "fp32")
+        ps = E.PointSampler(H, W, focal, 16, 2., 6.)
+        rgb = net.render_poses(ps, pose)
+        pe = E.PositionalEmbedder(10)
+        pts = ps.sample_test(pose)
+        rgb32 = torch.cat([net32(pe(pts[i:i + 32768])) for i in range(0, RAYS, 32768)], 0)
+        d = (rgb - rgb32).abs()
+        out["r2l_400x400_vs_fp32_path"] = {"max_abs_rgb": float(d.max()), "rays_beyond_2e-3": int((d.max(-1)[0] > 2e-3).sum()),
+                                           "operands": precision, "rays": RAYS}
     return out
 
 

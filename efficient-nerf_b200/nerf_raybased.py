@@ -265,9 +265,17 @@ class NeRF(nn.Module):
         ro, rd, vd = (_rows(t, dev) for t in (rays_o, rays_d, viewdirs))
         z = _lib.as_f32_cuda(z_vals, dev)
         raw = torch.empty((N, S, 4), dtype=torch.float32, device=dev)
+        evs = self.__dict__.get('_mlp_events')      # bench.py: CUDA events around the MLP launches of a step
         with torch.cuda.device(dev):
+            if evs is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             _lib.call("r2l_nerf_forward", h.h, N, S, _lib.ptr(ro), ro.stride(0), _lib.ptr(rd), rd.stride(0),
                       _lib.ptr(vd), vd.stride(0), _lib.ptr(z), _lib.ptr(raw), _lib.stream_ptr(dev))
+            if evs is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                evs.append((e0, e1))
         return raw
 
     # -- nn.Module API ---------------------------------------------------------------------
