@@ -40,6 +40,8 @@ SIGNATURES = {
     "r2l_merge_sorted": [_c_ll, _c_int, _c_int, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_vp],
     "r2l_image_error": [_c_int, _c_ll, _c_f32p, _c_f32p, _c_f32p, _c_vp, _c_vp],
     "r2l_ssim": [_c_int, _c_int, _c_int, _c_f32p, _c_f32p, _c_ll, _c_vp, _c_vp, _c_vp],
+    "r2l_flip": [_c_int, _c_int, _c_int, _c_f32p, _c_f32p, _c_ll, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_vp, _c_int, _c_int,
+                 _c_f32p, _c_f32p, _c_f32p, _c_vp, _c_vp],
     "r2l_linear_fp32": [_c_ll, _c_int, _c_int, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_f32p, _c_ll, _c_int,
                         _c_f32p, _c_ll, _c_vp],
     "r2l_nerf_create": [ctypes.POINTER(_c_vp), _c_int, ctypes.POINTER(_c_vp), ctypes.POINTER(_c_vp), _c_f32p,

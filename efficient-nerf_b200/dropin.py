@@ -12,6 +12,7 @@ What the launcher does, in this order (no file of the reference is edited or cop
    create_data.py:11, dataset/load_blender.py:8, load_llff.py:4) — that export this package's mirrors under the
    reference's names.  `PointSampler` and `PositionalEmbedder` are the lazy forms there, so main.py:297-309
    `model(positional_embedder(point_sampler.sample_test(c2w)))` is ONE kernel (ray generation + encoding + ResMLP).
+   `utils.flip_loss` (main.py:18) is bound to the device FLIP of `metrics` the same way.
 2. Packages the reference imports but this image does not have are stubbed IF absent (`smilelogging`, `imageio`,
    `lpips`, `matplotlib` is simply not needed): see `install_stubs`.  A real installation always wins.  The LPIPS
    stub returns NaN — a pretrained perceptual network is out of scope, PSNR / SSIM / FLIP are real.
@@ -142,6 +143,16 @@ def install(fused=True, stubs=True):
     except ImportError:
         compat.install_reference_aliases()
         sys.modules["model.nerf_raybased"], sys.modules["utils.run_nerf_raybased_helpers"] = mm, hm
+    if fused:
+        # main.py:18 `from utils.flip_loss import FLIP` -> the device FLIP (same class surface, csrc/flip.cu): the
+        # metric stage of render_path is what is left once a frame renders in a millisecond
+        from . import metrics as _metrics
+        fm = types.ModuleType("utils.flip_loss")
+        fm.FLIP, fm.FLIPLoss = _metrics.FLIP, _metrics.FLIPLoss
+        fm.__doc__ = "efficient_nerf_b200 stand-in (dropin.install)"
+        sys.modules["utils.flip_loss"] = fm
+        if "utils" in sys.modules:
+            setattr(sys.modules["utils"], "flip_loss", fm)
     if stubs:
         install_stubs()
     os.environ.setdefault("TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD", "1")   # main.py:483 torch.load of pickled modules (torch>=2.6)

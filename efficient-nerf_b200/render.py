@@ -316,9 +316,11 @@ def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=N
 
     model_name == 'nerf' renders through `render` (main.py:283-290); anything else is the R2L branch
     `model(positional_embedder(point_sampler.sample_test(c2w)))` (main.py:292-321).  Returns (rgbs [N,H,W,3],
-    disps, misc) with misc['test_loss', 'test_psnr', 'test_psnr_v2', 'test_ssim', 'errors'] as in main.py:384-394.
-    Out of scope: PNG writing (`savedir` must be None), LPIPS and FLIP (misc has no such keys),
-    `given_render_path_rays`."""
+    disps, misc) with misc['test_loss', 'test_psnr', 'test_psnr_v2', 'test_ssim', 'test_flip', 'errors'] as in
+    main.py:384-394.
+    misc['test_flip'] is the reference's FLIP stage (main.py:370-379) on the device (csrc/flip.cu).
+    Out of scope: PNG writing (`savedir` must be None), LPIPS (a pretrained network; misc has no
+    'test_lpips'), `given_render_path_rays`."""
     from . import metrics
     if savedir is not None:
         raise NotImplementedError("render_path: image files are written by the caller (PNG I/O is out of scope)")
@@ -355,6 +357,12 @@ def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=N
             misc["test_psnr"] = metrics.mse2psnr(test_loss)
             misc["test_psnr_v2"] = m["psnr"].mean()
             misc["test_ssim"] = m["ssim"].mean()
+            # FLIP of the stacks rescaled to [-1, 1] (each by its own min / max), exactly what main.py:362-379 computes:
+            # it reuses the LPIPS inputs; the sRGB decode inside FLIP then clamps the negative half to 0
+            lim = torch.stack(torch.aminmax(rgbs) + torch.aminmax(gt)).double().tolist()
+            sc = [(2. / (hi - lo), -lo * 2. / (hi - lo) - 1.) for lo, hi in (lim[0:2], lim[2:4])]
+            _, flips = metrics.flip_map(rgbs, gt, scale=sc, want_map=False)
+            misc["test_flip"] = flips.mean()
             misc["errors"] = m["errors"]
     if was_training and hasattr(net, "train"):
         net.train()

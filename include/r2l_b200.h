@@ -121,6 +121,16 @@ int r2l_image_error(int n_img, long long n_per_img, const float* a, const float*
 int r2l_ssim(int n_img, int H, int W, const float* a, const float* b, long long img_stride, const float* taps,
              double* sum_out, void* stream);
 
+/* LDR-FLIP of frame stacks (utils/flip_loss.py:69-140 as called from main.py:370-379): test, ref [n_img][H][W][3]
+ * fp32, every value mapped v -> v*scale + offset on load (main.py:366-368 rescales both stacks to [-1,1] first).
+ * consts: HOST pointer to 26 floats (sRGB->XYZ matrix A[9], its inverse[9], illuminant A*1 [3], cmax, qc, qf, pc, pt);
+ * taps: DEVICE pointer to the CSF filters A / RG / BY [3][(2 r_csf+1)^2] followed by the edge / point x-filters
+ * [2][(2 r_feat+1)^2], computed by the caller as the reference computes them; workspace: DEVICE [n_img][2][3][H][W]
+ * floats.  flip_map (optional) [n_img][H][W]; sum_out [n_img] double (zeroed by the call): mean = sum / (H W). */
+int r2l_flip(int n_img, int H, int W, const float* test, const float* ref, long long img_stride, double scale_test,
+             double offset_test, double scale_ref, double offset_ref, const float* consts, int r_csf, int r_feat,
+             const float* taps, float* workspace, float* flip_map, double* sum_out, void* stream);
+
 /* ---- MLPs ---------------------------------------------------------------------------------- */
 
 /* Y = act(X W^T + b [+ R]) in fp32 on CUDA cores (act: 0 none, 1 relu, 2 sigmoid); the

@@ -73,6 +73,16 @@ def test_render_path_r2l_and_nerf(E, O):
     assert abs(float(misc["test_loss"]) - float(O.img2mse(rgbs.cpu(), gt))) < 1e-9
     assert abs(float(misc["test_psnr"]) - float(O.mse2psnr(O.img2mse(rgbs.cpu(), gt)))) < 1e-4
     assert misc["errors"].shape == (3, H, W, 3)
+    # test_flip = FLIP of the stacks rescaled to [-1, 1] like main.py:362-379 does (it reuses the LPIPS inputs)
+    assert 0. < float(misc["test_flip"]) < 1.
+    import os
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "main.py")):
+        from oracle.make_golden_flip import load_reference_flip
+        rescale = lambda x, ymin, ymax: (ymax - ymin) / (x.max() - x.min()) * (x - x.min()) + ymin   # main.py:364-365
+        rec, ref = rescale(rgbs.permute(0, 3, 1, 2), -1, 1), rescale(gt.cuda().permute(0, 3, 1, 2), -1, 1)
+        with torch.no_grad():
+            want = load_reference_flip().FLIP().compute_flip(rec, ref, 0.7 * (3840 / 0.7) * (np.pi / 180)).mean()
+        assert abs(float(misc["test_flip"]) - float(want)) < 2e-5
     # NeRF branch
     sdc, sdf = O.nerf_state_dicts(0)
     coarse = E.NeRF(8, 256, 63, 27, 5, [4], True, precision="fp16")
@@ -86,3 +96,41 @@ def test_render_path_r2l_and_nerf(E, O):
         one, d1, _, _ = E.render_image(H, W, focal, chunk=32768, c2w=poses[1][:3, :4].cuda(), **kw)
     assert rgbs.shape == (2, H, W, 3) and disps.shape == (2, H, W) and misc == {}
     assert torch.equal(rgbs[1], one) and torch.equal(disps[1], d1, ) or torch.allclose(disps[1], d1, equal_nan=True)
+
+
+# ------------------------------------------------------------------ FLIP (utils/flip_loss.py, main.py:370-379)
+def test_flip_matches_the_reference_fixture(E, golden):
+    """tests/golden/flip.npz was produced on a B200 by the REFERENCE's own FLIP (oracle/make_golden_flip.py)."""
+    g = golden("flip")
+    test, ref = t(g["test"]).cuda(), t(g["ref"]).cuda()
+    for name, sc in (("unit", (1., 0.)), ("rescaled", (2., -1.))):
+        m, mean = E.metrics.flip_map(test, ref, float(g["ppd"]), scale=sc)
+        want = t(g["map_" + name])
+        assert float((m.cpu() - want).abs().max()) < 2e-4, name
+        assert abs(float(mean.mean()) - float(g["mean_" + name])) < 2e-5
+    # the module form, reference layout [N, 3, H, W] (main.py:362-377)
+    f = E.metrics.FLIP()
+    a, b = test.permute(0, 3, 1, 2), ref.permute(0, 3, 1, 2)
+    m = f.compute_flip(a, b, f.pixels_per_degree)
+    assert tuple(m.shape) == (2, 1, 48, 56)
+    assert abs(float(f(a, b)) - float(g["mean_unit"])) < 2e-5
+    assert float(E.metrics.flip_map(test, test)[1].abs().max()) == 0.        # identical images: FLIP = 0
+
+
+def test_flip_live_against_the_staged_reference(E):
+    """When baseline/_ref travelled to the box: the reference's own FLIP module, run here, on full-size frames."""
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.exists(os.path.join(root, "utils", "flip_loss.py")):
+        pytest.skip("baseline/_ref is not staged")
+    from oracle.make_golden_flip import load_reference_flip
+    ref_flip = load_reference_flip().FLIP()
+    torch.manual_seed(3)
+    gt = torch.rand(3, 100, 100, 3, device="cuda")
+    gt = torch.nn.functional.interpolate(gt.permute(0, 3, 1, 2), size=(400, 400), mode="bilinear").permute(0, 2, 3, 1).contiguous()
+    img = (gt + .05 * torch.randn_like(gt)).clamp(0, 1)
+    with torch.no_grad():
+        want = ref_flip.compute_flip(img.permute(0, 3, 1, 2), gt.permute(0, 3, 1, 2), ref_flip.pixels_per_degree)
+        got, mean = E.metrics.flip_map(img, gt)
+    assert float((got - want[:, 0]).abs().max()) < 2e-4
+    assert abs(float(mean.mean()) - float(want.mean())) < 1e-5
