@@ -14,6 +14,7 @@ enum : int {
   R2L_ERR_CUDA = 2,      // a CUDA runtime call / kernel launch failed
   R2L_ERR_UNSUPPORTED = 3,
   R2L_ERR_DEVICE_TRAP = 4,  // kernel watchdog fired (see DebugBuf)
+  R2L_ERR_RANGE = 5,        // a weight or an activation left the range of the 16-bit operand type (fp16: 65504)
 };
 
 void set_last_error(const std::string& msg);

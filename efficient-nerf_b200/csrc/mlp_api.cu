@@ -53,6 +53,15 @@ int sm_count() {
 //   element offset = s*(N*64) + ((k%64)/8)*(N*8) + n*8 + (k%8)
 // pair != 0: CTA-pair layout — every stage is split into two N-halves (rows [0,N/2) for the leader CTA, then rows
 // [N/2,N) for its peer), each half k-chunk major with N/2 rows, so each CTA bulk-copies one contiguous half stage.
+// g_pack_max: bit pattern of the largest |value| packed since it was last reset (non-negative floats order like their
+// bit patterns; NaN patterns are larger than every finite one, so a NaN weight fails the range check too).
+__device__ unsigned int g_pack_max;
+
+__device__ __forceinline__ void track_max(float v) {
+  const unsigned int m = __reduce_max_sync(__activemask(), __float_as_uint(fabsf(v)));
+  if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1) && m > 0x477fe000u) atomicMax(&g_pack_max, m);   // > 65504
+}
+
 __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, int N, int K_src, int Kpad,
                                   const int* __restrict__ kmap, float scale, uint16_t* __restrict__ dst, int bf16,
                                   int pair) {
@@ -63,6 +72,7 @@ __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, in
     const int ks = (kmap != nullptr) ? kmap[k] : k;
     float v = 0.0f;
     if (ks >= 0 && ks < K_src) v = W[n * ldw + ks] * scale;
+    track_max(v);
     uint16_t bits;
     if (bf16)
       bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -103,6 +113,7 @@ __global__ void pack_bias_kernel(const float* __restrict__ bias, int N, float sc
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * 16) return;
   const int n = idx / 16, k = idx % 16;
+  track_max(k == 0 ? bias[n] * scale : 0.0f);
   const uint16_t bits = (k < 2) ? bias_part(bias[n] * scale, k, bf16) : static_cast<uint16_t>(0);
   if (pair == 2) {   // v3: 64-row blocks ordered (CTA r, half h), n = 128h + 64r + i
     const int h = n / 128, r = (n % 128) / 64, i = n % 64, nh = N / 128;
@@ -125,6 +136,7 @@ __global__ void pack_view_stage_kernel(const float* __restrict__ views_w, long l
   uint16_t bits = 0;
   if (k < 27) {
     const float v = views_w[n * ldw + 256 + k];
+    track_max(v);
     bits = bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
   } else if (k < 29) {
     bits = bias_part(views_b[n], k - 27, bf16);
@@ -199,6 +211,25 @@ static int nerf_pp_default() {
 static int pair_mode_default() {
   const char* e = getenv("R2L_PAIR");
   return (e != nullptr && e[0] == '0') ? 0 : 1;
+}
+
+// Range check of everything packed between pack_max_reset and pack_max_check (fp16 operands only: bf16 has fp32's range)
+static int pack_max_reset(cudaStream_t st) {
+  const unsigned int zero = 0;
+  R2L_CUDA(cudaMemcpyToSymbolAsync(g_pack_max, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, st));
+  return R2L_OK;
+}
+static int pack_max_check(bool bf16, cudaStream_t st, const char* who) {
+  unsigned int bits = 0;
+  R2L_CUDA(cudaMemcpyFromSymbolAsync(&bits, g_pack_max, sizeof(bits), 0, cudaMemcpyDeviceToHost, st));
+  R2L_CUDA(cudaStreamSynchronize(st));
+  if (!bf16 && bits > 0x477fe000u) {
+    float v;
+    memcpy(&v, &bits, sizeof(v));
+    return fail(R2L_ERR_RANGE, "%s: a weight / bias of magnitude %g does not fit fp16 operands (max 65504): use "
+                "precision 'bf16' or 'fp32' for this model", who, static_cast<double>(v));
+  }
+  return R2L_OK;
 }
 
 static int alloc_debug(Mlp* m) {
@@ -556,6 +587,7 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
       cudaMalloc(reinterpret_cast<void**>(&m->aux), sizeof(float) * kNerfAuxTotal) != cudaSuccess)
     return cleanup(fail(R2L_ERR_CUDA, "r2l_nerf_create: cudaMalloc failed"));
   int rc = alloc_debug(m);
+  if (rc == R2L_OK) rc = pack_max_reset(st);
   if (rc != R2L_OK) return cleanup(rc);
   uint16_t* dst = reinterpret_cast<uint16_t*>(m->wstream);
   std::vector<int> kmap0(64), kmap5(320);
@@ -657,6 +689,8 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->rgb_b, rgb_b, 12, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cleanup(fail(R2L_ERR_CUDA, "r2l_nerf_create: %s", cudaGetErrorString(e)));
+  rc = pack_max_check(m->bf16, st, "r2l_nerf_create");
+  if (rc != R2L_OK) return cleanup(rc);
   *out_handle = m;
   return cleanup(R2L_OK);
 }
@@ -665,6 +699,14 @@ static int check_dbg(Mlp* m, const char* who) {
   if (m->dbg_host && m->dbg_host->flag != 0)
     return fail(R2L_ERR_DEVICE_TRAP, "%s: kernel watchdog fired earlier (block %u thread %u barrier %u parity %u)", who,
                 m->dbg_host->block, m->dbg_host->thread, m->dbg_host->barrier_id, m->dbg_host->parity);
+  if (m->dbg_host && m->dbg_host->aux0 != 0) {
+    // reported once, then cleared: the handle itself is healthy, the earlier RESULT was not
+    const unsigned int row = m->dbg_host->aux1;
+    m->dbg_host->aux0 = 0;
+    return fail(R2L_ERR_RANGE, "%s: an earlier launch on this handle produced non-finite outputs (first seen at row "
+                "%u): an activation left the range of %s operands%s", who, row, m->bf16 ? "bf16" : "fp16",
+                m->bf16 ? "" : " (65504) — use precision 'bf16' or 'fp32' for this model");
+  }
   return R2L_OK;
 }
 
@@ -877,6 +919,7 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
       cudaMalloc(reinterpret_cast<void**>(&m->aux), sizeof(float) * aux_floats) != cudaSuccess)
     return cleanup(fail(R2L_ERR_CUDA, "r2l_resmlp_create: cudaMalloc failed"));
   int rc = alloc_debug(m);
+  if (rc == R2L_OK) rc = pack_max_reset(st);
   if (rc != R2L_OK) return cleanup(rc);
   // head K order: point block s, in-block index i (see encode_point_block) <- reference column (3s+c)*21 + f'
   std::vector<int> kmap(K_head);
@@ -928,6 +971,8 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->b_tail, tail_b, 12, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cleanup(fail(R2L_ERR_CUDA, "r2l_resmlp_create: %s", cudaGetErrorString(e)));
+  rc = pack_max_check(m->bf16, st, "r2l_resmlp_create");
+  if (rc != R2L_OK) return cleanup(rc);
   *out_handle = m;
   return cleanup(R2L_OK);
 }
@@ -1096,12 +1141,15 @@ int r2l_mlp_destroy(void* handle) {
   return R2L_OK;
 }
 
-// 0 = healthy; otherwise the watchdog record of the first barrier that timed out.
+// 0 = healthy; R2L_ERR_DEVICE_TRAP: out8 = the watchdog record of the first barrier that timed out; R2L_ERR_RANGE: a
+// finished launch produced non-finite outputs (out8[5] = 1, out8[6] = row): an activation left the 16-bit operand range.
+// Reads the handle's mapped record without synchronising: call it after the stream has been synchronised.
 int r2l_mlp_status(void* handle, unsigned int* out8) {
   Mlp* m = static_cast<Mlp*>(handle);
   R2L_CHECK_ARG(m != nullptr, "r2l_mlp_status: null handle");
   if (out8 != nullptr && m->dbg_host != nullptr) memcpy(out8, m->dbg_host, sizeof(DebugBuf));
-  return (m->dbg_host && m->dbg_host->flag) ? R2L_ERR_DEVICE_TRAP : R2L_OK;
+  if (m->dbg_host && m->dbg_host->flag) return R2L_ERR_DEVICE_TRAP;
+  return (m->dbg_host && m->dbg_host->aux0) ? R2L_ERR_RANGE : R2L_OK;
 }
 
 }  // extern "C"

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
                 store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                  const float w = sAlphaW[col0 + i], h = fmaxf(__uint_as_float(v[i]), 0.0f);
+                  const float w = sAlphaW[col0 + i], h = relu_nan(__uint_as_float(v[i]));
                   sigma_part = fmaf(w, h, sigma_part);
                   abs_part = fmaf(fabsf(w), h, abs_part);
                 }
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int n = 64 * wg + i;
-          const float x = fmaxf(__uint_as_float(va[i]), 0.0f);
+          const float x = relu_nan(__uint_as_float(va[i]));
           r = fmaf(sRgbW[n], x, r);
           gch = fmaf(sRgbW[128 + n], x, gch);
           b = fmaf(sRgbW[256 + n], x, b);
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int n = 64 * wg + 32 + i;
-          const float x = fmaxf(__uint_as_float(vb[i]), 0.0f);
+          const float x = relu_nan(__uint_as_float(vb[i]));
           r = fmaf(sRgbW[n], x, r);
           gch = fmaf(sRgbW[128 + n], x, gch);
           b = fmaf(sRgbW[256 + n], x, b);
@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
           o.z = b + o1.z + p.rgb_b[2];
           o.w = sigma_part + o1.w + p.alpha_b;
           reinterpret_cast<float4*>(p.raw)[g_row] = o;
+          note_nonfinite(p.dbg, o.x + o.y + o.z + o.w, g_row);
           nerf_far_flag(p, g_row, g_row / p.S, o.w, abs_part + a1);
         }
       }

@@ -467,7 +467,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
                 store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                  const float w = sAlphaW[col0 + i], h = fmaxf(__uint_as_float(v[i]), 0.0f);
+                  const float w = sAlphaW[col0 + i], h = relu_nan(__uint_as_float(v[i]));
                   sp = fmaf(w, h, sp);
                   sa = fmaf(fabsf(w), h, sa);
                 }
@@ -506,7 +506,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const int n = 32 * wg + 4 * i4 + k;
-                  const float x = fmaxf(__uint_as_float(va[4 * i4 + k]) + bv[k], 0.0f);
+                  const float x = relu_nan(__uint_as_float(va[4 * i4 + k]) + bv[k]);
                   r = fmaf(sRgbW[n], x, r);
                   gch = fmaf(sRgbW[128 + n], x, gch);
                   b = fmaf(sRgbW[256 + n], x, b);
@@ -519,7 +519,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const int n = 64 + 32 * wg + 4 * i4 + k;
-                  const float x = fmaxf(__uint_as_float(vb[4 * i4 + k]) + bv[k], 0.0f);
+                  const float x = relu_nan(__uint_as_float(vb[4 * i4 + k]) + bv[k]);
                   r = fmaf(sRgbW[n], x, r);
                   gch = fmaf(sRgbW[128 + n], x, gch);
                   b = fmaf(sRgbW[256 + n], x, b);
@@ -543,6 +543,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
                 o.z = b + o1.z + p.rgb_b[2];
                 o.w = sigma_part[t] + o1.w + p.alpha_b;
                 reinterpret_cast<float4*>(p.raw)[g_row] = o;
+                note_nonfinite(p.dbg, o.x + o.y + o.z + o.w, g_row);
                 nerf_far_flag(p, g_row, ray, o.w, abs_part[t] + a1);
               }
             }

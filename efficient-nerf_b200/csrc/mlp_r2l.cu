@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           [&](uint32_t col0, uint32_t (&v)[32]) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float x = fmaxf(__uint_as_float(v[i]), 0.0f);
+              const float x = relu_nan(__uint_as_float(v[i]));
               if (p.dbg_head_acc != nullptr) {   // debug hook: raw accumulator (bias included) and x0
                 const long long o = (static_cast<long long>(tile) * kTileM + row) * 256 + col0 + i;
                 p.dbg_head_acc[o] = __uint_as_float(v[i]);
@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
         float o1 = t1 + sPart[row * 4 + 1] + p.b_tail[1];
         float o2 = t2 + sPart[row * 4 + 2] + p.b_tail[2];
         named_bar_arrive(2, 256);
+        if (valid) note_nonfinite(p.dbg, o0 + o1 + o2, ray);   // before the sigmoid hides an inf
         if (p.sigmoid_out) {
           o0 = 1.0f / (1.0f + expf(-o0));
           o1 = 1.0f / (1.0f + expf(-o1));

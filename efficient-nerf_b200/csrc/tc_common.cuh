@@ -31,10 +31,30 @@ struct DebugBuf {
   unsigned int thread;
   unsigned int barrier_id;
   unsigned int parity;
-  unsigned int aux0;
-  unsigned int aux1;
+  unsigned int aux0;       // range flag: != 0 when a launch produced a non-finite output row (see note_nonfinite)
+  unsigned int aux1;       // ... the low 32 bits of that row's index
   unsigned int aux2;
 };
+
+// fp16 operands hold |x| <= 65504.  The activation converts are NOT saturating on purpose: an activation (or a product
+// sum) that leaves the range becomes +-inf, inf / NaN then reach every later layer (and stay in R2L's fp32 residual
+// stream), so the kernel's OUTPUT row is non-finite — an overflow announces itself instead of silently rendering a
+// clamped, wrong colour as a .satfinite convert would.  The output stage tests its few fp32 values per row (free) and
+// records the event in the handle's mapped DebugBuf; the next call on the handle (and r2l_mlp_status) reports
+// R2L_ERR_RANGE.  Weights are range-checked when they are packed.
+// relu that PROPAGATES NaN (fmaxf(NaN, 0) is 0: it would turn an overflowed activation into a plausible-looking zero)
+__device__ __forceinline__ float relu_nan(float v) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+__device__ __forceinline__ void note_nonfinite(DebugBuf* dbg, float probe, long long row) {
+  if (!(fabsf(probe) <= 3.0e38f) && dbg != nullptr) {
+    *reinterpret_cast<volatile unsigned int*>(&dbg->aux1) = static_cast<unsigned int>(row);
+    *reinterpret_cast<volatile unsigned int*>(&dbg->aux0) = 1u;
+  }
+}
 
 #ifndef R2L_WATCHDOG_SPINS
 #define R2L_WATCHDOG_SPINS (1u << 24)

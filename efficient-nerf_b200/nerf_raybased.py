@@ -77,6 +77,12 @@ class _Handle:
     def __init__(self, h):
         self.h = h
 
+    def status(self):
+        """r2l_mlp_status: 0 healthy, 4 a kernel watchdog fired, 5 a finished launch produced non-finite outputs (an
+        activation left the fp16 range).  Reads the handle's mapped record: synchronise the stream first."""
+        rec = (ctypes.c_uint * 8)()
+        return int(_lib.load().r2l_mlp_status(self.h, rec)), list(rec)
+
     def __del__(self):
         try:
             if self.h:
@@ -246,6 +252,12 @@ class NeRF(nn.Module):
     def _apply_far(self, h):
         en, a, r = self.__dict__.get('_far', (True, None, None))
         _lib.call("r2l_nerf_far_fixup", h.h, 1 if en else 0, -1.0 if a is None else float(a), -1.0 if r is None else float(r))
+
+    def range_status(self):
+        """(code, record) of the packed handle after synchronising: code 5 = the last launches overflowed the 16-bit
+        operand range (outputs non-finite); the next forward raises the same error once."""
+        torch.cuda.synchronize(self.alpha_linear.weight.device)
+        return self.packed_handle().status()
 
     def far_flagged(self):
         """Rays the last forward_samples flagged for the fp32 far-sample fix-up (synchronises the stream)."""
@@ -566,6 +578,12 @@ class NeRF_v3_2(nn.Module):
         h = _Handle(out)
         self._packed[precision] = (key, h)
         return h
+
+    def range_status(self):
+        """(code, record) of the packed handle after synchronising: code 5 = the last launches overflowed the 16-bit
+        operand range (outputs non-finite); the next forward raises the same error once."""
+        torch.cuda.synchronize(self.head[0].weight.device)
+        return self.packed_handle().status()
 
     def forward_points(self, pts):
         """Fused PositionalEmbedder(L=10) + network: pts [N, n_points*3] -> rgb [N, 3]."""

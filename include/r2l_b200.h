@@ -10,6 +10,8 @@
  * Conventions
  *   - every function returns 0 on success, non-zero on error; r2l_last_error() gives the text
  *     (thread-local).  No exceptions cross the ABI.  There is NO CPU fallback.
+ *     Codes: 1 invalid argument, 2 CUDA error, 3 unsupported configuration, 4 device trap (kernel watchdog),
+ *     5 range (a weight or an activation does not fit the 16-bit operand type, see r2l_mlp_status).
  *   - all pointers are DEVICE pointers to fp32 data unless stated otherwise; tensors are
  *     row-major and contiguous, `*_stride` arguments are row strides in ELEMENTS.
  *   - `stream` is a cudaStream_t (as void*); calls are asynchronous on that stream.
@@ -219,7 +221,11 @@ int r2l_mlp_debug_wstream(void* handle, void* out_host, unsigned long long capac
 
 int r2l_mlp_destroy(void* handle);
 
-/* 0 = healthy; non-zero if a kernel watchdog fired.  out8: optional 8 x uint32 debug record. */
+/* 0 = healthy; 4 (device trap) if a kernel watchdog fired; 5 (range) if a finished launch produced non-finite outputs,
+ * i.e. an activation left the range of the 16-bit operands (fp16: 65504).  The activation converts do not saturate, so
+ * an overflow propagates as inf / NaN to the output row and is detected there instead of rendering a silently clamped
+ * colour; the next forward call on the handle fails with the same code (once).  Weights are range-checked by
+ * r2l_nerf_create / r2l_resmlp_create.  Reads the mapped record without synchronising.  out8: optional 8 x uint32. */
 int r2l_mlp_status(void* handle, unsigned int* out8);
 
 /* Unit-test probe: D [128,N] = A [128,K] x W [N,K]^T with 16-bit operands on tcgen05. */
