@@ -192,37 +192,53 @@ template <int K> struct BlkLayout {
   static constexpr int kWarpBytes = 2 * kStageBytes + kZBytes;   // two input stages + the weight row
 };
 
-// FULL: S == 32*K exactly (64 / 128 / 192 / 256 samples: every BASELINE config) -> no per-sample validity predicates.
-template <int K, bool FULL>
+// RPW rays per warp: a warp stages RPW CONSECUTIVE rays (one contiguous chunk of RPW*S samples) and lane l owns the K
+// consecutive samples [l*K, l*K+K) of that chunk, i.e. 32/RPW lanes per ray.  With S = 64 and one ray per warp a lane
+// holds only 2 samples and the per-ray warp-level work (fp64 scan, five reductions, output stores) dominates: the
+// kernel was issue-bound at 52 % of the HBM roofline (ncu r1g).  Four rays per warp (8 lanes x 8 samples per ray) run
+// a 3-step segmented scan and 3-step reductions once for FOUR rays.
+// FULL: RPW*S == 32*K exactly (64 / 128 / 192 / 256 samples: every BASELINE config) -> no per-sample predicates
+// (whole rays beyond n_rays in the last warp are still masked).
+template <int K, bool FULL, int RPW>
 __global__ void __launch_bounds__(kBlkWarps * 32)
 raw2outputs_blocked_kernel(long long n_rays, int S, const float4* __restrict__ raw, const float* __restrict__ z_vals,
                            const float* __restrict__ rays_d, long long d_stride, const float* __restrict__ noise,
                            int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ disp_map,
                            float* __restrict__ acc_map, float* __restrict__ weights, float* __restrict__ depth_map) {
   using L = BlkLayout<K>;
+  constexpr int LPR = 32 / RPW;   // lanes per ray
   extern __shared__ __align__(16) uint8_t smem_blk[];
   const int lane = threadIdx.x & 31;
+  const int sl = lane % LPR;      // lane within its ray
   uint8_t* const wbase = smem_blk + static_cast<size_t>(threadIdx.x >> 5) * L::kWarpBytes;
   float* const s_wt = reinterpret_cast<float*>(wbase + 2 * L::kStageBytes);
+  const long long n_groups = (n_rays + RPW - 1) / RPW;
   const long long warp0 = static_cast<long long>(blockIdx.x) * kBlkWarps + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * kBlkWarps;
+  const long long total = n_rays * S;   // samples in the whole call
 
-  // shared-memory slot (in elements) of sample i = c*32 + lane: owner lane i/K, position i%K; loop invariant
+  // shared-memory slot (in elements) of chunk element i = c*32 + lane: owner lane i/K, position i%K; loop invariant
   int slot[K];
 #pragma unroll
   for (int c = 0; c < K; ++c) {
     const int i = c * 32 + lane;
     slot[c] = (i / K) * L::KR + (i % K);
   }
-  auto issue = [&](long long ray, int stage) {
+  // elements of group g's chunk that exist: RPW*S, less for the last group / for S < 32K/RPW (generic path, RPW = 1)
+  auto chunk_len = [&](long long g) -> int {
+    const long long rest = total - g * RPW * S;
+    return static_cast<int>(rest < static_cast<long long>(RPW) * S ? rest : static_cast<long long>(RPW) * S);
+  };
+  auto issue = [&](long long g, int stage) {
     float4* s_raw = reinterpret_cast<float4*>(wbase + stage * L::kStageBytes);
     float* s_z = reinterpret_cast<float*>(wbase + stage * L::kStageBytes + L::kRawBytes);
-    const float4* rraw = raw + ray * S;
-    const float* rz = z_vals + ray * S;
+    const float4* rraw = raw + g * RPW * S;
+    const float* rz = z_vals + g * RPW * S;
+    const int n = chunk_len(g);
 #pragma unroll
     for (int c = 0; c < K; ++c) {
       const int i = c * 32 + lane;
-      if (FULL || i < S) {
+      if (i < n) {
         cp_async16(s_raw + slot[c], rraw + i);
         cp_async4(s_z + slot[c], rz + i);
       }
@@ -230,13 +246,16 @@ raw2outputs_blocked_kernel(long long n_rays, int S, const float4* __restrict__ r
   };
 
   int stage = 0;
-  if (warp0 < n_rays) issue(warp0, 0);
+  if (warp0 < n_groups) issue(warp0, 0);
   cp_async_commit();
-  for (long long ray = warp0; ray < n_rays; ray += nwarps, stage ^= 1) {
-    if (ray + nwarps < n_rays) issue(ray + nwarps, stage ^ 1);
+  for (long long g = warp0; g < n_groups; g += nwarps, stage ^= 1) {
+    if (g + nwarps < n_groups) issue(g + nwarps, stage ^ 1);
     cp_async_commit();
-    const float dx = __ldg(rays_d + ray * d_stride), dy = __ldg(rays_d + ray * d_stride + 1),
-                dz = __ldg(rays_d + ray * d_stride + 2);
+    const long long ray = g * RPW + lane / LPR;      // this lane's ray
+    const bool ray_ok = ray < n_rays;
+    const long long rd_ray = ray_ok ? ray : n_rays - 1;
+    const float dx = __ldg(rays_d + rd_ray * d_stride), dy = __ldg(rays_d + rd_ray * d_stride + 1),
+                dz = __ldg(rays_d + rd_ray * d_stride + 2);
     const float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     cp_async_wait<1>();
     __syncwarp();
@@ -250,38 +269,39 @@ raw2outputs_blocked_kernel(long long n_rays, int S, const float4* __restrict__ r
       zr[j] = s_z[j];
     }
     const float z_next_lane = __shfl_down_sync(0xffffffffu, zr[0], 1);
-    const int base = lane * K;
+    const int base = sl * K;      // index of this lane's first sample within its ray
     float alpha[K];
     double excl_in[K];
     double run = 1.0;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const int i = base + j;
+      const bool valid = ray_ok && (FULL || i < S);
       const float zn = (j + 1 < K) ? zr[j + 1] : z_next_lane;
       float dist = (i == S - 1) ? 1e10f : __fsub_rn(zn, zr[j]);
       dist = __fmul_rn(dist, dnorm);
       float sigma = rv[j].w;
-      if (noise != nullptr && (FULL || i < S)) sigma = __fadd_rn(sigma, __ldg(noise + ray * S + i));
+      if (noise != nullptr && valid) sigma = __fadd_rn(sigma, __ldg(noise + ray * S + i));
       const float rl = fmaxf(sigma, 0.0f);
       float a = __fsub_rn(1.0f, expf(__fmul_rn(-rl, dist)));
       if (sigma != sigma) a = sigma;  // relu/exp propagate NaN in the reference
       alpha[j] = a;
       excl_in[j] = run;
-      if (FULL || i < S) run *= static_cast<double>(__fadd_rn(__fsub_rn(1.0f, a), 1e-10f));
+      if (valid) run *= static_cast<double>(__fadd_rn(__fsub_rn(1.0f, a), 1e-10f));
     }
-    double p = run;   // inclusive scan of the lane totals
+    double p = run;   // inclusive scan of the lane totals, segmented by ray
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < LPR; o <<= 1) {
       const double q = shfl_up_f64(p, o);
-      if (lane >= o) p *= q;
+      if (sl >= o) p *= q;
     }
     double excl = shfl_up_f64(p, 1);
-    if (lane == 0) excl = 1.0;
+    if (sl == 0) excl = 1.0;
     float ar = 0.f, ag = 0.f, ab = 0.f, adepth = 0.f, aacc = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const float T = static_cast<float>(excl * excl_in[j]);
-      const bool valid = FULL || base + j < S;
+      const bool valid = ray_ok && (FULL || base + j < S);
       const float w = valid ? __fmul_rn(alpha[j], T) : 0.0f;
       s_wt[lane * L::KZ + j] = w;
       if (valid) {
@@ -295,20 +315,25 @@ raw2outputs_blocked_kernel(long long n_rays, int S, const float4* __restrict__ r
         aacc = __fadd_rn(aacc, w);
       }
     }
-    ar = warp_sum(ar);
-    ag = warp_sum(ag);
-    ab = warp_sum(ab);
-    adepth = warp_sum(adepth);
-    aacc = warp_sum(aacc);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      ar += __shfl_xor_sync(0xffffffffu, ar, o);
+      ag += __shfl_xor_sync(0xffffffffu, ag, o);
+      ab += __shfl_xor_sync(0xffffffffu, ab, o);
+      adepth += __shfl_xor_sync(0xffffffffu, adepth, o);
+      aacc += __shfl_xor_sync(0xffffffffu, aacc, o);
+    }
     __syncwarp();
     if (weights != nullptr) {
+      const int n = chunk_len(g);
+      float* wrow = weights + g * RPW * S;
 #pragma unroll
       for (int c = 0; c < K; ++c) {
         const int i = c * 32 + lane;
-        if (FULL || i < S) weights[ray * S + i] = s_wt[slot[c]];
+        if (i < n) wrow[i] = s_wt[slot[c]];
       }
     }
-    if (lane == 0) {
+    if (sl == 0 && ray_ok) {
       if (white_bkgd) {
         const float bg = __fsub_rn(1.0f, aacc);
         ar = __fadd_rn(ar, bg);
@@ -333,7 +358,7 @@ raw2outputs_blocked_kernel(long long n_rays, int S, const float4* __restrict__ r
   cp_async_wait<0>();
 }
 
-template <int K, bool FULL>
+template <int K, bool FULL, int RPW>
 static int launch_blocked(long long n_rays, int S, const float4* raw4, const float* z_vals, const float* rays_d,
                           long long d_stride, const float* noise, int white_bkgd, float* rgb_map, float* disp_map,
                           float* acc_map, float* weights, float* depth_map, cudaStream_t st) {
@@ -341,15 +366,16 @@ static int launch_blocked(long long n_rays, int S, const float4* raw4, const flo
   static int ctas_per_sm = 0;   // occupancy is a property of the kernel; query once
   if (ctas_per_sm == 0) {
     if (smem > 48 * 1024)
-      R2L_CUDA(cudaFuncSetAttribute(raw2outputs_blocked_kernel<K, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      R2L_CUDA(cudaFuncSetAttribute(raw2outputs_blocked_kernel<K, FULL, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int n = 0;
-    R2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raw2outputs_blocked_kernel<K, FULL>, kBlkWarps * 32, smem));
+    R2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raw2outputs_blocked_kernel<K, FULL, RPW>, kBlkWarps * 32, smem));
     ctas_per_sm = n > 0 ? n : 1;
   }
-  long long blocks = (n_rays + kBlkWarps - 1) / kBlkWarps;
+  const long long n_groups = (n_rays + RPW - 1) / RPW;
+  long long blocks = (n_groups + kBlkWarps - 1) / kBlkWarps;
   const long long cap = static_cast<long long>(sm_count()) * ctas_per_sm;   // one resident wave, grid-stride inside
   if (blocks > cap) blocks = cap;
-  raw2outputs_blocked_kernel<K, FULL><<<static_cast<int>(blocks), kBlkWarps * 32, smem, st>>>(
+  raw2outputs_blocked_kernel<K, FULL, RPW><<<static_cast<int>(blocks), kBlkWarps * 32, smem, st>>>(
       n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map, disp_map, acc_map, weights, depth_map);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
@@ -376,10 +402,17 @@ int r2l_raw2outputs(long long n_rays, int S, const float* raw, const float* z_va
   const float4* raw4 = reinterpret_cast<const float4*>(raw);
 #define R2L_BLOCKED(K)                                                                                              \
   return (S == 32 * K)                                                                                              \
-             ? launch_blocked<K, true>(n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map,       \
-                                       disp_map, acc_map, weights, depth_map, st)                                    \
-             : launch_blocked<K, false>(n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map,      \
-                                        disp_map, acc_map, weights, depth_map, st)
+             ? launch_blocked<K, true, 1>(n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map,    \
+                                          disp_map, acc_map, weights, depth_map, st)                                 \
+             : launch_blocked<K, false, 1>(n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map,   \
+                                           disp_map, acc_map, weights, depth_map, st)
+  // the coarse pass (64 samples): four rays per warp; 128 samples (LLFF fine pass): two
+  if (S == 64)
+    return launch_blocked<8, true, 4>(n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map, disp_map,
+                                      acc_map, weights, depth_map, st);
+  if (S == 128)
+    return launch_blocked<8, true, 2>(n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map, disp_map,
+                                      acc_map, weights, depth_map, st);
   if (S <= 64) R2L_BLOCKED(2);
   if (S <= 128) R2L_BLOCKED(4);
   if (S <= 192) R2L_BLOCKED(6);

@@ -170,3 +170,57 @@ def test_create_data_rand_on_gpu_matches_direct_render(E, O, tmp_path):
                                  split_size=256, fast_rng=True, stream="per_group", seed=3)
         arr = CD.load_shards(str(tmp_path / "f"))
         assert len(w2) == 8 and np.isfinite(arr).all() and arr[:, 6:9].min() >= 0. and arr[:, 6:9].max() <= 1.0 + 1e-5
+
+
+@pytest.mark.gpu
+def test_dataparallel_wrapped_teacher_takes_the_fused_path(E, O, tmp_path):
+    """utils/create_data.py:298-299 ALWAYS wraps teacher_fn / teacher_fine in torch.nn.DataParallel (main.py wraps in
+    MyDataParallel whenever it is not --render_only).  render_rays unwraps them, so the fused kernels run — same
+    frame, bit for bit, and the same number of library kernels — instead of the embed + DataParallel.forward detour
+    (ADVICE r1); a non-fused teacher (precision='fp32') still renders through the reference-style query function."""
+    from efficient_nerf_b200 import create_data as CD
+    sdc, sdf = O.nerf_state_dicts(0)
+    nets = []
+    for sd in (sdc, sdf):
+        n = E.NeRF(8, 256, 63, 27, 5, [4], True, precision="fp16")
+        n.load_state_dict(sd)
+        nets.append(n.cuda().eval())
+    wrapped = [torch.nn.DataParallel(n, device_ids=[0]) for n in nets]
+    H = W = 24
+    focal = O.LEGO["focal"] * W / 400
+    c2w = O.pose_spherical(20., -30., 4.)[:3, :4].cuda()
+    kw = dict(network_query_fn=None, N_samples=64, N_importance=128, perturb=0., white_bkgd=True, use_viewdirs=True,
+              ndc=False, near=2., far=6.)
+    with torch.no_grad():
+        nets[0].packed_handle(), nets[1].packed_handle()      # weight packing launches its own kernels, once
+        k0 = E._lib.kernel_launches()
+        a, _, _, _ = E.render_image(H, W, focal, chunk=32768, c2w=c2w, network_fn=nets[0], network_fine=nets[1], **kw)
+        k1 = E._lib.kernel_launches()
+        b, _, _, _ = E.render_image(H, W, focal, chunk=32768, c2w=c2w, network_fn=wrapped[0], network_fine=wrapped[1], **kw)
+        k2 = E._lib.kernel_launches()
+    assert torch.equal(a, b) and (k2 - k1) == (k1 - k0)
+    # the handles of the wrapped modules were reused, not re-packed per call
+    h0 = nets[0].packed_handle()
+    with torch.no_grad():
+        E.render_image(H, W, focal, chunk=32768, c2w=c2w, network_fn=wrapped[0], network_fine=wrapped[1], **kw)
+    assert nets[0].packed_handle() is h0
+    # DataParallel replicas get their own (empty) handle cache
+    rep = nets[0]._replicate_for_data_parallel()
+    assert rep._packed == {} and rep._packed is not nets[0]._packed
+    # create_data with wrapped teachers and with a teacher that is NOT on the tensor-core path
+    np.random.seed(4)
+    w1 = CD.create_data_rand(wrapped[0], wrapped[1], str(tmp_path / "dp"), 2, H, W, focal, perturb=0., i_save=2,
+                             split_size=128)
+    np.random.seed(4)
+    w2 = CD.create_data_rand(nets[0], nets[1], str(tmp_path / "plain"), 2, H, W, focal, perturb=0., i_save=2,
+                             split_size=128)
+    assert w1 == w2 and np.array_equal(CD.load_shards(str(tmp_path / "dp")), CD.load_shards(str(tmp_path / "plain")))
+    n32 = []
+    for sd in (sdc, sdf):
+        n = E.NeRF(8, 256, 63, 27, 5, [4], True, precision="fp32")
+        n.load_state_dict(sd)
+        n32.append(n.cuda().eval())
+    np.random.seed(4)
+    CD.create_data_rand(n32[0], n32[1], str(tmp_path / "fp32"), 2, H, W, focal, perturb=0., i_save=2, split_size=128)
+    got, ref = CD.load_shards(str(tmp_path / "fp32")), CD.load_shards(str(tmp_path / "plain"))
+    assert got.shape == ref.shape and np.abs(got[:, 6:9] - ref[:, 6:9]).max() <= 2e-3 and np.array_equal(got[:, :6], ref[:, :6])
