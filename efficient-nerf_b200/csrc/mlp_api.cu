@@ -161,6 +161,7 @@ struct Mlp {
   float* vb_ws = nullptr;          // workspace: per-ray view-branch bias [vb_cap rays][128]
   long long vb_cap = 0;
   NerfPpMaps* pp_maps = nullptr;   // tensor maps over wstream_pp
+  NerfHeadW* head_w = nullptr;     // host copy of alpha_linear / rgb_linear weights (kernel parameter, constant bank)
   // far-sample sigma fix-up (nerf_far.cu): fp32 transposed point layers, the flagged-ray list and its counters
   float* far_wt = nullptr;
   int* far_ws = nullptr;           // [0] count of this forward, [1] count of the last finished forward, [2..] ray list
@@ -273,6 +274,7 @@ static void destroy(Mlp* m) {
   if (m->aux) cudaFree(m->aux);
   if (m->dbg_host) cudaFreeHost(m->dbg_host);
   delete m->pp_maps;
+  delete m->head_w;
   delete m->r2l_maps;
   delete m;
 }
@@ -685,6 +687,9 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
   if (rc != R2L_OK) return cleanup(rc);
   cudaError_t e = cudaMemcpyAsync(m->aux + kNerfAuxAlphaW, alpha_w, 256 * 4, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->aux + kNerfAuxRgbW, rgb_w, 384 * 4, cudaMemcpyDeviceToDevice, st);
+  m->head_w = new NerfHeadW();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->head_w->alpha_w, alpha_w, 256 * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->head_w->rgb_w, rgb_w, 384 * 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&m->alpha_b, alpha_b, 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->rgb_b, rgb_b, 12, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -770,7 +775,7 @@ static int nerf_run_mlp(Mlp* m, NerfParams& p, cudaStream_t st) {
     const long long n_units = (n_tiles + 3) / 4;
     const long long max_pairs = sm_count() / 2;
     const int grid = static_cast<int>(2 * (n_units < max_pairs ? n_units : max_pairs));
-    return nerf_mlp_pp_launch(m->bf16, p, *m->pp_maps, grid, st);
+    return nerf_mlp_pp_launch(m->bf16, p, *m->pp_maps, *m->head_w, grid, st);
   }
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   return nerf_mlp_launch(m->bf16, p, grid, st);

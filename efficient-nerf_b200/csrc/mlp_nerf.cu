@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
                 for (int i = 0; i < 32; ++i) {
                   const float w = sAlphaW[col0 + i], h = relu_nan(__uint_as_float(v[i]));
                   sigma_part = fmaf(w, h, sigma_part);
-                  abs_part = fmaf(fabsf(w), h, abs_part);
+                  if ((i & 3) == 0) abs_part = fmaf(fabsf(w), h, abs_part);   // every 4th term: a scale estimate
                 }
               },
               signal);
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kNerfThreads, 1) nerf_mlp_kernel(const NerfPar
           o.w = sigma_part + o1.w + p.alpha_b;
           reinterpret_cast<float4*>(p.raw)[g_row] = o;
           note_nonfinite(p.dbg, o.x + o.y + o.z + o.w, g_row);
-          nerf_far_flag(p, g_row, g_row / p.S, o.w, abs_part + a1);
+          nerf_far_flag(p, g_row, g_row / p.S, o.w, 4.0f * (abs_part + a1));
         }
       }
     }

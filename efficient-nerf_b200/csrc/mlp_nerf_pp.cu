@@ -39,6 +39,7 @@
 #include "common.cuh"
 #include "mlp_params.cuh"
 #include "mlp_tc.cuh"
+#include <type_traits>
 
 namespace r2l {
 
@@ -89,7 +90,7 @@ __device__ __forceinline__ int pp_main_stages(int step) { return step == 0 ? 1 :
 
 template <bool BF16>
 __global__ void __launch_bounds__(kPpThreads, 1)
-nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) {
+nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, const __grid_constant__ NerfHeadW hw) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const sA = smem + kPpOffA;
   uint8_t* const sP = smem + kPpOffP;
@@ -121,8 +122,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
   const int unit_step = static_cast<int>(gridDim.x >> 1);
 
   // ---- one-time setup ----
-  for (int i = threadIdx.x; i < 256; i += kPpThreads) sAlphaW[i] = p.alpha_w[i];
-  for (int i = threadIdx.x; i < 384; i += kPpThreads) sRgbW[i] = p.rgb_w[i];
+  (void)sAlphaW, (void)sRgbW;   // the head weights come from the constant bank now (NerfHeadW)
   write_ones_block<BF16>(sOnes, threadIdx.x, kPpThreads);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPpRing; ++i) {
@@ -365,11 +365,13 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
           }
         }
       }
-    } else if (lane == 0) {
-      mma_issuer(0);
     }
-  } else if (warp == kPpMmaWarp1) {
-    if (rank == 0 && lane == 0) mma_issuer(1);
+  }
+  if (warp == kPpMmaWarp0 || warp == kPpMmaWarp1) {
+    // ONE call site: the issuer code exists once, the tile is a run-time argument (code size, see the epilogue)
+    if (rank == 0 && lane == 0) mma_issuer(warp - kPpMmaWarp0);
+  } else if (warp == kPpProducerWarp) {
+    // (handled above)
   } else if (warp >= 8) {
     // ===================== encoder warpgroup: the single point block, re-encoded before each use =====================
     // Order of uses per unit: T0 step 0, T1 step 0, T0 step 5, T1 step 5.  Before overwriting P the encoder waits for
@@ -441,21 +443,24 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
       tmem_ld32(base, va);
       tmem_ld_wait();
       tmem_ld32(base + 64, vb);
-      f(c0, va);
+      f(std::integral_constant<int, 0>{}, c0, va);
       tmem_ld_wait();
       tmem_ld32(base + 128, va);
-      f(c0 + 64, vb);
+      f(std::integral_constant<int, 1>{}, c0 + 64, vb);
       tmem_ld_wait();
       tmem_ld32(base + 192, vb);
-      f(c0 + 128, va);
+      f(std::integral_constant<int, 2>{}, c0 + 128, va);
       tmem_ld_wait();
-      f(c0 + 192, vb);
+      f(std::integral_constant<int, 3>{}, c0 + 192, vb);
     };
     for (int unit = unit0; unit < n_units; unit += unit_step, ++eit) {
-      float sigma_part[2] = {0.0f, 0.0f};
-      float abs_part[2] = {0.0f, 0.0f};   // sum |w_a| relu(h7): scale of the far-sample guard band (nerf_far.cu)
+      float sigma_part0 = 0.0f, sigma_part1 = 0.0f;   // per tile (scalars: t is a run-time index)
+      float abs_part0 = 0.0f, abs_part1 = 0.0f;       // sum |w_a| relu(h7): scale of the far-sample guard band (nerf_far.cu)
       for (int step = 0; step < 10; ++step) {
-#pragma unroll
+        // t is a RUN-TIME loop variable on purpose: unrolled, the epilogue code of both tiles (4 for_pieces variants
+        // x 2) made the kernel 131 KB of SASS; A/B on one box showed every step slowing down once the kernel grew
+        // past ~128 KB (instruction cache), so code size is kept in check here
+#pragma unroll 1
         for (int t = 0; t < 2; ++t) {
           uint8_t* const a_row = sA + t * kABufBytes + row * 16;
           wait_d(t, 300 + step * 2 + t);
@@ -463,23 +468,28 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
           if (step < 9) {
             if (step == 7) {
               float sp = 0.0f, sa = 0.0f;
-              for_pieces(t, [&](uint32_t col0, uint32_t (&v)[32]) {
-                store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
+              // alpha_linear on the fp32 accumulators; the weight index is a compile-time constant per (WG, piece, i)
+              auto sigma_dot = [&](auto wg_c) {
+                constexpr int WG = decltype(wg_c)::value;
+                for_pieces(t, [&](auto piece_c, uint32_t col0, uint32_t (&v)[32]) {
+                  constexpr int C0 = 32 * WG + 64 * decltype(piece_c)::value;
+                  store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float w = sAlphaW[col0 + i], h = relu_nan(__uint_as_float(v[i]));
-                  sp = fmaf(w, h, sp);
-                  sa = fmaf(fabsf(w), h, sa);
-                }
-              });
-              sigma_part[t] = sp;
-              abs_part[t] = sa;
+                  for (int i = 0; i < 32; ++i) {
+                    const float h = relu_nan(__uint_as_float(v[i]));
+                    sp = fmaf(hw.alpha_w[C0 + i], h, sp);
+                    if ((i & 3) == 0) sa = fmaf(fabsf(hw.alpha_w[C0 + i]), h, sa);   // every 4th term: a scale estimate
+                  }
+                });
+              };
+              if (wg == 0) sigma_dot(std::integral_constant<int, 0>{}); else sigma_dot(std::integral_constant<int, 1>{});
+              if (t == 0) sigma_part0 = sp, abs_part0 = sa; else sigma_part1 = sp, abs_part1 = sa;
             } else if (step == 8) {
-              for_pieces(t, [&](uint32_t col0, uint32_t (&v)[32]) {
+              for_pieces(t, [&](auto, uint32_t col0, uint32_t (&v)[32]) {
                 store_sub<BF16, false>(v, a_row + (col0 >> 5) * kSubBytes);
               });
             } else {
-              for_pieces(t, [&](uint32_t col0, uint32_t (&v)[32]) {
+              for_pieces(t, [&](auto, uint32_t col0, uint32_t (&v)[32]) {
                 store_sub<BF16, true>(v, a_row + (col0 >> 5) * kSubBytes);
               });
             }
@@ -499,36 +509,44 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
               tmem_ld32(lane_taddr + 256 * t + 64 + 32 * wg, vb);
               tmem_ld_wait();
               warp_arrive<true>(&a_done[t], lane);   // D[t] is drained: the next unit's step 0 may overwrite it
+              // rgb_linear on relu(accumulator + per-ray view bias); weights from the constant bank (static indices)
+              auto rgb_dot = [&](auto wg_c) {
+                constexpr int WG = decltype(wg_c)::value;
 #pragma unroll
-              for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 bb = __ldg(vb4 + 8 * wg + i4);
-                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                for (int i4 = 0; i4 < 8; ++i4) {
+                  const float4 bb = __ldg(vb4 + 8 * WG + i4);
+                  const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int n = 32 * wg + 4 * i4 + k;
-                  const float x = relu_nan(__uint_as_float(va[4 * i4 + k]) + bv[k]);
-                  r = fmaf(sRgbW[n], x, r);
-                  gch = fmaf(sRgbW[128 + n], x, gch);
-                  b = fmaf(sRgbW[256 + n], x, b);
+                  for (int k = 0; k < 4; ++k) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int n = 32 * WG + 4 * i4 + k;
+                    const float x = relu_nan(__uint_as_float(va[4 * i4 + k]) + bv[k]);
+                    r = fmaf(hw.rgb_w[n], x, r);
+                    gch = fmaf(hw.rgb_w[128 + n], x, gch);
+                    b = fmaf(hw.rgb_w[256 + n], x, b);
+                  }
                 }
-              }
 #pragma unroll
-              for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 bb = __ldg(vb4 + 16 + 8 * wg + i4);
-                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                for (int i4 = 0; i4 < 8; ++i4) {
+                  const float4 bb = __ldg(vb4 + 16 + 8 * WG + i4);
+                  const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int n = 64 + 32 * wg + 4 * i4 + k;
-                  const float x = relu_nan(__uint_as_float(vb[4 * i4 + k]) + bv[k]);
-                  r = fmaf(sRgbW[n], x, r);
-                  gch = fmaf(sRgbW[128 + n], x, gch);
-                  b = fmaf(sRgbW[256 + n], x, b);
+                  for (int k = 0; k < 4; ++k) {
+                    const int n = 64 + 32 * WG + 4 * i4 + k;
+                    const float x = relu_nan(__uint_as_float(vb[4 * i4 + k]) + bv[k]);
+                    r = fmaf(hw.rgb_w[n], x, r);
+                    gch = fmaf(hw.rgb_w[128 + n], x, gch);
+                    b = fmaf(hw.rgb_w[256 + n], x, b);
+                  }
                 }
-              }
+              };
+              if (wg == 0) rgb_dot(std::integral_constant<int, 0>{}); else rgb_dot(std::integral_constant<int, 1>{});
             }
+            const float sigma_mine = t == 0 ? sigma_part0 : sigma_part1, abs_mine = t == 0 ? abs_part0 : abs_part1;
             if (wg == 1) {
-              sPart[row] = make_float4(r, gch, b, sigma_part[t]);
-              sAbs[row] = abs_part[t];
+              sPart[row] = make_float4(r, gch, b, sigma_mine);
+              sAbs[row] = abs_mine;
               named_bar_arrive(1, 256);
               named_bar_sync(2, 256);   // WG0 has consumed sPart
             } else {
@@ -541,10 +559,10 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps) 
                 o.x = r + o1.x + p.rgb_b[0];
                 o.y = gch + o1.y + p.rgb_b[1];
                 o.z = b + o1.z + p.rgb_b[2];
-                o.w = sigma_part[t] + o1.w + p.alpha_b;
+                o.w = sigma_mine + o1.w + p.alpha_b;
                 reinterpret_cast<float4*>(p.raw)[g_row] = o;
                 note_nonfinite(p.dbg, o.x + o.y + o.z + o.w, g_row);
-                nerf_far_flag(p, g_row, ray, o.w, abs_part[t] + a1);
+                nerf_far_flag(p, g_row, ray, o.w, 4.0f * (abs_mine + a1));
               }
             }
           }
@@ -617,7 +635,7 @@ nerf_view_bias_kernel(long long n_rays, const float* __restrict__ viewdirs, long
 }
 
 template <bool BF16>
-int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, int grid, cudaStream_t st) {
+int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid, cudaStream_t st) {
   R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -631,14 +649,15 @@ int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, int grid, cudaSt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16>, p, maps));
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16>, p, maps, hw));
   count_launch();
   return R2L_OK;
 }
 
 // grid must be even (CTA pairs); weights packed in the pair layout WITHOUT the view stage (mlp_api.cu)
-int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, int grid, cudaStream_t st) {
-  return bf16 ? launch_nerf_pp<true>(p, maps, grid, st) : launch_nerf_pp<false>(p, maps, grid, st);
+int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid,
+                       cudaStream_t st) {
+  return bf16 ? launch_nerf_pp<true>(p, maps, hw, grid, st) : launch_nerf_pp<false>(p, maps, hw, grid, st);
 }
 
 int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,

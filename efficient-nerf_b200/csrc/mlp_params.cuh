@@ -52,6 +52,16 @@ __device__ __forceinline__ void nerf_far_flag(const NerfParams& p, long long g_r
   }
 }
 
+// fp32 weights of the two heads that run on CUDA cores (alpha_linear [256], rgb_linear [3][128]), passed BY VALUE as a
+// kernel parameter: with compile-time indices every FFMA takes its weight straight from the constant bank
+// (c[0x0][imm]) — no load instruction, no register, no shared-memory traffic under the MMAs' operand reads.  With the
+// weights in shared memory the rgb dot product made the last epilogue 2800 cycles long (in-kernel trace: 1850 of them
+// in 48 LDS.128 + 192 FFMA per thread, latency-bound because the 128-register budget leaves nothing to hoist loads).
+struct NerfHeadW {
+  float alpha_w[256];
+  float rgb_w[384];
+};
+
 // Tensor maps over the ping-pong kernel's stage stream seen as rows of 256 x 16-bit (512 bytes): boxes of 32 / 16 / 8
 // rows = one CTA's half of a K=64 stage (N 256), of a K=64 stage (N 128), of a bias stage
 struct NerfPpMaps {
@@ -104,7 +114,8 @@ struct R2lPairMaps {
 };
 int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, const R2lPairMaps* maps, int grid, cudaStream_t st);
 // CTA-pair "ping-pong" NeRF kernel (mlp_nerf_pp.cu): grid even, pair-layout stream without the view stage
-int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, int grid, cudaStream_t st);
+int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid,
+                       cudaStream_t st);
 int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,
                           const float* wvd, const float* bv, float* vb, cudaStream_t st);
 

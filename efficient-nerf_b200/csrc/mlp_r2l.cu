@@ -50,7 +50,10 @@ static_assert(kR2lOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
 // (M = 256): each CTA streams only ITS N-half of every weight stage (half the L2 -> shared-memory traffic and half
 // the B-operand shared-memory reads per SM), the leader CTA's MMA thread issues for both, and all "operand ready"
 // barriers live in the leader and collect the warps of both CTAs; MMA completion is multicast to both.
-template <bool BF16, bool PAIR>
+// DBG = true: the instantiation behind r2l_resmlp_debug_head (tests only) that also dumps the head layer's accumulators.
+// Inside the unrolled head epilogue that hook was 1500 SASS instructions (24 KB of a 130 KB kernel) — and these
+// kernels are sensitive to code size (see mlp_nerf_pp.cu) — so the production instantiation does not contain it.
+template <bool BF16, bool PAIR, bool DBG>
 __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams p, const __grid_constant__ R2lPairMaps maps) {
   constexpr int kRing = PAIR ? 8 : 4;
   constexpr int kBiasRing = PAIR ? 4 : 2;
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float x = relu_nan(__uint_as_float(v[i]));
-              if (p.dbg_head_acc != nullptr) {   // debug hook: raw accumulator (bias included) and x0
+              if (DBG && p.dbg_head_acc != nullptr) {   // debug hook: raw accumulator (bias included) and x0
                 const long long o = (static_cast<long long>(tile) * kTileM + row) * 256 + col0 + i;
                 p.dbg_head_acc[o] = __uint_as_float(v[i]);
                 p.dbg_head_x0[o] = x;
@@ -477,9 +480,9 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
   }
 }
 
-template <bool BF16, bool PAIR>
-int launch_r2l(const R2lParams& p, const R2lPairMaps& maps, int grid, cudaStream_t st) {
-  R2L_CUDA(cudaFuncSetAttribute(r2l_mlp_kernel<BF16, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <bool BF16, bool PAIR, bool DBG>
+int launch_r2l_(const R2lParams& p, const R2lPairMaps& maps, int grid, cudaStream_t st) {
+  R2L_CUDA(cudaFuncSetAttribute(r2l_mlp_kernel<BF16, PAIR, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kR2lSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -493,9 +496,14 @@ int launch_r2l(const R2lParams& p, const R2lPairMaps& maps, int grid, cudaStream
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  R2L_CUDA(cudaLaunchKernelEx(&cfg, r2l_mlp_kernel<BF16, PAIR>, p, maps));
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, r2l_mlp_kernel<BF16, PAIR, DBG>, p, maps));
   count_launch();
   return R2L_OK;
+}
+template <bool BF16, bool PAIR>
+int launch_r2l(const R2lParams& p, const R2lPairMaps& maps, int grid, cudaStream_t st) {
+  return p.dbg_head_acc != nullptr ? launch_r2l_<BF16, PAIR, true>(p, maps, grid, st)
+                                   : launch_r2l_<BF16, PAIR, false>(p, maps, grid, st);
 }
 
 // pair: CTA-pair mode (the weights must have been packed in the pair layout); grid is then a multiple of 2

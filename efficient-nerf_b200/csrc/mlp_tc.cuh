@@ -115,12 +115,19 @@ __device__ __forceinline__ void mbar_wait_x(uint64_t* bar, uint32_t parity, Debu
 // sin/cos of (x, 2x, 4x, ..., 2^(L-1) x) for L <= 10: accurate sincosf at octaves 0 and 5, exact double-angle
 // recurrence in between (4 doublings amplify the ~1 ulp seed error to < 2e-6, far below the 16-bit operand
 // rounding).  The reference computes sin(x * 2^f) with the product exact in fp32 (helpers:41-56).
+// (out of line: the accurate sincosf carries a Payne-Hanek slow path of ~1.5 KB of SASS per inlined copy)
+static __device__ __noinline__ float2 sincos_accurate(float x) {
+  float s, c;
+  sincosf(x, &s, &c);
+  return make_float2(s, c);
+}
 template <int L>
 __device__ __forceinline__ void sincos_octaves(float x, float (&s)[L], float (&c)[L]) {
 #pragma unroll
   for (int f = 0; f < L; ++f) {
     if (f == 0 || f == 5) {
-      sincosf(x * static_cast<float>(1 << f), &s[f], &c[f]);
+      const float2 sc = sincos_accurate(x * static_cast<float>(1 << f));
+      s[f] = sc.x, c[f] = sc.y;
     } else {
       const float t = 2.0f * s[f - 1];
       s[f] = t * c[f - 1];
@@ -219,16 +226,7 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t par_a, uint
   while (!(a && b)) {
     if (!a) a = tw(bar_a, par_a);
     if (!b) b = tw(bar_b, par_b);
-    if (++spins > R2L_WATCHDOG_SPINS) {
-      if (dbg != nullptr && atomicCAS(&dbg->flag, 0u, 1u) == 0u) {
-        dbg->block = blockIdx.x;
-        dbg->thread = threadIdx.x;
-        dbg->barrier_id = id + (a ? 1000u : 0u);
-        dbg->parity = par_a | (par_b << 1);
-        __threadfence_system();
-      }
-      __trap();
-    }
+    if (++spins > R2L_WATCHDOG_SPINS) mbar_watchdog_fire(dbg, id + (a ? 1000u : 0u), par_a | (par_b << 1));
   }
 }
 

@@ -94,20 +94,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Wait for the phase with the given parity to complete.  `id` only feeds the watchdog.
 // `patience` multiplies the watchdog limit: producers wait with more patience than consumers, so that the record
 // names the consumer that is really stuck rather than the producer starved behind it.
+// The watchdog's slow path is ONE out-of-line function: inlined at every wait site it cost ~0.3 KB of SASS each, and
+// the fused MLP kernels are sensitive to code size (a kernel that grows past ~128 KB slows down in every phase:
+// measured A/B on one box, see mlp_nerf_pp.cu).
+static __device__ __noinline__ void mbar_watchdog_fire(DebugBuf* dbg, uint32_t id, uint32_t parity) {
+  if (dbg != nullptr && atomicCAS(&dbg->flag, 0u, 1u) == 0u) {
+    dbg->block = blockIdx.x;
+    dbg->thread = threadIdx.x;
+    dbg->barrier_id = id;
+    dbg->parity = parity;
+    __threadfence_system();
+  }
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugBuf* dbg, uint32_t id,
                                           uint32_t patience = 1) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > R2L_WATCHDOG_SPINS * patience) {
-      if (dbg != nullptr && atomicCAS(&dbg->flag, 0u, 1u) == 0u) {
-        dbg->block = blockIdx.x;
-        dbg->thread = threadIdx.x;
-        dbg->barrier_id = id;
-        dbg->parity = parity;
-        __threadfence_system();
-      }
-      __trap();
-    }
+    if (++spins > R2L_WATCHDOG_SPINS * patience) mbar_watchdog_fire(dbg, id, parity);
   }
 }
 
