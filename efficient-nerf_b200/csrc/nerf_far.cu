@@ -15,9 +15,10 @@
 // reference's K order then + bias (linear_fp32.cu) — so the patched sigma is BIT-IDENTICAL to that path's (tested),
 // which is itself within 1e-5 of the torch-CPU reference.
 //
-// Work per flagged point: 0.98 MFLOP fp32; weights (transposed fp32 copy, 1.96 MB per net) stream from L2.  One block =
-// 256 threads = the 256 output neurons of a layer, 8 flagged rays at a time (8 accumulators per thread, the group's
-// activations broadcast from shared memory), grid = 2 blocks per SM looping over the list.
+// Work per flagged point: 0.98 MFLOP fp32; weights (transposed fp32 copy, 1.96 MB per net) stream from L2 through a
+// cp.async ring.  One block = 256 threads = the 256 output neurons of a layer, 8 flagged rays at a time (8
+// accumulators per thread, the group's activations broadcast from shared memory), grid = 2 blocks per SM looping
+// over the list.
 #include "common.cuh"
 #include "mlp_params.cuh"
 
@@ -47,11 +48,25 @@ __global__ void far_transpose_kernel(const float* __restrict__ W, int K, float* 
   Wt[idx] = W[n * K + k];
 }
 
+// The whole net is one sequence of 1918 weight rows of 1 KiB.  With a handful of flagged rays per launch nothing hides
+// the L2 latency of a per-thread weight load (a first version with loads issued from the FMA loop cost 0.4 ms for 30
+// rays: ~480 dependent round trips), so the rows are streamed through a 4-deep cp.async ring of 16-row chunks that runs
+// ahead ACROSS layer boundaries; the FMA loop reads weights and activations from shared memory only.
+constexpr int kFarChunk = 16;                       // rows per chunk (16 KiB)
+constexpr int kFarStages = 4;
+constexpr int kFarRingBytes = kFarStages * kFarChunk * 256 * 4;
+
+__device__ __forceinline__ void far_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(256)
 nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __restrict__ list,
                       const int* __restrict__ count, int cap, int* __restrict__ stats, const float* __restrict__ rays_o,
                       long long o_stride, const float* __restrict__ rays_d, long long d_stride,
                       const float* __restrict__ z_vals, int S, float* __restrict__ raw) {
+  extern __shared__ __align__(16) float s_ring[];      // [kFarStages][kFarChunk][256]
   __shared__ __align__(16) float s_emb[64][kFarG];    // embedded point, reference order (63 used)
   __shared__ __align__(16) float s_h[2][256][kFarG];  // hidden activations, ping-pong
   __shared__ float s_pt[kFarG][3];
@@ -59,9 +74,20 @@ nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __
   if (n > cap) n = cap;
   if (blockIdx.x == 0 && threadIdx.x == 0) stats[0] = *count;   // flagged by the last forward (may exceed cap)
   const int tid = threadIdx.x;
+  constexpr int n_chunks = (kFarRows + kFarChunk - 1) / kFarChunk;   // 120 (the last one holds 14 rows)
+  auto issue = [&](int c) {   // chunk c -> ring slot c % kFarStages (rows past the end read the bias block: harmless)
+    if (c < n_chunks) {
+      float* dst = s_ring + (c % kFarStages) * kFarChunk * 256;
+      const float* src = Wt + static_cast<size_t>(c) * kFarChunk * 256;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) far_cp16(dst + (tid + 256 * i) * 4, src + (tid + 256 * i) * 4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   for (int g0 = blockIdx.x * kFarG; g0 < n; g0 += gridDim.x * kFarG) {
     const int ng = min(kFarG, n - g0);
     __syncthreads();
+    for (int c = 0; c < kFarStages - 1; ++c) issue(c);
     if (tid < kFarG * 3) {
       const int g = tid / 3, c = tid % 3;
       float v = 0.0f;
@@ -81,62 +107,83 @@ nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __
       s_emb[3 + 6 * f + c][g] = s;
       s_emb[3 + 6 * f + 3 + c][g] = co;
     }
-    __syncthreads();
-    int cur = 0;
-    for (int l = 0; l < 8; ++l) {
-      float acc[kFarG];
+    // rows are consumed in order; `l` / `k` = layer and input index of the current row
+    int l = 0, k = 0, cur = 0;
+    float acc[kFarG];
 #pragma unroll
-      for (int g = 0; g < kFarG; ++g) acc[g] = 0.0f;
-      const float* w = Wt + static_cast<size_t>(far_layer_row0(l)) * 256 + tid;
-      auto run = [&](const float (*x)[kFarG], int K) {
-        int k = 0;
-        for (; k + 4 <= K; k += 4) {   // 4 weight loads in flight
-          const float w0 = __ldg(w + (k + 0) * 256), w1 = __ldg(w + (k + 1) * 256);
-          const float w2 = __ldg(w + (k + 2) * 256), w3 = __ldg(w + (k + 3) * 256);
-          const float wk[4] = {w0, w1, w2, w3};
+    for (int g = 0; g < kFarG; ++g) acc[g] = 0.0f;
+    for (int c = 0; c < n_chunks; ++c) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kFarStages - 2) : "memory");   // chunk c has landed (this thread's part)
+      __syncthreads();            // ... everybody's part, and everybody is done with chunk c - 1 (and with s_emb / s_h writes)
+      issue(c + kFarStages - 1);  // into the slot chunk c - 1 occupied
+      const float* wrow = s_ring + (c % kFarStages) * kFarChunk * 256 + tid;
+      const int rows = min(kFarChunk, kFarRows - c * kFarChunk);
+      for (int r = 0; r < rows;) {
+        // input of this row: layer 0 and the first 63 rows of the skip layer read the embedding (cat[input_pts, h])
+        const bool from_emb = (l == 0) || (l == 5 && k < 63);
+        const float* x = from_emb ? &s_emb[k][0] : &s_h[cur][l == 5 ? k - 63 : k][0];
+        const int k_end = (l == 5 && k < 63) ? 63 : far_layer_k(l);   // rows left before the input source changes
+        if (r + 4 <= rows && k + 4 <= k_end) {
+          // four rows at a time, every shared-memory load issued before the first FMA (same FMA order per accumulator)
+          float wv[4];
+          float4 xa[4], xb[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 xa = *reinterpret_cast<const float4*>(&x[k + j][0]);
-            const float4 xb = *reinterpret_cast<const float4*>(&x[k + j][4]);
-            acc[0] = fmaf(xa.x, wk[j], acc[0]);
-            acc[1] = fmaf(xa.y, wk[j], acc[1]);
-            acc[2] = fmaf(xa.z, wk[j], acc[2]);
-            acc[3] = fmaf(xa.w, wk[j], acc[3]);
-            acc[4] = fmaf(xb.x, wk[j], acc[4]);
-            acc[5] = fmaf(xb.y, wk[j], acc[5]);
-            acc[6] = fmaf(xb.z, wk[j], acc[6]);
-            acc[7] = fmaf(xb.w, wk[j], acc[7]);
+            wv[j] = wrow[(r + j) * 256];
+            xa[j] = *reinterpret_cast<const float4*>(x + j * kFarG);
+            xb[j] = *reinterpret_cast<const float4*>(x + j * kFarG + 4);
           }
-        }
-        for (; k < K; ++k) {
-          const float wv = __ldg(w + k * 256);
 #pragma unroll
-          for (int g = 0; g < kFarG; ++g) acc[g] = fmaf(x[k][g], wv, acc[g]);
+          for (int j = 0; j < 4; ++j) {
+            acc[0] = fmaf(xa[j].x, wv[j], acc[0]);
+            acc[1] = fmaf(xa[j].y, wv[j], acc[1]);
+            acc[2] = fmaf(xa[j].z, wv[j], acc[2]);
+            acc[3] = fmaf(xa[j].w, wv[j], acc[3]);
+            acc[4] = fmaf(xb[j].x, wv[j], acc[4]);
+            acc[5] = fmaf(xb[j].y, wv[j], acc[5]);
+            acc[6] = fmaf(xb[j].z, wv[j], acc[6]);
+            acc[7] = fmaf(xb[j].w, wv[j], acc[7]);
+          }
+          r += 4, k += 4;
+          if (k != far_layer_k(l)) continue;
+          --k;   // fall through to the layer-end handling below (which increments k again)
+        } else {
+          const float wv = wrow[r * 256];
+          const float4 xa = *reinterpret_cast<const float4*>(x);
+          const float4 xb = *reinterpret_cast<const float4*>(x + 4);
+          acc[0] = fmaf(xa.x, wv, acc[0]);
+          acc[1] = fmaf(xa.y, wv, acc[1]);
+          acc[2] = fmaf(xa.z, wv, acc[2]);
+          acc[3] = fmaf(xa.w, wv, acc[3]);
+          acc[4] = fmaf(xb.x, wv, acc[4]);
+          acc[5] = fmaf(xb.y, wv, acc[5]);
+          acc[6] = fmaf(xb.z, wv, acc[6]);
+          acc[7] = fmaf(xb.w, wv, acc[7]);
+          ++r;
         }
-        w += static_cast<size_t>(K) * 256;
-      };
-      if (l == 0) {
-        run(s_emb, 63);
-      } else if (l == 5) {   // skip layer: cat[input_pts, h]  (model/nerf_raybased.py:381-385)
-        run(s_emb, 63);
-        run(s_h[cur], 256);
-      } else {
-        run(s_h[cur], 256);
+        if (++k == far_layer_k(l)) {   // layer complete: bias, relu, hand the activations to the next layer
+          const float bl = __ldg(Wt + kFarBiasOff + l * 256 + tid);
+          const int nxt = (l == 0) ? 0 : (cur ^ 1);
+          __syncthreads();             // every thread has finished reading s_h[cur] ... (uniform branch)
+#pragma unroll
+          for (int g = 0; g < kFarG; ++g) {
+            s_h[nxt][tid][g] = fmaxf(acc[g] + bl, 0.0f);
+            acc[g] = 0.0f;
+          }
+          cur = nxt;
+          ++l, k = 0;
+          __syncthreads();             // ... and sees the new layer's input
+        }
       }
-      const float b = __ldg(Wt + kFarBiasOff + l * 256 + tid);
-      float* out = &s_h[l == 0 ? 0 : (cur ^ 1)][tid][0];
-#pragma unroll
-      for (int g = 0; g < kFarG; ++g) out[g] = fmaxf(acc[g] + b, 0.0f);
-      if (l > 0) cur ^= 1;
-      __syncthreads();
     }
     if (tid < ng) {   // alpha_linear: sequential k, like the fp32 path's K loop
-      float acc = 0.0f;
+      float a = 0.0f;
       const float* aw = Wt + kFarAlphaOff;
-      for (int k = 0; k < 256; ++k) acc = fmaf(s_h[cur][k][tid], __ldg(aw + k), acc);
+      for (int kk = 0; kk < 256; ++kk) a = fmaf(s_h[cur][kk][tid], __ldg(aw + kk), a);
       const long long ray = list[g0 + tid];
-      raw[(ray * S + (S - 1)) * 4 + 3] = acc + alpha_b;
+      raw[(ray * S + (S - 1)) * 4 + 3] = a + alpha_b;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 }
 
@@ -157,7 +204,12 @@ size_t nerf_far_weight_bytes() { return sizeof(float) * kFarFloats; }
 int nerf_far_fixup_launch(const float* Wt, float alpha_b, const int* list, const int* count, int cap, int* stats,
                           const NerfParams& p, cudaStream_t st) {
   const int grid = 2 * sm_count();
-  nerf_far_fixup_kernel<<<grid, 256, 0, st>>>(Wt, alpha_b, list, count, cap, stats, p.rays_o, p.o_stride, p.rays_d,
+  static bool attr_set = false;
+  if (!attr_set) {
+    R2L_CUDA(cudaFuncSetAttribute(nerf_far_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFarRingBytes));
+    attr_set = true;
+  }
+  nerf_far_fixup_kernel<<<grid, 256, kFarRingBytes, st>>>(Wt, alpha_b, list, count, cap, stats, p.rays_o, p.o_stride, p.rays_d,
                                              p.d_stride, p.z_vals, p.S, p.raw);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
