@@ -88,7 +88,9 @@ static_assert(kPpOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
 
 __device__ __forceinline__ int pp_main_stages(int step) { return step == 0 ? 1 : (step == 5 ? 5 : 4); }
 
-template <bool BF16>
+// PROF = true: the instantiation behind r2l_nerf_profile (in-kernel cycle counters / event timeline); the production
+// kernel carries none of that code (code size, see the epilogue).
+template <bool BF16, bool PROF>
 __global__ void __launch_bounds__(kPpThreads, 1)
 nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, const __grid_constant__ NerfHeadW hw) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -150,7 +152,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   // debug timeline (r2l_nerf_profile with R2L_PROF_MODE=5): CTA 0 records (tag, clock) pairs for its 4th unit
-  const bool tracing = p.prof != nullptr && p.prof_mode == 5 && blockIdx.x == 0;
+  const bool tracing = PROF && p.prof != nullptr && p.prof_mode == 5 && blockIdx.x == 0;
   // (the prof buffer must hold 3 x 400 + 8 int64 in this mode; each role appends to its own region, no atomics)
   int n_trace = 0;
   auto trace = [&](uint32_t it_, long long tag) {
@@ -179,7 +181,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
     uint32_t par_done = 0;         // parity of the next a_done[t] phase
     uint32_t par_p = 0;            // parity of the next p_ready[t] phase
     uint32_t n_turn = 0;           // turns taken so far
-    const bool prof = p.prof != nullptr && p.prof_mode != 5;
+    const bool prof = PROF && p.prof != nullptr && p.prof_mode != 5;
     long long t_a = 0, t_w = 0, t_p = 0, t_b = 0;
     const long long t_start = prof ? clock64() : 0;
     auto next_w = [&]() -> uint32_t {
@@ -423,7 +425,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
     const int wg = warp >> 2;                       // owns the 32-column pieces wg, wg+2, wg+4, wg+6
     const int row = (warp & 3) * 32 + lane;         // tile row == TMEM lane
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0 && p.prof_mode != 5;
+    const bool prof = PROF && p.prof != nullptr && (threadIdx.x & 127) == 0 && p.prof_mode != 5;
     uint32_t eit = 0;
     long long t_d = 0;
     const long long t_start = prof ? clock64() : 0;
@@ -634,9 +636,9 @@ nerf_view_bias_kernel(long long n_rays, const float* __restrict__ viewdirs, long
   }
 }
 
-template <bool BF16>
+template <bool BF16, bool PROF>
 int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid, cudaStream_t st) {
-  R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kPpThreads);
@@ -649,7 +651,7 @@ int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16>, p, maps, hw));
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16, PROF>, p, maps, hw));
   count_launch();
   return R2L_OK;
 }
@@ -657,7 +659,9 @@ int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW&
 // grid must be even (CTA pairs); weights packed in the pair layout WITHOUT the view stage (mlp_api.cu)
 int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid,
                        cudaStream_t st) {
-  return bf16 ? launch_nerf_pp<true>(p, maps, hw, grid, st) : launch_nerf_pp<false>(p, maps, hw, grid, st);
+  if (p.prof != nullptr)
+    return bf16 ? launch_nerf_pp<true, true>(p, maps, hw, grid, st) : launch_nerf_pp<false, true>(p, maps, hw, grid, st);
+  return bf16 ? launch_nerf_pp<true, false>(p, maps, hw, grid, st) : launch_nerf_pp<false, false>(p, maps, hw, grid, st);
 }
 
 int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,

@@ -50,7 +50,8 @@ static_assert(kR2lOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
 // (M = 256): each CTA streams only ITS N-half of every weight stage (half the L2 -> shared-memory traffic and half
 // the B-operand shared-memory reads per SM), the leader CTA's MMA thread issues for both, and all "operand ready"
 // barriers live in the leader and collect the warps of both CTAs; MMA completion is multicast to both.
-// DBG = true: the instantiation behind r2l_resmlp_debug_head (tests only) that also dumps the head layer's accumulators.
+// DBG = true: the instantiation behind r2l_resmlp_debug_head / r2l_resmlp_profile (tests, profiling) that also dumps
+// the head layer's accumulators and keeps the in-kernel cycle counters.
 // Inside the unrolled head epilogue that hook was 1500 SASS instructions (24 KB of a 130 KB kernel) — and these
 // kernels are sensitive to code size (see mlp_nerf_pp.cu) — so the production instantiation does not contain it.
 template <bool BF16, bool PAIR, bool DBG>
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       const uint32_t aBiasRing = smem_u32(sBiasRing);
       uint32_t g = 0, gb = 0;
       uint32_t par_a = 0;   // parity of the a_ready phase the next layer / chunk waits for (all 4 groups in step)
-      const bool prof = p.prof != nullptr;
+      const bool prof = DBG && p.prof != nullptr;
       long long t_a = 0, t_w = 0;
       const long long t_start = prof ? clock64() : 0;
       // the K=16 bias step of a layer (needs no activations)
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
     const int wg = warp >> 2;                    // owns the 32-column pieces wg, wg+2, wg+4, wg+6
     const int row = (warp & 3) * 32 + lane;      // tile row == TMEM lane
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
+    const bool prof = DBG && p.prof != nullptr && (threadIdx.x & 127) == 0;
     long long t_d = 0, t_enc = 0;
     const long long t_start = prof ? clock64() : 0;
     uint32_t par_d = 0;      // bit dbuf: parity of the next d_full phase
@@ -502,7 +503,7 @@ int launch_r2l_(const R2lParams& p, const R2lPairMaps& maps, int grid, cudaStrea
 }
 template <bool BF16, bool PAIR>
 int launch_r2l(const R2lParams& p, const R2lPairMaps& maps, int grid, cudaStream_t st) {
-  return p.dbg_head_acc != nullptr ? launch_r2l_<BF16, PAIR, true>(p, maps, grid, st)
+  return (p.dbg_head_acc != nullptr || p.prof != nullptr) ? launch_r2l_<BF16, PAIR, true>(p, maps, grid, st)
                                    : launch_r2l_<BF16, PAIR, false>(p, maps, grid, st);
 }
 
