@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libr2l_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
 
-SOURCES = ["rays.cu", "embed.cu", "composite.cu", "sample_pdf.cu", "linear_fp32.cu", "metrics.cu", "flip.cu", "mlp_nerf.cu", "mlp_nerf_pp.cu", "mlp_r2l.cu", "nerf_far.cu",
+SOURCES = ["rays.cu", "embed.cu", "composite.cu", "sample_pdf.cu", "linear_fp32.cu", "metrics.cu", "flip.cu", "mlp_nerf.cu", "mlp_nerf_pp.cu", "mlp_r2l.cu", "mlp_r2l_pp.cu", "nerf_far.cu",
            "mlp_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

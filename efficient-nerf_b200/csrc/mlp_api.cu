@@ -171,6 +171,7 @@ struct Mlp {
   R2lPairMaps* r2l_maps = nullptr; // R2L pair mode: tensor maps over wstream
   // R2L
   int n_points = 0, n_blocks = 0, sigmoid_out = 1, outer_skip = 1;
+  int r2l_pp = 0;                  // 1: ping-pong kernel (needs pair == 1)
   float b_tail[3] = {0.f, 0.f, 0.f};
 };
 
@@ -212,6 +213,16 @@ static int nerf_pp_default() {
 static int pair_mode_default() {
   const char* e = getenv("R2L_PAIR");
   return (e != nullptr && e[0] == '0') ? 0 : 1;
+}
+// R2L_PP=1 selects the ping-pong kernel (mlp_r2l_pp.cu: two 64-row tiles per CTA, M = 128 cta_group::2 MMAs, same packed
+// weights, results equal to a few ulp of the fp32 tail sum) for pair-mode handles.  Measured on B200 (A/B in one process, 4 frames per launch):
+// 102.1 vs 104.5 Mrays/s for the one-tile-per-CTA pair kernel of mlp_r2l.cu, at 1612 vs 1630 MHz under the power cap
+// — the tensor pipe is busier (72 % vs 67 % by the in-kernel counters) but every M = 128 MMA re-reads the weight
+// operand for half as many rows (96 instead of 64 B/cycle of operand reads), which costs more energy per FLOP than the
+// overlap buys.  So the default stays 0; the kernel is kept as a tested alternative.
+static int r2l_pp_default() {
+  const char* e = getenv("R2L_PP");
+  return (e != nullptr && e[0] == '1') ? 1 : 0;
 }
 
 // Range check of everything packed between pack_max_reset and pack_max_check (fp16 operands only: bf16 has fp32's range)
@@ -904,6 +915,7 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
   m->kind = 1;
   m->bf16 = dtype == 1;
   m->pair = pair_mode_default();
+  m->r2l_pp = (m->pair == 1) ? r2l_pp_default() : 0;
   m->n_points = n_points;
   m->n_blocks = n_blocks;
   m->sigmoid_out = sigmoid_out;
@@ -1017,6 +1029,12 @@ static int resmlp_run(Mlp* m, long long n_rays, const float* pts, long long pts_
   (void)dbg_a;
   p.prof = prof;
   int grid;
+  if (m->r2l_pp && dbg_acc == nullptr) {
+    const long long n_units = (n_rays + 255) / 256;
+    const long long max_pairs = sm_count() / 2;
+    grid = static_cast<int>(2 * (n_units < max_pairs ? n_units : max_pairs));
+    return r2l_mlp_pp_launch(m->bf16, p, *m->r2l_maps, grid, st);
+  }
   if (m->pair) {
     const long long n_units = (n_tiles + 1) / 2;
     const long long max_pairs = sm_count() / 2;

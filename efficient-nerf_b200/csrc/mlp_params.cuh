@@ -113,6 +113,8 @@ struct R2lPairMaps {
   CUtensorMap m16, m4;
 };
 int r2l_mlp_launch(bool bf16, bool pair, const R2lParams& p, const R2lPairMaps* maps, int grid, cudaStream_t st);
+// CTA-pair ping-pong kernel with two 64-row tiles per CTA (mlp_r2l_pp.cu): pair-layout weights, grid even
+int r2l_mlp_pp_launch(bool bf16, const R2lParams& p, const R2lPairMaps& maps, int grid, cudaStream_t st);
 // CTA-pair "ping-pong" NeRF kernel (mlp_nerf_pp.cu): grid even, pair-layout stream without the view stage
 int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid,
                        cudaStream_t st);

@@ -551,3 +551,26 @@ def test_r2l_ray_generation_fused_into_the_kernel(E, O):
         assert torch.equal(lp.view(n, 16, 3), ps.sample_test2(poses[1]))
         assert torch.equal(E.PositionalEmbedder(10)(lps.sample_test(poses[1])), E.PositionalEmbedder(10)(ps.sample_test(poses[1])))
         assert torch.equal(emb(lps.sample_test(poses[1])).materialize(), E.PositionalEmbedder(10)(ps.sample_test(poses[1])))
+
+
+def test_r2l_pingpong_kernel_matches_the_default(E, O, monkeypatch):
+    """mlp_r2l_pp.cu (R2L_PP=1: two 64-row tiles per CTA, tcgen05.mma.cta_group::2 with M = 128) runs the same MMAs in
+    the same K order as the default pair kernel; only the fp32 tail sum (256 -> 3) is associated differently (four
+    partial sums per row instead of two): equal to a few ulp, on full tiles, ragged tails and one ray."""
+    sd = O.r2l_state_dict(0)
+    ps = E.PointSampler(400, 400, O.LEGO["focal"], 16, 2., 6.)
+    c2w = O.pose_spherical(75., -30., 4.)[:3, :4].cuda()
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("R2L_PP", mode)      # read when the handle is created
+        net = load_r2l(E, O, sd, "fp16")
+        with torch.no_grad():
+            pts = ps.sample_test(c2w)
+            outs[mode] = [net.render_poses(ps, c2w, rows=(0, 40000)), net.forward_points(pts[1000:1000 + 777]),
+                          net.forward_points(pts[5:6]), net(E.PositionalEmbedder(10)(pts[:300]))]
+        torch.cuda.synchronize()
+        assert net.range_status()[0] == 0
+    for a, b in zip(outs["0"], outs["1"]):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-6
+    ref = O.render_r2l(sd, 400, 400, O.LEGO["focal"], 2., 6., c2w.cpu(), rows=torch.arange(0, 40000, 401))
+    assert maxabs(outs["1"][0][::401], ref) <= RGB_TOL
