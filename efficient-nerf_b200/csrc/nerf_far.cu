@@ -16,9 +16,8 @@
 // which is itself within 1e-5 of the torch-CPU reference.
 //
 // Work per flagged point: 0.98 MFLOP fp32; weights (transposed fp32 copy, 1.96 MB per net) stream from L2 through a
-// cp.async ring.  One block = 256 threads = the 256 output neurons of a layer, 8 flagged rays at a time (8
-// accumulators per thread, the group's activations broadcast from shared memory), grid = 2 blocks per SM looping
-// over the list.
+// cp.async ring.  One block = 256 threads works on 32 flagged rays at a time (4 neurons x 8 rays per thread), grid =
+// one block per SM looping over the list.
 #include "common.cuh"
 #include "mlp_params.cuh"
 
@@ -48,32 +47,43 @@ __global__ void far_transpose_kernel(const float* __restrict__ W, int K, float* 
   Wt[idx] = W[n * K + k];
 }
 
-// The whole net is one sequence of 1918 weight rows of 1 KiB.  With a handful of flagged rays per launch nothing hides
-// the L2 latency of a per-thread weight load (a first version with loads issued from the FMA loop cost 0.4 ms for 30
-// rays: ~480 dependent round trips), so the rows are streamed through a 4-deep cp.async ring of 16-row chunks that runs
-// ahead ACROSS layer boundaries; the FMA loop reads weights and activations from shared memory only.
+// The whole net is one sequence of 1918 weight rows of 1 KiB, streamed through a 4-deep cp.async ring of 16-row chunks
+// that runs ahead ACROSS layer boundaries (with a handful of flagged rays per launch nothing else hides the L2 latency:
+// a first version with loads issued from the FMA loop cost 0.4 ms for 30 rays).  A block works on 32 flagged rays at
+// a time: thread (s, j) = (tid / 64, tid % 64) owns output neurons 4j..4j+3 of the 8 rays of sub-batch s — per weight
+// row one LDS.128 of weights and two broadcast LDS.128 of activations feed 32 FMAs, and the ring is shared by all 32
+// rays.  (The 8-rays-per-block version was LDS-bound at 3 loads per 8 FMAs: 300 us for the ~2600 rays the coarse
+// pass of a frame flags; ncu r2d.)  Every output still accumulates k = 0, 1, 2, ... in order: bit-identical to the
+// fp32 path.
 constexpr int kFarChunk = 16;                       // rows per chunk (16 KiB)
 constexpr int kFarStages = 4;
-constexpr int kFarRingBytes = kFarStages * kFarChunk * 256 * 4;
+constexpr int kFarSub = 4;                          // sub-batches of kFarG rays per block
+constexpr int kFarBatch = kFarSub * kFarG;          // 32 rays per block iteration
+constexpr int kFarRingFloats = kFarStages * kFarChunk * 256;
+constexpr int kFarEmbFloats = kFarSub * 64 * kFarG;
+constexpr int kFarHFloats = 2 * kFarSub * 256 * kFarG;
+constexpr int kFarSmemBytes = (kFarRingFloats + kFarEmbFloats + kFarHFloats) * 4;
 
 __device__ __forceinline__ void far_cp16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
                : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __restrict__ list,
                       const int* __restrict__ count, int cap, int* __restrict__ stats, const float* __restrict__ rays_o,
                       long long o_stride, const float* __restrict__ rays_d, long long d_stride,
                       const float* __restrict__ z_vals, int S, float* __restrict__ raw) {
-  extern __shared__ __align__(16) float s_ring[];      // [kFarStages][kFarChunk][256]
-  __shared__ __align__(16) float s_emb[64][kFarG];    // embedded point, reference order (63 used)
-  __shared__ __align__(16) float s_h[2][256][kFarG];  // hidden activations, ping-pong
-  __shared__ float s_pt[kFarG][3];
+  extern __shared__ __align__(16) float s_far[];
+  float* const s_ring = s_far;                              // [kFarStages][kFarChunk][256]
+  float* const s_emb = s_ring + kFarRingFloats;             // [sub][64][kFarG]: embedded point, reference order
+  float* const s_h = s_emb + kFarEmbFloats;                 // [2][sub][256][kFarG]: hidden activations, ping-pong
+  __shared__ float s_pt[kFarBatch][3];
   int n = *count;
   if (n > cap) n = cap;
   if (blockIdx.x == 0 && threadIdx.x == 0) stats[0] = *count;   // flagged by the last forward (may exceed cap)
   const int tid = threadIdx.x;
+  const int sub = tid >> 6, j4 = (tid & 63) * 4;              // sub-batch, first of this thread's 4 neurons
   constexpr int n_chunks = (kFarRows + kFarChunk - 1) / kFarChunk;   // 120 (the last one holds 14 rows)
   auto issue = [&](int c) {   // chunk c -> ring slot c % kFarStages (rows past the end read the bias block: harmless)
     if (c < n_chunks) {
@@ -84,11 +94,11 @@ nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  for (int g0 = blockIdx.x * kFarG; g0 < n; g0 += gridDim.x * kFarG) {
-    const int ng = min(kFarG, n - g0);
+  for (int g0 = blockIdx.x * kFarBatch; g0 < n; g0 += gridDim.x * kFarBatch) {
+    const int ng = min(kFarBatch, n - g0);
     __syncthreads();
     for (int c = 0; c < kFarStages - 1; ++c) issue(c);
-    if (tid < kFarG * 3) {
+    if (tid < kFarBatch * 3) {
       const int g = tid / 3, c = tid % 3;
       float v = 0.0f;
       if (g < ng) {
@@ -97,78 +107,93 @@ nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __
         v = __fadd_rn(rays_o[ray * o_stride + c], __fmul_rn(rays_d[ray * d_stride + c], z));   // main.py:701
       }
       s_pt[g][c] = v;
-      s_emb[c][g] = v;
+      s_emb[((g / kFarG) * 64 + c) * kFarG + (g % kFarG)] = v;
     }
     __syncthreads();
-    if (tid < kFarG * 30) {   // (ray, coord, freq): Embedder order 3 + 6 f + {c, 3 + c}  (helpers:24-56)
-      const int g = tid / 30, r = tid % 30, c = r / 10, f = r % 10;
-      float s, co;
-      sincosf(s_pt[g][c] * exp2f(static_cast<float>(f)), &s, &co);
-      s_emb[3 + 6 * f + c][g] = s;
-      s_emb[3 + 6 * f + 3 + c][g] = co;
+    for (int it = tid; it < kFarBatch * 30; it += 256) {   // (ray, coord, freq): Embedder order 3 + 6 f + {c, 3 + c}
+      const int g = it / 30, r = it % 30, c = r / 10, f = r % 10;
+      float sn, co;
+      sincosf(s_pt[g][c] * exp2f(static_cast<float>(f)), &sn, &co);
+      float* e = s_emb + (g / kFarG) * 64 * kFarG + (g % kFarG);
+      e[(3 + 6 * f + c) * kFarG] = sn;
+      e[(3 + 6 * f + 3 + c) * kFarG] = co;
     }
     // rows are consumed in order; `l` / `k` = layer and input index of the current row
     int l = 0, k = 0, cur = 0;
-    float acc[kFarG];
+    float acc[4][kFarG];
 #pragma unroll
-    for (int g = 0; g < kFarG; ++g) acc[g] = 0.0f;
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int g = 0; g < kFarG; ++g) acc[q][g] = 0.0f;
+    const float* const emb_s = s_emb + sub * 64 * kFarG;
     for (int c = 0; c < n_chunks; ++c) {
       asm volatile("cp.async.wait_group %0;" ::"n"(kFarStages - 2) : "memory");   // chunk c has landed (this thread's part)
       __syncthreads();            // ... everybody's part, and everybody is done with chunk c - 1 (and with s_emb / s_h writes)
       issue(c + kFarStages - 1);  // into the slot chunk c - 1 occupied
-      const float* wrow = s_ring + (c % kFarStages) * kFarChunk * 256 + tid;
+      const float* wrow = s_ring + (c % kFarStages) * kFarChunk * 256 + j4;
       const int rows = min(kFarChunk, kFarRows - c * kFarChunk);
       for (int r = 0; r < rows;) {
         // input of this row: layer 0 and the first 63 rows of the skip layer read the embedding (cat[input_pts, h])
         const bool from_emb = (l == 0) || (l == 5 && k < 63);
-        const float* x = from_emb ? &s_emb[k][0] : &s_h[cur][l == 5 ? k - 63 : k][0];
+        const float* x = from_emb ? emb_s + k * kFarG : s_h + ((cur * kFarSub + sub) * 256 + (l == 5 ? k - 63 : k)) * kFarG;
         const int k_end = (l == 5 && k < 63) ? 63 : far_layer_k(l);   // rows left before the input source changes
-        if (r + 4 <= rows && k + 4 <= k_end) {
-          // four rows at a time, every shared-memory load issued before the first FMA (same FMA order per accumulator)
-          float wv[4];
-          float4 xa[4], xb[4];
+        auto fma_row = [&](const float4& w4, const float4& xa, const float4& xb) {
+          const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[q][0] = fmaf(xa.x, wq[q], acc[q][0]);
+            acc[q][1] = fmaf(xa.y, wq[q], acc[q][1]);
+            acc[q][2] = fmaf(xa.z, wq[q], acc[q][2]);
+            acc[q][3] = fmaf(xa.w, wq[q], acc[q][3]);
+            acc[q][4] = fmaf(xb.x, wq[q], acc[q][4]);
+            acc[q][5] = fmaf(xb.y, wq[q], acc[q][5]);
+            acc[q][6] = fmaf(xb.z, wq[q], acc[q][6]);
+            acc[q][7] = fmaf(xb.w, wq[q], acc[q][7]);
+          }
+        };
+        if (sub * kFarG >= ng) {
+          // this sub-batch holds no ray of the (last, partial) batch: skip the arithmetic, keep the control flow
+          const int adv = min(min(4, rows - r), k_end - k);
+          r += adv, k += adv;
+          if (k != far_layer_k(l)) continue;
+          --k;
+        } else if (r + 4 <= rows && k + 4 <= k_end) {
+          // four rows at a time: all twelve shared-memory loads are issued before the first FMA (same FMA order per
+          // accumulator), otherwise every row exposes an LDS round trip with two warps per scheduler
+          float4 w4[4], xa[4], xb[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            wv[j] = wrow[(r + j) * 256];
+            w4[j] = *reinterpret_cast<const float4*>(wrow + (r + j) * 256);
             xa[j] = *reinterpret_cast<const float4*>(x + j * kFarG);
             xb[j] = *reinterpret_cast<const float4*>(x + j * kFarG + 4);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            acc[0] = fmaf(xa[j].x, wv[j], acc[0]);
-            acc[1] = fmaf(xa[j].y, wv[j], acc[1]);
-            acc[2] = fmaf(xa[j].z, wv[j], acc[2]);
-            acc[3] = fmaf(xa[j].w, wv[j], acc[3]);
-            acc[4] = fmaf(xb[j].x, wv[j], acc[4]);
-            acc[5] = fmaf(xb[j].y, wv[j], acc[5]);
-            acc[6] = fmaf(xb[j].z, wv[j], acc[6]);
-            acc[7] = fmaf(xb[j].w, wv[j], acc[7]);
-          }
+          for (int j = 0; j < 4; ++j) fma_row(w4[j], xa[j], xb[j]);
           r += 4, k += 4;
           if (k != far_layer_k(l)) continue;
-          --k;   // fall through to the layer-end handling below (which increments k again)
+          --k;   // layer complete: fall through to the hand-over below (which increments k again)
         } else {
-          const float wv = wrow[r * 256];
-          const float4 xa = *reinterpret_cast<const float4*>(x);
-          const float4 xb = *reinterpret_cast<const float4*>(x + 4);
-          acc[0] = fmaf(xa.x, wv, acc[0]);
-          acc[1] = fmaf(xa.y, wv, acc[1]);
-          acc[2] = fmaf(xa.z, wv, acc[2]);
-          acc[3] = fmaf(xa.w, wv, acc[3]);
-          acc[4] = fmaf(xb.x, wv, acc[4]);
-          acc[5] = fmaf(xb.y, wv, acc[5]);
-          acc[6] = fmaf(xb.z, wv, acc[6]);
-          acc[7] = fmaf(xb.w, wv, acc[7]);
+          fma_row(*reinterpret_cast<const float4*>(wrow + r * 256), *reinterpret_cast<const float4*>(x),
+                  *reinterpret_cast<const float4*>(x + 4));
           ++r;
         }
         if (++k == far_layer_k(l)) {   // layer complete: bias, relu, hand the activations to the next layer
-          const float bl = __ldg(Wt + kFarBiasOff + l * 256 + tid);
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(Wt + kFarBiasOff + l * 256 + j4));
+          const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
           const int nxt = (l == 0) ? 0 : (cur ^ 1);
           __syncthreads();             // every thread has finished reading s_h[cur] ... (uniform branch)
+          float* out = s_h + ((nxt * kFarSub + sub) * 256 + j4) * kFarG;
 #pragma unroll
-          for (int g = 0; g < kFarG; ++g) {
-            s_h[nxt][tid][g] = fmaxf(acc[g] + bl, 0.0f);
-            acc[g] = 0.0f;
+          for (int q = 0; q < 4; ++q) {
+            float4 o0, o1;
+            o0.x = fmaxf(acc[q][0] + bq[q], 0.0f), o0.y = fmaxf(acc[q][1] + bq[q], 0.0f);
+            o0.z = fmaxf(acc[q][2] + bq[q], 0.0f), o0.w = fmaxf(acc[q][3] + bq[q], 0.0f);
+            o1.x = fmaxf(acc[q][4] + bq[q], 0.0f), o1.y = fmaxf(acc[q][5] + bq[q], 0.0f);
+            o1.z = fmaxf(acc[q][6] + bq[q], 0.0f), o1.w = fmaxf(acc[q][7] + bq[q], 0.0f);
+            *reinterpret_cast<float4*>(out + q * kFarG) = o0;
+            *reinterpret_cast<float4*>(out + q * kFarG + 4) = o1;
+#pragma unroll
+            for (int g = 0; g < kFarG; ++g) acc[q][g] = 0.0f;
           }
           cur = nxt;
           ++l, k = 0;
@@ -179,7 +204,8 @@ nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __
     if (tid < ng) {   // alpha_linear: sequential k, like the fp32 path's K loop
       float a = 0.0f;
       const float* aw = Wt + kFarAlphaOff;
-      for (int kk = 0; kk < 256; ++kk) a = fmaf(s_h[cur][kk][tid], __ldg(aw + kk), a);
+      const float* h = s_h + ((cur * kFarSub + tid / kFarG) * 256) * kFarG + (tid % kFarG);
+      for (int kk = 0; kk < 256; ++kk) a = fmaf(h[kk * kFarG], __ldg(aw + kk), a);
       const long long ray = list[g0 + tid];
       raw[(ray * S + (S - 1)) * 4 + 3] = a + alpha_b;
     }
@@ -203,13 +229,13 @@ size_t nerf_far_weight_bytes() { return sizeof(float) * kFarFloats; }
 
 int nerf_far_fixup_launch(const float* Wt, float alpha_b, const int* list, const int* count, int cap, int* stats,
                           const NerfParams& p, cudaStream_t st) {
-  const int grid = 2 * sm_count();
+  const int grid = sm_count();
   static bool attr_set = false;
   if (!attr_set) {
-    R2L_CUDA(cudaFuncSetAttribute(nerf_far_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFarRingBytes));
+    R2L_CUDA(cudaFuncSetAttribute(nerf_far_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFarSmemBytes));
     attr_set = true;
   }
-  nerf_far_fixup_kernel<<<grid, 256, kFarRingBytes, st>>>(Wt, alpha_b, list, count, cap, stats, p.rays_o, p.o_stride, p.rays_d,
+  nerf_far_fixup_kernel<<<grid, 256, kFarSmemBytes, st>>>(Wt, alpha_b, list, count, cap, stats, p.rays_o, p.o_stride, p.rays_d,
                                              p.d_stride, p.z_vals, p.S, p.raw);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
