@@ -881,6 +881,7 @@ int r2l_nerf_profile(void* handle, long long n_rays, int S, const float* rays_o,
   R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_profile: not a NeRF handle");
   R2L_CHECK_ARG(n_rays > 0 && S > 0 && rays_o && rays_d && viewdirs && z_vals && raw && prof,
                 "r2l_nerf_profile: bad arguments");
+  R2L_CHECK_ARG(S >= 64 && S % 32 == 0, "r2l_nerf_profile: the profiling instantiation covers S >= 64, S %% 32 == 0");
   NerfParams p{};
   p.rays_o = rays_o;
   p.rays_d = rays_d;

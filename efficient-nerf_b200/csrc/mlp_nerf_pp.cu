@@ -80,7 +80,8 @@ constexpr int kPpOffRgbW = kPpOffAlphaW + 256 * 4;                    // 3*128 f
 constexpr int kPpOffPart = kPpOffRgbW + 384 * 4;                      // 128 x float4
 constexpr int kPpOffAbs = kPpOffPart + 128 * 16;                      // 128 floats: WG1's half of sum |w_a| relu(h7)
 constexpr int kPpOffBars = kPpOffAbs + 128 * 4;
-constexpr int kPpNumBars = 2 * kPpRing + 2 * kPpBiasRing + 2 + 2 + 2 + 2 + 2;
+constexpr int kPpNumBars = 2 * kPpRing + 2 * kPpBiasRing + 2 + 2 + 2 + 2 + 2 + 1;
+static_assert(2 * 2 * 128 * 4 <= (256 + 384) * 4, "view-bias rows must fit the old head-weight region");
 constexpr int kPpOffTmem = kPpOffBars + kPpNumBars * 8;
 constexpr int kPpSmemBytes = kPpOffTmem + 16;
 static_assert(kPpSmemBytes <= 227 * 1024, "NeRF ping-pong kernel shared memory exceeds 227 KiB");
@@ -90,7 +91,13 @@ __device__ __forceinline__ int pp_main_stages(int step) { return step == 0 ? 1 :
 
 // PROF = true: the instantiation behind r2l_nerf_profile (in-kernel cycle counters / event timeline); the production
 // kernel carries none of that code (code size, see the epilogue).
-template <bool BF16, bool PROF>
+// UNI = true (every render call: ray samples with S a multiple of 32 and S >= 64): the 32 rows of a warp belong to ONE
+// ray and a tile holds at most two rays, so the encoder warps stage the tile's (at most two) per-ray view-bias rows
+// in shared memory ahead of time and the last epilogue reads them with broadcast LDS.128 — every thread fetching its
+// own 16 x float4 from L2 after the accumulator wait put ~2300 cycles into that epilogue (in-kernel trace), and the
+// two step-9 epilogues are what the unit boundary waits for.  UNI = false: general S and the NeRF.forward(x) rows
+// (every row its own bias row, loaded from global memory).
+template <bool BF16, bool PROF, bool UNI>
 __global__ void __launch_bounds__(kPpThreads, 1)
 nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, const __grid_constant__ NerfHeadW hw) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -99,8 +106,9 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
   uint8_t* const sOnes = smem + kPpOffOnes;
   uint8_t* const sRing = smem + kPpOffRing;
   uint8_t* const sBiasRing = smem + kPpOffBiasRing;
-  float* const sAlphaW = reinterpret_cast<float*>(smem + kPpOffAlphaW);
-  float* const sRgbW = reinterpret_cast<float*>(smem + kPpOffRgbW);
+  // [tile][ray of the tile 0|1][128] fp32 view-bias rows (UNI); the head weights that used to live here come from the
+  // constant bank now (NerfHeadW)
+  float* const sVb = reinterpret_cast<float*>(smem + kPpOffAlphaW);
   float4* const sPart = reinterpret_cast<float4*>(smem + kPpOffPart);
   float* const sAbs = reinterpret_cast<float*>(smem + kPpOffAbs);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kPpOffBars);
@@ -113,6 +121,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
   uint64_t* const p_ready = a_done + 2;             // [tile]: leader; 8 encoder warps have written P for tile t
   uint64_t* const p_free = p_ready + 2;             // [tile]: tile t's MMAs that read P have completed (commit, both CTAs)
   uint64_t* const turn = p_free + 2;                // [tile]: leader; the other issuer has issued its tile-layer
+  uint64_t* const vb_ready = turn + 2;              // THIS CTA: its 4 encoder warps have staged the unit's view-bias rows
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + kPpOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -124,7 +133,6 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
   const int unit_step = static_cast<int>(gridDim.x >> 1);
 
   // ---- one-time setup ----
-  (void)sAlphaW, (void)sRgbW;   // the head weights come from the constant bank now (NerfHeadW)
   write_ones_block<BF16>(sOnes, threadIdx.x, kPpThreads);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPpRing; ++i) {
@@ -142,6 +150,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
       mbar_init(&p_free[i], 1);
       mbar_init(&turn[i], 1);
     }
+    mbar_init(vb_ready, 4);
     mbar_fence_init();
   }
   fence_proxy_async_smem();
@@ -419,6 +428,22 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
         __syncwarp();
         if (lane == 0) lane_arrive<true>(&p_ready[t]);
       }
+      if (UNI) {
+        // the unit's view-bias rows: thread `row` copies column `row` of the (at most two) rays of each tile.  The
+        // previous unit's step-9 epilogues have finished reading the buffer: this point is only reached after T0's
+        // step-5 MMAs of THIS unit (p_free), which the same epilogue warps fed after finishing the previous unit.
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const long long r_first = (4LL * unit + 2 * t + rank) * kTileM;
+          long long ra = r_first, rb = r_first + kTileM - 1;
+          if (ra >= p.n_rows) ra = p.n_rows - 1;
+          if (rb >= p.n_rows) rb = p.n_rows - 1;
+          sVb[(2 * t + 0) * 128 + row] = __ldg(p.vb + (ra / p.S) * 128 + row);
+          sVb[(2 * t + 1) * 128 + row] = __ldg(p.vb + (rb / p.S) * 128 + row);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(vb_ready);
+      }
     }
   } else {
     // ===================== epilogue warpgroups (both tiles, alternating) =====================
@@ -503,7 +528,18 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
             const long long g_row = tile * kTileM + row;
             const bool valid = g_row < p.n_rows;
             const long long ray = (valid ? g_row : (p.n_rows - 1)) / p.S;
-            const float4* vb4 = reinterpret_cast<const float4*>(p.vb + ray * 128);
+            const float4* vb4;
+            if (UNI) {
+              // this warp's 32 rows share one ray: the tile's first or second (rows of a tile straddle at most 2 rays)
+              long long r0w = tile * kTileM + (warp & 3) * 32, r0t = tile * kTileM;
+              if (r0w >= p.n_rows) r0w = p.n_rows - 1;
+              if (r0t >= p.n_rows) r0t = p.n_rows - 1;
+              const int second = (r0w / p.S != r0t / p.S) ? 1 : 0;
+              vb4 = reinterpret_cast<const float4*>(sVb + (2 * t + second) * 128);
+              if (t == 0) mbar_wait(vb_ready, eit & 1u, p.dbg, 330);   // staged long ago; one phase per unit
+            } else {
+              vb4 = reinterpret_cast<const float4*>(p.vb + ray * 128);
+            }
             float r = 0.f, gch = 0.f, b = 0.f;
             {
               uint32_t va[32], vb[32];
@@ -516,7 +552,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
                 constexpr int WG = decltype(wg_c)::value;
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
-                  const float4 bb = __ldg(vb4 + 8 * WG + i4);
+                  const float4 bb = UNI ? vb4[8 * WG + i4] : __ldg(vb4 + 8 * WG + i4);
                   const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
@@ -531,7 +567,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
                 }
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
-                  const float4 bb = __ldg(vb4 + 16 + 8 * WG + i4);
+                  const float4 bb = UNI ? vb4[16 + 8 * WG + i4] : __ldg(vb4 + 16 + 8 * WG + i4);
                   const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
@@ -636,9 +672,9 @@ nerf_view_bias_kernel(long long n_rays, const float* __restrict__ viewdirs, long
   }
 }
 
-template <bool BF16, bool PROF>
+template <bool BF16, bool PROF, bool UNI>
 int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid, cudaStream_t st) {
-  R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16, PROF, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kPpThreads);
@@ -651,7 +687,7 @@ int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16, PROF>, p, maps, hw));
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16, PROF, UNI>, p, maps, hw));
   count_launch();
   return R2L_OK;
 }
@@ -659,9 +695,11 @@ int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW&
 // grid must be even (CTA pairs); weights packed in the pair layout WITHOUT the view stage (mlp_api.cu)
 int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid,
                        cudaStream_t st) {
-  if (p.prof != nullptr)
-    return bf16 ? launch_nerf_pp<true, true>(p, maps, hw, grid, st) : launch_nerf_pp<false, true>(p, maps, hw, grid, st);
-  return bf16 ? launch_nerf_pp<true, false>(p, maps, hw, grid, st) : launch_nerf_pp<false, false>(p, maps, hw, grid, st);
+  const bool uni = p.embedded == nullptr && p.S >= 64 && (p.S % 32) == 0;
+  if (p.prof != nullptr)   // the profiling hooks exist for the render form only
+    return bf16 ? launch_nerf_pp<true, true, true>(p, maps, hw, grid, st) : launch_nerf_pp<false, true, true>(p, maps, hw, grid, st);
+  if (uni) return bf16 ? launch_nerf_pp<true, false, true>(p, maps, hw, grid, st) : launch_nerf_pp<false, false, true>(p, maps, hw, grid, st);
+  return bf16 ? launch_nerf_pp<true, false, false>(p, maps, hw, grid, st) : launch_nerf_pp<false, false, false>(p, maps, hw, grid, st);
 }
 
 int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,
