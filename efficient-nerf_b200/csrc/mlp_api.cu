@@ -766,6 +766,7 @@ static int nerf_run_mlp(Mlp* m, NerfParams& p, cudaStream_t st) {
   p.n_tiles = static_cast<int>(n_tiles);
   p.dbg = m->dbg_dev;
   if (m->nerf_pp) {
+    R2L_CHECK_ARG(n_tiles < (1LL << 29), "r2l_nerf_forward: too many samples for one call");
     // per-ray view bias into the handle's workspace (grown on demand: the only allocation a forward can make),
     // then the ping-pong kernel: units of 4 tiles (2 per CTA of a pair)
     const bool emb = p.embedded != nullptr;

@@ -523,30 +523,39 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
             warp_arrive<true>(&a_done[t], lane);
             if (threadIdx.x == 0) trace(eit, 400000 + t * 10000 + step * 100);   // ... and has ended (warp 0)
           } else {
-            // step 9: view branch (N = 128 -> D[t] columns [0,128)); this warp owns columns 32*wg and 64 + 32*wg
+            // step 9: view branch (N = 128 -> D[t] columns [0,128)); this warp owns columns 32*wg and 64 + 32*wg.
+            // The TMEM loads are issued FIRST: the index arithmetic below (64-bit divisions) runs under their latency.
+            uint32_t va[32], vb[32];
+            tmem_ld32(lane_taddr + 256 * t + 32 * wg, va);
+            tmem_ld32(lane_taddr + 256 * t + 64 + 32 * wg, vb);
             const long long tile = 4LL * unit + 2 * t + rank;
             const long long g_row = tile * kTileM + row;
             const bool valid = g_row < p.n_rows;
-            const long long ray = (valid ? g_row : (p.n_rows - 1)) / p.S;
+            long long ray;
             const float4* vb4;
             if (UNI) {
-              // this warp's 32 rows share one ray: the tile's first or second (rows of a tile straddle at most 2 rays)
-              long long r0w = tile * kTileM + (warp & 3) * 32, r0t = tile * kTileM;
-              if (r0w >= p.n_rows) r0w = p.n_rows - 1;
-              if (r0t >= p.n_rows) r0t = p.n_rows - 1;
-              const int second = (r0w / p.S != r0t / p.S) ? 1 : 0;
-              vb4 = reinterpret_cast<const float4*>(sVb + (2 * t + second) * 128);
+              // this warp's 32 rows share one ray: the tile's first or second (rows of a tile straddle at most 2 rays).
+              // S is a multiple of 32 here, so ray = (row / 32) / (S / 32) on 32-row units (tile counts are < 2^29: host)
+              const unsigned s32 = static_cast<unsigned>(p.S) >> 5;
+              unsigned u_w = 4u * static_cast<unsigned>(tile) + static_cast<unsigned>(warp & 3), u_t = 4u * static_cast<unsigned>(tile);
+              const unsigned u_last = static_cast<unsigned>((p.n_rows - 1) >> 5);
+              u_w = min(u_w, u_last), u_t = min(u_t, u_last);
+              const unsigned ray_w = u_w / s32;
+              ray = ray_w;
+              vb4 = reinterpret_cast<const float4*>(sVb + (2 * t + (ray_w != u_t / s32 ? 1 : 0)) * 128);
               if (t == 0) mbar_wait(vb_ready, eit & 1u, p.dbg, 330);   // staged long ago; one phase per unit
             } else {
+              ray = (valid ? g_row : (p.n_rows - 1)) / p.S;
               vb4 = reinterpret_cast<const float4*>(p.vb + ray * 128);
             }
             float r = 0.f, gch = 0.f, b = 0.f;
             {
-              uint32_t va[32], vb[32];
-              tmem_ld32(lane_taddr + 256 * t + 32 * wg, va);
-              tmem_ld32(lane_taddr + 256 * t + 64 + 32 * wg, vb);
               tmem_ld_wait();
-              warp_arrive<true>(&a_done[t], lane);   // D[t] is drained: the next unit's step 0 may overwrite it
+              // D[t] is drained: the next unit's step 0 may overwrite it.  (No proxy fence: this epilogue wrote no
+              // shared-memory operand.)
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) lane_arrive<true>(&a_done[t]);
               // rgb_linear on relu(accumulator + per-ray view bias); weights from the constant bank (static indices)
               auto rgb_dot = [&](auto wg_c) {
                 constexpr int WG = decltype(wg_c)::value;
