@@ -580,11 +580,23 @@ def main():
     if world == 1 and not args.no_extras:
         line["extras"] = extras(E, peaks, args.precision, args.workload, flush, no_cpu=args.no_cpu_baseline)
     if world > 1 and not args.no_extras and not by_rays:
-        # strong scaling of ONE frame, driver-visible: rays of every frame sharded over the ranks
+        # strong scaling of ONE frame, driver-visible: rays of every frame sharded over the ranks.  The headline line
+        # must survive this secondary phase: an exception is recorded, and a hang (a collective that one rank never
+        # enters) is cut off by an alarm that prints the line without the phase and leaves.
+        import signal
+
+        def give_up(signum, frame):
+            if rank == 0:
+                line.setdefault("extras", {})["ray_sharded"] = {"error": "timed out after 240 s"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        signal.signal(signal.SIGALRM, give_up)
+        signal.alarm(240)
         try:
             rs = ray_sharded_phase(E, dist, args.precision, rank, world, barrier)
-        except Exception as e:      # the headline line must survive a failure of the secondary phase
+        except Exception as e:
             rs = {"error": f"{type(e).__name__}: {e}"}
+        signal.alarm(0)
         if rank == 0:
             line.setdefault("extras", {})["ray_sharded"] = rs
     if rank == 0:
