@@ -421,8 +421,12 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
           const float px = __fadd_rn(__ldg(o + 0), __fmul_rn(__ldg(dd + 0), z));
           const float py = __fadd_rn(__ldg(o + 1), __fmul_rn(__ldg(dd + 1), z));
           const float pz = __fadd_rn(__ldg(o + 2), __fmul_rn(__ldg(dd + 2), z));
+          // encode into registers FIRST, wait for the block to be free, then only store: the ~800 cycles of sin / cos
+          // work stay off the p_free -> p_ready path (T1's steps 0 and 5 start that much earlier after T0's)
+          uint4 q[8];
+          encode_point_packed<BF16>(px, py, pz, q);
           if (n_enc > 0) mbar_wait(&p_free[1 - t], prev_par, p.dbg, 500 + t, 4);
-          encode_point_block<BF16>(sP, row, px, py, pz);
+          store_point_block(sP, row, q);
         }
         fence_proxy_async_smem();
         __syncwarp();

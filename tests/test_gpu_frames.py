@@ -150,3 +150,16 @@ def test_r2l_whole_frame_vs_cpu_oracle(E, O):
     print(f"\n[R2L whole frame] max |rgb - oracle| {float(d.max()):.2e}, rays beyond 2e-3: {int((d.max(-1)[0] > RGB_TOL).sum())}")
     assert float(d.max()) <= RGB_TOL
     assert abs(psnr(rgb[::16], target) - psnr(ref[::16], target)) <= 0.05
+
+
+def test_single_cta_kernel_flags_and_fixes_far_samples_too(E, O, monkeypatch):
+    """R2L_NERF_PP=0 handles (mlp_nerf.cu, one tile per CTA) share the guard-band test and the fp32 fix-up: a
+    200x200 frame agrees with the fp32 path within 2e-3 on every ray of rgb_map and rgb0."""
+    monkeypatch.setenv("R2L_NERF_PP", "0")        # read when the handles are created
+    cam = dict(O.LEGO, H=200, W=200, focal=O.LEGO["focal"] / 2)
+    c2w = O.pose_spherical(40., -30., 4.)[:3, :4].cuda()
+    out = census(E, O, cam, c2w)
+    fx, rw = out["fixup"], out["raw16"]
+    print(f"\n[census 200x200, single-CTA kernel] with fix-up: {fx['bad']} / {fx['bad0']} rays beyond 2e-3 (flagged "
+          f"{fx['flagged']}); without: {rw['bad']} / {rw['bad0']}")
+    assert fx["bad"] == 0 and fx["bad0"] == 0 and fx["flagged"] > 0
