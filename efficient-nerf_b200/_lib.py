@@ -48,6 +48,9 @@ SIGNATURES = {
                         _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_vp],
     "r2l_nerf_forward": [_c_vp, _c_ll, _c_int, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_f32p,
                          _c_vp],
+    "r2l_nerf_render": [_c_vp, _c_ll, _c_int, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_int, _c_f32p,
+                        _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_vp],
+    "r2l_nerf_render_mode": [_c_vp, _c_int],
     "r2l_nerf_far_fixup": [_c_vp, _c_int, _c_dbl, _c_dbl],
     "r2l_nerf_far_count": [_c_vp, ctypes.POINTER(_c_ll), _c_vp],
     "r2l_nerf_forward_embedded": [_c_vp, _c_ll, _c_f32p, _c_ll, _c_f32p, _c_vp],
@@ -71,7 +74,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"r2l_last_error": ctypes.c_char_p, "r2l_kernel_launches": ctypes.c_longlong}
 
-ABI_VERSION = 6   # r2l_abi_version() of the library this binding was written for (include/r2l_b200.h)
+ABI_VERSION = 7   # r2l_abi_version() of the library this binding was written for (include/r2l_b200.h)
 
 _lock = threading.Lock()
 _lib = None

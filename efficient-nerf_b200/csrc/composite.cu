@@ -16,23 +16,12 @@
 // reference's sequential double-accumulated cumprod.
 // Algorithmic HBM bytes per ray: 16S (raw) + 4S (z) + 12 (d) in, 4S (weights) + 24 out.
 #include "common.cuh"
+#include "composite_math.cuh"
 
 namespace r2l {
 
 constexpr int kCompWarps = 8;
 
-__device__ __forceinline__ double shfl_up_f64(double v, int delta) {
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  lo = __shfl_up_sync(0xffffffffu, lo, delta);
-  hi = __shfl_up_sync(0xffffffffu, hi, delta);
-  return __hiloint2double(hi, lo);
-}
-__device__ __forceinline__ double shfl_idx_f64(double v, int src) {
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  lo = __shfl_sync(0xffffffffu, lo, src);
-  hi = __shfl_sync(0xffffffffu, hi, src);
-  return __hiloint2double(hi, lo);
-}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -174,14 +163,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// 1 / (1 + 2^(-x*log2 e)): FMUL + MUFU.EX2 + FADD + MUFU.RCP (flush-to-zero is harmless: 1 + tiny = 1, rcp(inf) = 0)
-__device__ __forceinline__ float fast_sigmoid(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, e)));
-  return r;
-}
-
 constexpr int kBlkWarps = 4;
 template <int K> struct BlkLayout {
   static constexpr int KR = K + 1;   // float4 per lane in the raw row (padded)
@@ -256,7 +237,7 @@ raw2outputs_blocked_kernel(long long n_rays, int S, const float4* __restrict__ r
     const long long rd_ray = ray_ok ? ray : n_rays - 1;
     const float dx = __ldg(rays_d + rd_ray * d_stride), dy = __ldg(rays_d + rd_ray * d_stride + 1),
                 dz = __ldg(rays_d + rd_ray * d_stride + 2);
-    const float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float dnorm = comp_dnorm(dx, dy, dz);
     cp_async_wait<1>();
     __syncwarp();
     const float4* s_raw = reinterpret_cast<const float4*>(wbase + stage * L::kStageBytes) + lane * L::KR;
@@ -269,60 +250,12 @@ raw2outputs_blocked_kernel(long long n_rays, int S, const float4* __restrict__ r
       zr[j] = s_z[j];
     }
     const float z_next_lane = __shfl_down_sync(0xffffffffu, zr[0], 1);
-    const int base = sl * K;      // index of this lane's first sample within its ray
-    float alpha[K];
-    double excl_in[K];
-    double run = 1.0;
+    float w[K];
+    float ar, ag, ab, adepth, aacc;
+    blocked_composite<K, FULL, LPR>(rv, zr, z_next_lane, sl, S, ray_ok, dnorm,
+                                    noise != nullptr ? noise + ray * S : nullptr, w, ar, ag, ab, adepth, aacc);
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const int i = base + j;
-      const bool valid = ray_ok && (FULL || i < S);
-      const float zn = (j + 1 < K) ? zr[j + 1] : z_next_lane;
-      float dist = (i == S - 1) ? 1e10f : __fsub_rn(zn, zr[j]);
-      dist = __fmul_rn(dist, dnorm);
-      float sigma = rv[j].w;
-      if (noise != nullptr && valid) sigma = __fadd_rn(sigma, __ldg(noise + ray * S + i));
-      const float rl = fmaxf(sigma, 0.0f);
-      float a = __fsub_rn(1.0f, expf(__fmul_rn(-rl, dist)));
-      if (sigma != sigma) a = sigma;  // relu/exp propagate NaN in the reference
-      alpha[j] = a;
-      excl_in[j] = run;
-      if (valid) run *= static_cast<double>(__fadd_rn(__fsub_rn(1.0f, a), 1e-10f));
-    }
-    double p = run;   // inclusive scan of the lane totals, segmented by ray
-#pragma unroll
-    for (int o = 1; o < LPR; o <<= 1) {
-      const double q = shfl_up_f64(p, o);
-      if (sl >= o) p *= q;
-    }
-    double excl = shfl_up_f64(p, 1);
-    if (sl == 0) excl = 1.0;
-    float ar = 0.f, ag = 0.f, ab = 0.f, adepth = 0.f, aacc = 0.f;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const float T = static_cast<float>(excl * excl_in[j]);
-      const bool valid = ray_ok && (FULL || base + j < S);
-      const float w = valid ? __fmul_rn(alpha[j], T) : 0.0f;
-      s_wt[lane * L::KZ + j] = w;
-      if (valid) {
-        // sigmoid with ex2.approx / rcp.approx: |error| <= s(1-s)*(2+1.16|x|) ulp + 1 ulp < 1.2e-7 absolute, inside
-        // the 2e-6 gate of the fp32 path; it removes three IEEE-division slow-path stubs per sample.
-        const float sr = fast_sigmoid(rv[j].x), sg = fast_sigmoid(rv[j].y), sb = fast_sigmoid(rv[j].z);
-        ar = __fadd_rn(ar, __fmul_rn(w, sr));
-        ag = __fadd_rn(ag, __fmul_rn(w, sg));
-        ab = __fadd_rn(ab, __fmul_rn(w, sb));
-        adepth = __fadd_rn(adepth, __fmul_rn(w, zr[j]));
-        aacc = __fadd_rn(aacc, w);
-      }
-    }
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
-      ar += __shfl_xor_sync(0xffffffffu, ar, o);
-      ag += __shfl_xor_sync(0xffffffffu, ag, o);
-      ab += __shfl_xor_sync(0xffffffffu, ab, o);
-      adepth += __shfl_xor_sync(0xffffffffu, adepth, o);
-      aacc += __shfl_xor_sync(0xffffffffu, aacc, o);
-    }
+    for (int j = 0; j < K; ++j) s_wt[lane * L::KZ + j] = w[j];
     __syncwarp();
     if (weights != nullptr) {
       const int n = chunk_len(g);
@@ -347,11 +280,7 @@ raw2outputs_blocked_kernel(long long n_rays, int S, const float4* __restrict__ r
       }
       if (depth_map != nullptr) depth_map[ray] = adepth;
       if (acc_map != nullptr) acc_map[ray] = aacc;
-      if (disp_map != nullptr) {
-        const float q = __fdiv_rn(adepth, aacc);
-        const float m = (q != q) ? q : fmaxf(1e-10f, q);   // torch.max propagates NaN
-        disp_map[ray] = __fdiv_rn(1.0f, m);
-      }
+      if (disp_map != nullptr) disp_map[ray] = comp_disp(adepth, aacc);
     }
     __syncwarp();   // every lane is done with this stage and with s_wt before they are overwritten
   }
@@ -377,6 +306,95 @@ static int launch_blocked(long long n_rays, int S, const float4* raw4, const flo
   if (blocks > cap) blocks = cap;
   raw2outputs_blocked_kernel<K, FULL, RPW><<<static_cast<int>(blocks), kBlkWarps * 32, smem, st>>>(
       n_rays, S, raw4, z_vals, rays_d, d_stride, noise, white_bkgd, rgb_map, disp_map, acc_map, weights, depth_map);
+  R2L_LAUNCH_CHECK();
+  return R2L_OK;
+}
+
+// ---- the flagged rays of a fused NeRF frame (mlp_nerf_pp.cu compositor + nerf_far.cu) ----------------------------
+// Entry e < min(*count, cap) of `list` names a ray whose staged rows were copied to far_raw[e][S] and whose far-sample
+// sigma the fp32 fix-up has just patched there: composite it again (same blocked arithmetic, same K / lanes per ray
+// as r2l_raw2outputs uses for this S) and overwrite the ray's outputs.
+template <int K, int RPW>
+__global__ void __launch_bounds__(kBlkWarps * 32)
+raw2outputs_list_kernel(const int* __restrict__ list, const int* __restrict__ count, int cap, int S,
+                        const float4* __restrict__ far_raw, const float* __restrict__ z_vals,
+                        const float* __restrict__ rays_d, long long d_stride, int white_bkgd, float* __restrict__ rgb_map,
+                        float* __restrict__ disp_map, float* __restrict__ acc_map, float* __restrict__ weights,
+                        float* __restrict__ depth_map) {
+  constexpr int LPR = 32 / RPW;
+  const int lane = threadIdx.x & 31;
+  const int sl = lane % LPR;
+  int n = *count;
+  if (n > cap) n = cap;
+  const int n_groups = (n + RPW - 1) / RPW;
+  for (int g = blockIdx.x * kBlkWarps + (threadIdx.x >> 5); g < n_groups; g += gridDim.x * kBlkWarps) {
+    const int e = g * RPW + lane / LPR;
+    const bool ok = e < n;
+    const int ec = ok ? e : n - 1;
+    const long long ray = list[ec];
+    const float dnorm = comp_dnorm(__ldg(rays_d + ray * d_stride), __ldg(rays_d + ray * d_stride + 1),
+                                   __ldg(rays_d + ray * d_stride + 2));
+    const int base = sl * K;
+    float4 rv[K];
+    float zr[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      rv[j] = far_raw[static_cast<long long>(ec) * S + base + j];
+      zr[j] = __ldg(z_vals + ray * S + base + j);
+    }
+    const float z_next_lane = __shfl_down_sync(0xffffffffu, zr[0], 1);
+    float w[K];
+    float ar, ag, ab, adepth, aacc;
+    blocked_composite<K, true, LPR>(rv, zr, z_next_lane, sl, S, ok, dnorm, nullptr, w, ar, ag, ab, adepth, aacc);
+    if (ok && weights != nullptr) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) weights[ray * S + base + j] = w[j];
+    }
+    if (sl == 0 && ok) {
+      if (white_bkgd) {
+        const float bg = __fsub_rn(1.0f, aacc);
+        ar = __fadd_rn(ar, bg);
+        ag = __fadd_rn(ag, bg);
+        ab = __fadd_rn(ab, bg);
+      }
+      if (rgb_map != nullptr) {
+        rgb_map[3 * ray] = ar;
+        rgb_map[3 * ray + 1] = ag;
+        rgb_map[3 * ray + 2] = ab;
+      }
+      if (depth_map != nullptr) depth_map[ray] = adepth;
+      if (acc_map != nullptr) acc_map[ray] = aacc;
+      if (disp_map != nullptr) disp_map[ray] = comp_disp(adepth, aacc);
+    }
+  }
+}
+
+bool fused_composite_shape(int S, int* K, int* RPW) {
+  int k = 0, r = 0;
+  if (S == 64) k = 8, r = 4;
+  else if (S == 128) k = 8, r = 2;
+  else if (S == 192) k = 6, r = 1;
+  else if (S == 256) k = 8, r = 1;
+  if (K) *K = k;
+  if (RPW) *RPW = r;
+  return k != 0;
+}
+
+int raw2outputs_list_launch(const int* list, const int* count, int cap, int S, const float4* far_raw,
+                            const float* z_vals, const float* rays_d, long long d_stride, int white_bkgd,
+                            float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map,
+                            cudaStream_t st) {
+  const int grid = sm_count();
+#define R2L_LIST(K, RPW)                                                                                             \
+  raw2outputs_list_kernel<K, RPW><<<grid, kBlkWarps * 32, 0, st>>>(list, count, cap, S, far_raw, z_vals, rays_d,      \
+                                                                    d_stride, white_bkgd, rgb_map, disp_map, acc_map, \
+                                                                    weights, depth_map)
+  if (S == 64) R2L_LIST(8, 4);
+  else if (S == 128) R2L_LIST(8, 2);
+  else if (S == 192) R2L_LIST(6, 1);
+  else if (S == 256) R2L_LIST(8, 1);
+  else return fail(R2L_ERR_UNSUPPORTED, "raw2outputs_list: S = %d has no fused compositing shape", S);
+#undef R2L_LIST
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }

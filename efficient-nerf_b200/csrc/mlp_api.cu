@@ -168,6 +168,15 @@ struct Mlp {
   long long far_cap = 0;
   int far_mode = 1;                // 0: off (raw sigma of the 16-bit kernels), 1: flag + fp32 fix-up
   float far_abs = 1e-4f, far_rel = 9.765625e-4f;   // guard band: |sigma| < max(far_abs, far_rel * sum |w_a| relu(h7))
+  // fused compositing (r2l_nerf_render): per-CTA staging rings + far slots, the compact copy of the flagged rays' rows,
+  // and the raw workspace of the unfused route
+  float4* comp_ring = nullptr;
+  int* comp_aux = nullptr;
+  float4* comp_far_raw = nullptr;
+  size_t comp_far_bytes = 0;
+  float* raw_ws = nullptr;
+  size_t raw_ws_bytes = 0;
+  int comp_mode = 1;               // 0: r2l_nerf_render always takes the unfused route (MLP -> raw -> raw2outputs)
   R2lPairMaps* r2l_maps = nullptr; // R2L pair mode: tensor maps over wstream
   // R2L
   int n_points = 0, n_blocks = 0, sigmoid_out = 1, outer_skip = 1;
@@ -222,6 +231,17 @@ static int pair_mode_default() {
 // overlap buys.  So the default stays 0; the kernel is kept as a tested alternative.
 static int r2l_pp_default() {
   const char* e = getenv("R2L_PP");
+  return (e != nullptr && e[0] == '1') ? 1 : 0;
+}
+
+// r2l_nerf_render's route.  Fused compositing (R2L_NERF_FUSED=1 or r2l_nerf_render_mode) removes the raw [N,S,4] round
+// trip — 1.3 GB of HBM traffic per 400x400 frame — and is bit-identical, but the frame is NOT faster: A/B on one box,
+// 160 000 rays x (64 + 192) samples: two-step route 35.9-36.0 ms, fused 36.4-36.5 ms, the same kernel with the
+// compositor's body skipped 35.95 ms.  The compositor runs on the encoder warps, which share their schedulers with the
+// epilogue warps: its ~1 k instructions per unit land on the epilogues every tile-layer waits for.  The MLP kernel is
+// tensor-bound, the stand-alone raw2outputs runs at 80 % of the HBM roofline and costs 0.23 ms; so the default is 0.
+static int nerf_fused_default() {
+  const char* e = getenv("R2L_NERF_FUSED");
   return (e != nullptr && e[0] == '1') ? 1 : 0;
 }
 
@@ -282,6 +302,10 @@ static void destroy(Mlp* m) {
   if (m->vb_ws) cudaFree(m->vb_ws);
   if (m->far_wt) cudaFree(m->far_wt);
   if (m->far_ws) cudaFree(m->far_ws);
+  if (m->comp_ring) cudaFree(m->comp_ring);
+  if (m->comp_aux) cudaFree(m->comp_aux);
+  if (m->comp_far_raw) cudaFree(m->comp_far_raw);
+  if (m->raw_ws) cudaFree(m->raw_ws);
   if (m->aux) cudaFree(m->aux);
   if (m->dbg_host) cudaFreeHost(m->dbg_host);
   delete m->pp_maps;
@@ -476,7 +500,7 @@ using namespace r2l;
 extern "C" {
 
 const char* r2l_last_error(void) { return g_last_error.c_str(); }
-int r2l_abi_version(void) { return 6; }
+int r2l_abi_version(void) { return 7; }
 
 // Number of CUDA kernels this library has launched so far in this process (all entry points, all streams).
 long long r2l_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
@@ -644,6 +668,7 @@ int r2l_nerf_create(void** out_handle, int dtype, const float* const* pts_w, con
   if (rc != R2L_OK) return cleanup(rc);
   if (off != elems) return cleanup(fail(R2L_ERR_INVALID, "r2l_nerf_create: internal stream size mismatch"));
   m->nerf_pp = nerf_pp_default();
+  m->comp_mode = nerf_fused_default();
   if (m->nerf_pp) {
     // second stream for the ping-pong kernel: CTA-pair layout (two N-halves per stage), no view stage — the view
     // half of views_linears[0] becomes a per-ray fp32 bias (nerf_view_bias_kernel) from view_tab
@@ -752,7 +777,15 @@ static int nerf_run(Mlp* m, NerfParams& p, cudaStream_t st) {
   }
   int rc = nerf_run_mlp(m, p, st);
   if (rc != R2L_OK || !far) return rc;
-  return nerf_far_fixup_launch(m->far_wt, m->alpha_b, p.far_list, p.far_count, p.far_cap, m->far_ws + 1, p, st);
+  if (p.comp_ring == nullptr)
+    return nerf_far_fixup_launch(m->far_wt, m->alpha_b, p.far_list, p.far_count, p.far_cap, m->far_ws + 1, p, p.raw, 0, st);
+  // fused compositing: the flagged rays' rows sit in comp_far_raw (list order): patch sigma there, composite them again
+  const int cap = p.far_cap < p.comp_far_cap ? p.far_cap : p.comp_far_cap;
+  rc = nerf_far_fixup_launch(m->far_wt, m->alpha_b, p.far_list, p.far_count, cap, m->far_ws + 1, p,
+                             reinterpret_cast<float*>(p.comp_far_raw), 1, st);
+  if (rc != R2L_OK) return rc;
+  return raw2outputs_list_launch(p.far_list, p.far_count, cap, p.S, p.comp_far_raw, p.z_vals, p.rays_d, p.d_stride,
+                                 p.white_bkgd, p.o_rgb, p.o_disp, p.o_acc, p.o_weights, p.o_depth, st);
 }
 
 static int nerf_run_mlp(Mlp* m, NerfParams& p, cudaStream_t st) {
@@ -784,10 +817,25 @@ static int nerf_run_mlp(Mlp* m, NerfParams& p, cudaStream_t st) {
     if (rc != R2L_OK) return rc;
     p.vb = m->vb_ws;
     p.wstream = m->wstream_pp;
-    const long long n_units = (n_tiles + 3) / 4;
-    const long long max_pairs = sm_count() / 2;
-    const int grid = static_cast<int>(2 * (n_units < max_pairs ? n_units : max_pairs));
-    return nerf_mlp_pp_launch(m->bf16, p, *m->pp_maps, *m->head_w, grid, st);
+    // CTA c owns tiles [c*T, (c+1)*T).  T is a multiple of `gran` tiles: 2 (the two tiles a CTA runs side by side),
+    // and with fused compositing also of the tiles a compositing group spans, so every group stays inside one CTA.
+    long long gran = 2;
+    if (p.comp_ring != nullptr) {
+      const long long grows = 32LL * p.comp_K;            // rows of a group: 256 or 192
+      long long a = grows, b = kTileM;
+      while (b) { const long long r = a % b; a = b; b = r; }
+      const long long g_tiles = grows / a;                // tiles until group and tile boundaries coincide: 2 or 3
+      gran = (g_tiles % 2 == 0) ? g_tiles : 2 * g_tiles;
+    }
+    const long long chunks = (n_tiles + gran - 1) / gran;
+    const long long max_ctas = sm_count() & ~1;
+    long long ctas = chunks < max_ctas ? chunks : max_ctas;
+    ctas += ctas & 1;
+    p.tiles_per_cta = static_cast<int>(((chunks + ctas - 1) / ctas) * gran);
+    // CTAs (pairs) that would start past the last tile are not launched
+    long long used = (n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    used += used & 1;
+    return nerf_mlp_pp_launch(m->bf16, p, *m->pp_maps, *m->head_w, static_cast<int>(used), st);
   }
   const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   return nerf_mlp_launch(m->bf16, p, grid, st);
@@ -815,8 +863,103 @@ int r2l_nerf_forward(void* handle, long long n_rays, int S, const float* rays_o,
   p.z_vals = z_vals;
   p.S = S;
   p.n_rows = n_rays * S;
+  p.n_rays = n_rays;
   p.raw = raw;
   return nerf_run(m, p, static_cast<cudaStream_t>(stream));
+}
+
+int r2l_raw2outputs(long long n_rays, int S, const float* raw, const float* z_vals, const float* rays_d,
+                    long long d_stride, const float* noise, int white_bkgd, float* rgb_map, float* disp_map,
+                    float* acc_map, float* weights, float* depth_map, void* stream);   // composite.cu
+
+// render_rays' inner half in one call (main.py:707-709 / 738-741): raw = network(points), then raw2outputs(raw) ->
+// rgb_map [n,3], disp_map, acc_map, depth_map [n] (nullable), weights [n,S] (nullable).  No noise (raw_noise_std = 0).
+// Fused route (ping-pong kernel, S in {64,128,192,256}): the MLP kernel composites the rays itself, raw [n,S,4] never
+// exists; otherwise MLP -> workspace -> r2l_raw2outputs.  Both routes give the same bits.
+int r2l_nerf_render(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
+                    const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
+                    const float* z_vals, int white_bkgd, float* rgb_map, float* disp_map, float* acc_map,
+                    float* weights, float* depth_map, void* stream) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_render: not a NeRF handle");
+  R2L_CHECK_ARG(n_rays >= 0 && S >= 2 && d_stride >= 3, "r2l_nerf_render: bad sizes");
+  if (n_rays == 0) return R2L_OK;
+  R2L_CHECK_ARG(rays_o && rays_d && viewdirs && z_vals && rgb_map, "r2l_nerf_render: null pointer");
+  R2L_CHECK_ARG(n_rays < (1LL << 31) / 4, "r2l_nerf_render: too many rays for one call");
+  int rc = check_dbg(m, "r2l_nerf_render");
+  if (rc != R2L_OK) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  NerfParams p{};
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.viewdirs = viewdirs;
+  p.o_stride = o_stride;
+  p.d_stride = d_stride;
+  p.v_stride = v_stride;
+  p.z_vals = z_vals;
+  p.S = S;
+  p.n_rows = n_rays * S;
+  p.n_rays = n_rays;
+  int K = 0, RPW = 0;
+  const bool fused = m->comp_mode != 0 && m->nerf_pp && fused_composite_shape(S, &K, &RPW);
+  if (!fused) {
+    const size_t need = static_cast<size_t>(n_rays) * S * 16;
+    if (need > m->raw_ws_bytes) {
+      R2L_CUDA(cudaStreamSynchronize(st));
+      if (m->raw_ws) cudaFree(m->raw_ws);
+      m->raw_ws = nullptr;
+      m->raw_ws_bytes = 0;
+      R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->raw_ws), need));
+      m->raw_ws_bytes = need;
+    }
+    p.raw = m->raw_ws;
+    rc = nerf_run(m, p, st);
+    if (rc != R2L_OK) return rc;
+    return r2l_raw2outputs(n_rays, S, m->raw_ws, z_vals, rays_d, d_stride, nullptr, white_bkgd, rgb_map, disp_map,
+                           acc_map, weights, depth_map, stream);
+  }
+  if (m->comp_ring == nullptr) {
+    const size_t rows = static_cast<size_t>(sm_count()) * 512;
+    R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->comp_ring), rows * sizeof(float4)));
+    R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->comp_aux), rows * sizeof(int)));
+  }
+  // compact copy of the flagged rays' rows: room for a quarter of the rays (random-init nets flag ~2 % in the coarse
+  // pass, trained ones far fewer); rays beyond it keep the 16-bit sigma and show up in r2l_nerf_far_count
+  long long far_rows = n_rays / 4;
+  if (far_rows < 4096) far_rows = n_rays < 4096 ? n_rays : 4096;
+  if (m->far_mode != 0) {
+    const size_t need = static_cast<size_t>(far_rows) * S * sizeof(float4);
+    if (need > m->comp_far_bytes) {
+      R2L_CUDA(cudaStreamSynchronize(st));
+      if (m->comp_far_raw) cudaFree(m->comp_far_raw);
+      m->comp_far_raw = nullptr;
+      m->comp_far_bytes = 0;
+      R2L_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->comp_far_raw), need));
+      m->comp_far_bytes = need;
+    }
+  }
+  p.comp_ring = m->comp_ring;
+  p.comp_aux = m->comp_aux;
+  p.comp_far_raw = m->comp_far_raw;
+  p.comp_far_cap = static_cast<int>(far_rows);
+  p.comp_K = K;
+  p.comp_RPW = RPW;
+  p.white_bkgd = white_bkgd;
+  p.o_rgb = rgb_map;
+  p.o_disp = disp_map;
+  p.o_acc = acc_map;
+  p.o_depth = depth_map;
+  p.o_weights = weights;
+  return nerf_run(m, p, st);
+}
+
+// 0 (default): r2l_nerf_render takes the two-step route (MLP -> raw workspace -> raw2outputs); 1: fused where it applies
+int r2l_nerf_render_mode(void* handle, int fused) {
+  Mlp* m = static_cast<Mlp*>(handle);
+  R2L_CHECK_ARG(m != nullptr && m->kind == 0, "r2l_nerf_render_mode: not a NeRF handle");
+  R2L_CHECK_ARG(fused == 0 || fused == 1, "r2l_nerf_render_mode: mode must be 0 or 1");
+  m->comp_mode = fused;
+  return R2L_OK;
 }
 
 // NeRF.forward(x) API path: x [M, ldx] holds 63 embedded-point features followed by 27
@@ -893,6 +1036,7 @@ int r2l_nerf_profile(void* handle, long long n_rays, int S, const float* rays_o,
   p.z_vals = z_vals;
   p.S = S;
   p.n_rows = n_rays * S;
+  p.n_rays = n_rays;
   p.raw = raw;
   p.prof = prof;
   { const char* e = getenv("R2L_PROF_MODE"); p.prof_mode = (e != nullptr) ? atoi(e) : 0; }

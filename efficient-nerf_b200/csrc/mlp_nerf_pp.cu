@@ -38,6 +38,7 @@
 // Per tile: 10 steps (see mlp_nerf.cu): 0 = W0 P, 1-4, 5 = W5 [P, h], 6, 7 (+sigma), 8 = feature, 9 = views (N 128).
 #include "common.cuh"
 #include "mlp_params.cuh"
+#include "composite_math.cuh"
 #include "mlp_tc.cuh"
 #include <type_traits>
 
@@ -80,12 +81,116 @@ constexpr int kPpOffRgbW = kPpOffAlphaW + 256 * 4;                    // 3*128 f
 constexpr int kPpOffPart = kPpOffRgbW + 384 * 4;                      // 128 x float4
 constexpr int kPpOffAbs = kPpOffPart + 128 * 16;                      // 128 floats: WG1's half of sum |w_a| relu(h7)
 constexpr int kPpOffBars = kPpOffAbs + 128 * 4;
-constexpr int kPpNumBars = 2 * kPpRing + 2 * kPpBiasRing + 2 + 2 + 2 + 2 + 2 + 1;
+constexpr int kPpNumBars = 2 * kPpRing + 2 * kPpBiasRing + 2 + 2 + 2 + 2 + 2 + 1 + 2;
 static_assert(2 * 2 * 128 * 4 <= (256 + 384) * 4, "view-bias rows must fit the old head-weight region");
 constexpr int kPpOffTmem = kPpOffBars + kPpNumBars * 8;
 constexpr int kPpSmemBytes = kPpOffTmem + 16;
 static_assert(kPpSmemBytes <= 227 * 1024, "NeRF ping-pong kernel shared memory exceeds 227 KiB");
 static_assert(kPpOffRing % 1024 == 0, "weight ring must stay 1 KiB aligned");
+
+constexpr int kCompRingRows = 512;   // rows of a CTA's staging ring (two units)
+
+// Fused compositing (NerfParams::comp_ring): one warp composites group `gidx` of this CTA — comp_RPW consecutive rays =
+// 32 * comp_K staged rows — with the arithmetic, the sample partition and the scan order of raw2outputs_blocked_kernel
+// (composite.cu; shared definitions in composite_math.cuh), so a fused frame equals MLP + r2l_raw2outputs bit for
+// bit.  Compact on purpose (two passes over the lane's samples instead of register arrays, run-time K): it is called
+// once per unit and the ping-pong kernel is sensitive to code size.
+static __device__ __noinline__ void pp_composite_group(const NerfParams& p, const float4* ring, const int* aux,
+                                                       unsigned cta_unit0, int gidx, int lane) {
+  const int K = p.comp_K, LPR = 32 / p.comp_RPW, S = p.S;
+  const int sl = lane & (LPR - 1), rl = lane / LPR;
+  const unsigned n_rays = static_cast<unsigned>(p.n_rays);
+  const unsigned grow0 = static_cast<unsigned>(gidx) * 32u * static_cast<unsigned>(K);   // CTA-local row of the group
+  // first ray of the group, on 32-row units (S is a multiple of 32; tile counts are < 2^29: host)
+  const unsigned ray = (cta_unit0 + static_cast<unsigned>(gidx) * K) / (static_cast<unsigned>(S) >> 5) + rl;
+  const bool ray_ok = ray < n_rays;
+  const long long rr = ray_ok ? ray : n_rays - 1;
+  const float* dp = p.rays_d + rr * p.d_stride;
+  const float dnorm = comp_dnorm(__ldg(dp), __ldg(dp + 1), __ldg(dp + 2));
+  const int base = sl * K;
+  const unsigned r0 = grow0 + static_cast<unsigned>(lane * K);
+  const float* zrow = p.z_vals + rr * S + base;
+  // Every load of the lane's samples is issued up front (one L2 round trip, not one per sample) and the loops are
+  // unrolled for K = 8 with `j < K` predicates, so everything stays in registers: with run-time loops the arrays lived
+  // in local memory, and with the 227 KB shared-memory carve-out the L1 is too small to hold them — the compositor
+  // then took long enough to delay the point blocks these warps owe the issuers (2 ms per frame, A/B on one box).
+  float4 rv[8];
+  float zr[9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    zr[j] = 0.0f;
+    if (j < K) {
+      rv[j] = __ldcg(&ring[(r0 + j) & (kCompRingRows - 1)]);
+      zr[j] = __ldg(zrow + j);
+    }
+  }
+  const float z_after = (base + K < S) ? __ldg(zrow + K) : 0.0f;   // first sample of the next lane
+  zr[8] = z_after;
+  // far slot of this lane's ray (written by the thread that owned the ray's last sample)
+  int fs = -1;
+  if (p.far_list != nullptr) {
+    if (sl == LPR - 1) fs = __ldcg(&aux[(grow0 + static_cast<unsigned>(rl * S + S - 1)) & (kCompRingRows - 1)]);
+    fs = __shfl_sync(0xffffffffu, fs, rl * LPR + LPR - 1);
+    if (!ray_ok || fs >= p.comp_far_cap) fs = -1;
+  }
+  float alpha[8];
+  double excl_in[8];
+  double run = 1.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float zn = (j + 1 == K) ? z_after : zr[j + 1];
+    const float a = comp_alpha(rv[j].w, comp_dist(zr[j], zn, base + j == S - 1, dnorm));
+    alpha[j] = a;
+    excl_in[j] = run;
+    if (ray_ok && j < K) run *= static_cast<double>(__fadd_rn(__fsub_rn(1.0f, a), 1e-10f));
+  }
+  double pr = run;   // inclusive scan of the lane totals, segmented by ray
+  for (int o = 1; o < LPR; o <<= 1) {
+    const double q = shfl_up_f64(pr, o);
+    if (sl >= o) pr *= q;
+  }
+  double excl = shfl_up_f64(pr, 1);
+  if (sl == 0) excl = 1.0;
+  float ar = 0.f, ag = 0.f, ab = 0.f, adepth = 0.f, aacc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float T = static_cast<float>(excl * excl_in[j]);
+    const float wj = __fmul_rn(alpha[j], T);
+    if (ray_ok && j < K) {
+      const float4 v = rv[j];
+      const float sr = fast_sigmoid(v.x), sg = fast_sigmoid(v.y), sb = fast_sigmoid(v.z);
+      ar = __fadd_rn(ar, __fmul_rn(wj, sr));
+      ag = __fadd_rn(ag, __fmul_rn(wj, sg));
+      ab = __fadd_rn(ab, __fmul_rn(wj, sb));
+      adepth = __fadd_rn(adepth, __fmul_rn(wj, zr[j]));
+      aacc = __fadd_rn(aacc, wj);
+      if (p.o_weights != nullptr) p.o_weights[rr * S + base + j] = wj;
+      if (fs >= 0) p.comp_far_raw[static_cast<long long>(fs) * S + base + j] = v;
+    }
+  }
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+    ag += __shfl_xor_sync(0xffffffffu, ag, o);
+    ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    adepth += __shfl_xor_sync(0xffffffffu, adepth, o);
+    aacc += __shfl_xor_sync(0xffffffffu, aacc, o);
+  }
+  if (sl == 0 && ray_ok) {
+    if (p.white_bkgd) {
+      const float bg = __fsub_rn(1.0f, aacc);
+      ar = __fadd_rn(ar, bg);
+      ag = __fadd_rn(ag, bg);
+      ab = __fadd_rn(ab, bg);
+    }
+    p.o_rgb[3 * rr] = ar;
+    p.o_rgb[3 * rr + 1] = ag;
+    p.o_rgb[3 * rr + 2] = ab;
+    if (p.o_depth != nullptr) p.o_depth[rr] = adepth;
+    if (p.o_acc != nullptr) p.o_acc[rr] = aacc;
+    if (p.o_disp != nullptr) p.o_disp[rr] = comp_disp(adepth, aacc);
+  }
+}
 
 __device__ __forceinline__ int pp_main_stages(int step) { return step == 0 ? 1 : (step == 5 ? 5 : 4); }
 
@@ -97,9 +202,13 @@ __device__ __forceinline__ int pp_main_stages(int step) { return step == 0 ? 1 :
 // own 16 x float4 from L2 after the accumulator wait put ~2300 cycles into that epilogue (in-kernel trace), and the
 // two step-9 epilogues are what the unit boundary waits for.  UNI = false: general S and the NeRF.forward(x) rows
 // (every row its own bias row, loaded from global memory).
-template <bool BF16, bool PROF, bool UNI>
+// COMP = true (needs UNI; r2l_nerf_render's fused route): the kernel composites the rays itself (NerfParams::comp_ring).
+// Its own instantiation: the compositor is ~26 KB of code, and the kernel without it is measurably faster per frame
+// (these kernels are sensitive to code size, see the epilogue), so the plain forward does not carry it.
+template <bool BF16, bool PROF, bool UNI, bool COMP>
 __global__ void __launch_bounds__(kPpThreads, 1)
-nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, const __grid_constant__ NerfHeadW hw) {
+nerf_mlp_pp_kernel(const __grid_constant__ NerfParams p, const __grid_constant__ NerfPpMaps maps,
+                   const __grid_constant__ NerfHeadW hw) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const sA = smem + kPpOffA;
   uint8_t* const sP = smem + kPpOffP;
@@ -122,15 +231,19 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
   uint64_t* const p_free = p_ready + 2;             // [tile]: tile t's MMAs that read P have completed (commit, both CTAs)
   uint64_t* const turn = p_free + 2;                // [tile]: leader; the other issuer has issued its tile-layer
   uint64_t* const vb_ready = turn + 2;              // THIS CTA: its 4 encoder warps have staged the unit's view-bias rows
+  uint64_t* const raw_ready = vb_ready + 1;         // [tile] THIS CTA (fused compositing): WG0's 4 warps have staged the tile's (rgb, sigma) rows
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + kPpOffTmem);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
-  // a unit = 4 tiles: tile(unit, t, rank) = 4*unit + 2*t + rank
-  const int n_units = (p.n_tiles + 3) / 4;
-  const int unit0 = static_cast<int>(blockIdx.x >> 1);
-  const int unit_step = static_cast<int>(gridDim.x >> 1);
+  // CTA c owns the CONTIGUOUS tiles [c*T, (c+1)*T) (T even): a unit = tiles tile0 + 2*unit + {0, 1} of BOTH CTAs of
+  // the pair, so a ray's samples stay inside one CTA (what the fused compositing needs).  The pair runs while its
+  // leader (the lower tile range) has tiles left; rows past the end are clamped / masked as before.
+  const long long tile0 = static_cast<long long>(blockIdx.x) * p.tiles_per_cta;
+  const long long lead_left = static_cast<long long>(p.n_tiles) - static_cast<long long>(blockIdx.x & ~1u) * p.tiles_per_cta;
+  const int n_units = lead_left <= 0 ? 0 : static_cast<int>(lead_left >= p.tiles_per_cta ? p.tiles_per_cta / 2 : (lead_left + 1) / 2);
+  constexpr int unit0 = 0, unit_step = 1;
 
   // ---- one-time setup ----
   write_ones_block<BF16>(sOnes, threadIdx.x, kPpThreads);
@@ -151,6 +264,8 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
       mbar_init(&turn[i], 1);
     }
     mbar_init(vb_ready, 4);
+    mbar_init(&raw_ready[0], 4);
+    mbar_init(&raw_ready[1], 4);
     mbar_fence_init();
   }
   fence_proxy_async_smem();
@@ -389,10 +504,24 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
     // the PREVIOUS use's MMAs (p_free of the other tile).
     const int row = (warp & 3) * 32 + lane;
     uint32_t n_enc = 0;   // uses encoded so far; use n belongs to tile n & 1
+    // Fused compositing: the groups (comp_RPW rays = 32 * comp_K rows) whose last row unit v staged, one per warp.
+    // The ring rows read here are rewritten by unit v + 2's last epilogues (v + 1's for the carried part of a
+    // straddling ray), which come after the step-5 MMAs that wait for the block these warps encode NEXT: no extra
+    // barrier is needed for the reuse.
+    auto composite_unit = [&](int v) {
+      mbar_wait(&raw_ready[0], v & 1u, p.dbg, 520, 8);
+      mbar_wait(&raw_ready[1], v & 1u, p.dbg, 521, 8);
+      const int grows = 32 * p.comp_K;
+      const int g_first = (2 * kTileM * v) / grows, g_end = (2 * kTileM * (v + 1)) / grows;
+      for (int g = g_first + (warp & 3); g < g_end; g += 4)
+        pp_composite_group(p, p.comp_ring + static_cast<size_t>(blockIdx.x) * kCompRingRows,
+                           p.comp_aux + static_cast<size_t>(blockIdx.x) * kCompRingRows,
+                           static_cast<unsigned>(tile0) * (kTileM / 32), g, lane);
+    };
     for (int unit = unit0; unit < n_units; unit += unit_step) {
       for (int use = 0; use < 4; ++use, ++n_enc) {
         const int t = use & 1;
-        const long long tile = 4LL * unit + 2 * t + rank;
+        const long long tile = tile0 + 2 * unit + t;
         long long gr = tile * kTileM + row;
         if (gr >= p.n_rows) gr = p.n_rows - 1;
         // previous use n_enc-1 was tile 1-t's ((n_enc-1)/2)-th use: its p_free phase index is (n_enc-1)/2
@@ -431,6 +560,10 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) lane_arrive<true>(&p_ready[t]);
+        // Fused compositing of the PREVIOUS unit's rays: this point (T1's first block of the unit is encoded) is
+        // reached right after T0's step 0 of this unit, i.e. when the previous unit's last epilogues are finishing, and
+        // the next thing these warps owe anybody (T0's step-5 block) is five layers away.
+        if (COMP && use == 1 && unit > 0) composite_unit(unit - 1);
       }
       if (UNI) {
         // the unit's view-bias rows: thread `row` copies column `row` of the (at most two) rays of each tile.  The
@@ -438,7 +571,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
         // step-5 MMAs of THIS unit (p_free), which the same epilogue warps fed after finishing the previous unit.
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          const long long r_first = (4LL * unit + 2 * t + rank) * kTileM;
+          const long long r_first = (tile0 + 2 * unit + t) * kTileM;
           long long ra = r_first, rb = r_first + kTileM - 1;
           if (ra >= p.n_rows) ra = p.n_rows - 1;
           if (rb >= p.n_rows) rb = p.n_rows - 1;
@@ -449,6 +582,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
         if (lane == 0) mbar_arrive(vb_ready);
       }
     }
+    if (COMP && n_units > 0) composite_unit(n_units - 1);
   } else {
     // ===================== epilogue warpgroups (both tiles, alternating) =====================
     const int wg = warp >> 2;                       // owns the 32-column pieces wg, wg+2, wg+4, wg+6
@@ -532,7 +666,7 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
             uint32_t va[32], vb[32];
             tmem_ld32(lane_taddr + 256 * t + 32 * wg, va);
             tmem_ld32(lane_taddr + 256 * t + 64 + 32 * wg, vb);
-            const long long tile = 4LL * unit + 2 * t + rank;
+            const long long tile = tile0 + 2 * unit + t;
             const long long g_row = tile * kTileM + row;
             const bool valid = g_row < p.n_rows;
             long long ray;
@@ -611,9 +745,21 @@ nerf_mlp_pp_kernel(const NerfParams p, const __grid_constant__ NerfPpMaps maps, 
                 o.y = gch + o1.y + p.rgb_b[1];
                 o.z = b + o1.z + p.rgb_b[2];
                 o.w = sigma_mine + o1.w + p.alpha_b;
-                reinterpret_cast<float4*>(p.raw)[g_row] = o;
                 note_nonfinite(p.dbg, o.x + o.y + o.z + o.w, g_row);
-                nerf_far_flag(p, g_row, ray, o.w, 4.0f * (abs_mine + a1));
+                const int fslot = nerf_far_flag(p, g_row, ray, o.w, 4.0f * (abs_mine + a1));
+                if (COMP) {
+                  // fused compositing: stage the row in this CTA's ring (global memory, L2 resident)
+                  const size_t slot = static_cast<size_t>(blockIdx.x) * kCompRingRows +
+                                      ((2u * kTileM * static_cast<unsigned>(unit) + kTileM * t + row) & (kCompRingRows - 1));
+                  p.comp_ring[slot] = o;
+                  if (g_row - ray * p.S == p.S - 1) p.comp_aux[slot] = fslot;
+                } else {
+                  reinterpret_cast<float4*>(p.raw)[g_row] = o;
+                }
+              }
+              if (COMP) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_ready[t]);
               }
             }
           }
@@ -685,9 +831,9 @@ nerf_view_bias_kernel(long long n_rays, const float* __restrict__ viewdirs, long
   }
 }
 
-template <bool BF16, bool PROF, bool UNI>
+template <bool BF16, bool PROF, bool UNI, bool COMP = false>
 int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid, cudaStream_t st) {
-  R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16, PROF, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  R2L_CUDA(cudaFuncSetAttribute(nerf_mlp_pp_kernel<BF16, PROF, UNI, COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kPpThreads);
@@ -700,7 +846,7 @@ int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16, PROF, UNI>, p, maps, hw));
+  R2L_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_pp_kernel<BF16, PROF, UNI, COMP>, p, maps, hw));
   count_launch();
   return R2L_OK;
 }
@@ -709,6 +855,11 @@ int launch_nerf_pp(const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW&
 int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, const NerfHeadW& hw, int grid,
                        cudaStream_t st) {
   const bool uni = p.embedded == nullptr && p.S >= 64 && (p.S % 32) == 0;
+  if (p.comp_ring != nullptr) {
+    if (!uni || p.prof != nullptr) return fail(R2L_ERR_INVALID, "nerf_mlp_pp_launch: fused compositing needs ray samples with S %% 32 == 0");
+    return bf16 ? launch_nerf_pp<true, false, true, true>(p, maps, hw, grid, st)
+                : launch_nerf_pp<false, false, true, true>(p, maps, hw, grid, st);
+  }
   if (p.prof != nullptr)   // the profiling hooks exist for the render form only
     return bf16 ? launch_nerf_pp<true, true, true>(p, maps, hw, grid, st) : launch_nerf_pp<false, true, true>(p, maps, hw, grid, st);
   if (uni) return bf16 ? launch_nerf_pp<true, false, true>(p, maps, hw, grid, st) : launch_nerf_pp<false, false, true>(p, maps, hw, grid, st);

@@ -21,6 +21,7 @@ struct NerfParams {
   const float* z_vals;      // [n_rays*S]
   int S;
   long long n_rows;         // n_rays*S
+  long long n_rays;         // ray-sample calls (embedded == nullptr)
   float* raw;               // [n_rows][4]
   int n_tiles;
   DebugBuf* dbg;
@@ -35,21 +36,56 @@ struct NerfParams {
   int* far_count;
   int far_cap;
   float far_abs, far_rel;
+  // ping-pong kernel: CTA c owns the CONTIGUOUS tiles [c*T, (c+1)*T), T = tiles_per_cta (even; with fused compositing
+  // a multiple of the tiles a compositing group spans, so that no ray straddles two CTAs)
+  int tiles_per_cta;
+  // fused compositing (ping-pong kernel, UNI rows, S in {64,128,192,256}; raw2outputs main.py:556-621 inside the MLP
+  // kernel): the last epilogue stages (rgb, sigma) rows in a per-CTA ring in GLOBAL memory (512 rows = 8 KB per CTA:
+  // it never leaves the L2) instead of writing raw [N,S,4]; the otherwise idle encoder warps composite every ray
+  // whose last sample has arrived, with the arithmetic of raw2outputs_blocked_kernel (composite.cu: comp_K consecutive
+  // samples per lane, 32/comp_RPW lanes per ray).  Rays whose far sample is flagged (far_list) are composited too,
+  // and their staged rows are ALSO copied to comp_far_raw[slot] (slot = position in far_list) for the fix-up pass.
+  float4* comp_ring;        // nullptr: write raw (no compositing)
+  int* comp_aux;            // [grid][512]: far slot of a ray's LAST sample (-1 = not flagged), same indexing as the ring
+  float4* comp_far_raw;     // [comp_far_cap][S]
+  int comp_far_cap;
+  int comp_K, comp_RPW;
+  int white_bkgd;
+  float* o_rgb;             // [n_rays][3]
+  float* o_disp;            // [n_rays] or nullptr
+  float* o_acc;             // [n_rays] or nullptr
+  float* o_depth;           // [n_rays] or nullptr
+  float* o_weights;         // [n_rays][S] or nullptr
 };
 
 // far-sample sigma fix-up (nerf_far.cu)
 size_t nerf_far_weight_bytes();
 int nerf_far_pack(const float* const* pts_w, const float* const* pts_b, const float* alpha_w, float* Wt, cudaStream_t st);
+// out: raw [n_rays][S][4] (compact == 0: sigma of ray r's last sample) or the compact copy [cap][S][4] of the flagged
+// rays' rows (compact == 1: list position i -> row i)
 int nerf_far_fixup_launch(const float* Wt, float alpha_b, const int* list, const int* count, int cap, int* stats,
-                          const NerfParams& p, cudaStream_t st);
+                          const NerfParams& p, float* out, int compact, cudaStream_t st);
+
+// fused compositing (composite.cu): the (samples per lane, rays per warp) r2l_raw2outputs uses for S samples — the
+// compositor inside the ping-pong kernel follows the same partition; false: S has no fused shape
+bool fused_composite_shape(int S, int* K, int* RPW);
+int raw2outputs_list_launch(const int* list, const int* count, int cap, int S, const float4* far_raw,
+                            const float* z_vals, const float* rays_d, long long d_stride, int white_bkgd,
+                            float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map,
+                            cudaStream_t st);
 
 // The epilogue's test: is row g_row the far sample of its ray, and is its sigma inside the guard band?
-__device__ __forceinline__ void nerf_far_flag(const NerfParams& p, long long g_row, long long ray, float sigma,
-                                              float abs_sum) {
+// Returns the ray's position in far_list (-1: not flagged / not a far sample / dropped).
+__device__ __forceinline__ int nerf_far_flag(const NerfParams& p, long long g_row, long long ray, float sigma,
+                                             float abs_sum) {
   if (p.far_list != nullptr && g_row - ray * p.S == p.S - 1 && fabsf(sigma) < fmaxf(p.far_abs, p.far_rel * abs_sum)) {
     const int idx = atomicAdd(p.far_count, 1);
-    if (idx < p.far_cap) p.far_list[idx] = static_cast<int>(ray);
+    if (idx < p.far_cap) {
+      p.far_list[idx] = static_cast<int>(ray);
+      return idx;
+    }
   }
+  return -1;
 }
 
 // fp32 weights of the two heads that run on CUDA cores (alpha_linear [256], rgb_linear [3][128]), passed BY VALUE as a

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256, 1)
 nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __restrict__ list,
                       const int* __restrict__ count, int cap, int* __restrict__ stats, const float* __restrict__ rays_o,
                       long long o_stride, const float* __restrict__ rays_d, long long d_stride,
-                      const float* __restrict__ z_vals, int S, float* __restrict__ raw) {
+                      const float* __restrict__ z_vals, int S, float* __restrict__ out, int compact) {
   extern __shared__ __align__(16) float s_far[];
   float* const s_ring = s_far;                              // [kFarStages][kFarChunk][256]
   float* const s_emb = s_ring + kFarRingFloats;             // [sub][64][kFarG]: embedded point, reference order
@@ -206,8 +206,9 @@ nerf_far_fixup_kernel(const float* __restrict__ Wt, float alpha_b, const int* __
       const float* aw = Wt + kFarAlphaOff;
       const float* h = s_h + ((cur * kFarSub + tid / kFarG) * 256) * kFarG + (tid % kFarG);
       for (int kk = 0; kk < 256; ++kk) a = fmaf(h[kk * kFarG], __ldg(aw + kk), a);
-      const long long ray = list[g0 + tid];
-      raw[(ray * S + (S - 1)) * 4 + 3] = a + alpha_b;
+      // row of the patched sigma: the ray's own row of raw, or (fused compositing) row `list position` of the compact copy
+      const long long orow = compact ? static_cast<long long>(g0 + tid) : static_cast<long long>(list[g0 + tid]);
+      out[(orow * S + (S - 1)) * 4 + 3] = a + alpha_b;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
@@ -228,7 +229,7 @@ int nerf_far_pack(const float* const* pts_w, const float* const* pts_b, const fl
 size_t nerf_far_weight_bytes() { return sizeof(float) * kFarFloats; }
 
 int nerf_far_fixup_launch(const float* Wt, float alpha_b, const int* list, const int* count, int cap, int* stats,
-                          const NerfParams& p, cudaStream_t st) {
+                          const NerfParams& p, float* out, int compact, cudaStream_t st) {
   const int grid = sm_count();
   static bool attr_set = false;
   if (!attr_set) {
@@ -236,7 +237,7 @@ int nerf_far_fixup_launch(const float* Wt, float alpha_b, const int* list, const
     attr_set = true;
   }
   nerf_far_fixup_kernel<<<grid, 256, kFarSmemBytes, st>>>(Wt, alpha_b, list, count, cap, stats, p.rays_o, p.o_stride, p.rays_d,
-                                             p.d_stride, p.z_vals, p.S, p.raw);
+                                             p.d_stride, p.z_vals, p.S, out, compact);
   R2L_LAUNCH_CHECK();
   return R2L_OK;
 }

@@ -290,6 +290,44 @@ class NeRF(nn.Module):
                 evs.append((e0, e1))
         return raw
 
+    def render_samples(self, rays_o, rays_d, viewdirs, z_vals, white_bkgd=False, want_weights=True):
+        """Fused encode + MLP + raw2outputs (main.py:707-709 / 738-741 with raw_noise_std = 0): returns rgb_map,
+        disp_map, acc_map, weights (or None), depth_map — one library call (r2l_nerf_render); the same bits as
+        raw2outputs(forward_samples(...)).  With set_fused_compositing(True) (or R2L_NERF_FUSED=1) and 64 / 128 / 192 /
+        256 samples the CTA-pair kernel composites the rays itself and raw [N, S, 4] is never written: 1.3 GB less HBM
+        traffic per 400x400 frame, bit-identical, ~1 % slower — hence not the default."""
+        _check_infer_input(z_vals, "z_vals")
+        dev = z_vals.device
+        N, S = z_vals.shape
+        h = self.packed_handle()
+        ro, rd, vd = (_rows(t, dev) for t in (rays_o, rays_d, viewdirs))
+        z = _lib.as_f32_cuda(z_vals, dev)
+        rgb_map = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        disp_map = torch.empty((N,), dtype=torch.float32, device=dev)
+        acc_map = torch.empty((N,), dtype=torch.float32, device=dev)
+        depth_map = torch.empty((N,), dtype=torch.float32, device=dev)
+        weights = torch.empty((N, S), dtype=torch.float32, device=dev) if want_weights else None
+        evs = self.__dict__.get('_mlp_events')      # bench.py: CUDA events around the MLP launches of a step
+        with torch.cuda.device(dev):
+            if evs is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            _lib.call("r2l_nerf_render", h.h, N, S, _lib.ptr(ro), ro.stride(0), _lib.ptr(rd), rd.stride(0),
+                      _lib.ptr(vd), vd.stride(0), _lib.ptr(z), int(bool(white_bkgd)), _lib.ptr(rgb_map),
+                      _lib.ptr(disp_map), _lib.ptr(acc_map), _lib.ptr(weights), _lib.ptr(depth_map),
+                      _lib.stream_ptr(dev))
+            if evs is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                evs.append((e0, e1))
+        return rgb_map, disp_map, acc_map, weights, depth_map
+
+    def set_fused_compositing(self, enabled=True):
+        """True: render_samples composites inside the MLP kernel where it can; False (default): MLP -> raw workspace ->
+        raw2outputs inside the same library call."""
+        _lib.call("r2l_nerf_render_mode", self.packed_handle().h, 1 if enabled else 0)
+        self.__dict__['_fused_comp'] = bool(enabled)
+
     # -- nn.Module API ---------------------------------------------------------------------
     def forward(self, x):
         _check_infer_input(x, "x")

@@ -130,11 +130,22 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             return net.forward_samples(rays_o, rays_d, viewdirs, z)
         return network_query_fn(_points(rays_o, rays_d, z), viewdirs, net)
 
-    raw = query(z_vals, network_fn)
-    if noise0 is None and raw_noise_std > 0.:
-        noise0 = _host_noise((N_rays, N_samples), raw_noise_std, pytest)
-    rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd,
-                                                                 pytest=pytest, noise=noise0)
+    # deterministic renders that do not hand `raw` out: network + raw2outputs in ONE library call (r2l_nerf_render;
+    # in its fused mode the NeRF kernel composites the rays itself); same bits as the two-step route below
+    one_call = (raw_noise_std == 0. and noise0 is None and noise1 is None and not retraw and not return_debug
+                and rays_d.stride(-1) == 1)
+
+    def shade(z, net, noise, S_noise, want_weights):
+        if one_call and _fused_ok(net, viewdirs):
+            rgb, disp, acc, w, depth = net.render_samples(rays_o, rays_d, viewdirs, z, white_bkgd, want_weights)
+            return None, rgb, disp, acc, w, depth
+        raw_ = query(z, net)
+        if noise is None and raw_noise_std > 0.:
+            noise = _host_noise((N_rays, S_noise), raw_noise_std, pytest)
+        return (raw_,) + tuple(raw2outputs(raw_, z, rays_d, raw_noise_std, white_bkgd, pytest=pytest, noise=noise))
+
+    raw, rgb_map, disp_map, acc_map, weights, depth_map = shade(z_vals, network_fn, noise0, N_samples,
+                                                                N_importance > 0)
     debug = {}
     if N_importance > 0:
         rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
@@ -161,11 +172,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                 z_samples = sample_pdf(z_vals_mid, weights[..., 1:-1], N_importance, u=u)
             z_vals, z_std = merge_sorted(z_vals, z_samples, want_std=True)
         run_fn = network_fn if network_fine is None else network_fine
-        raw = query(z_vals, run_fn)
-        if noise1 is None and raw_noise_std > 0.:
-            noise1 = _host_noise((N_rays, N_samples + N_importance), raw_noise_std, pytest)
-        rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd,
-                                                                     pytest=pytest, noise=noise1)
+        raw, rgb_map, disp_map, acc_map, weights, depth_map = shade(z_vals, run_fn, noise1, N_samples + N_importance,
+                                                                    False)
 
     ret = {'rgb_map': rgb_map, 'disp_map': disp_map, 'acc_map': acc_map}
     if return_depth:

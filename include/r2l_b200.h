@@ -156,6 +156,20 @@ int r2l_nerf_forward(void* handle, long long n_rays, int S, const float* rays_o,
                      const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
                      const float* z_vals, float* raw, void* stream);
 
+/* render_rays' inner half in ONE call (main.py:707-709 coarse, :738-741 fine): raw = network(points o + d z), then
+ * raw2outputs(raw, z_vals, rays_d, raw_noise_std = 0, white_bkgd) (main.py:556-621) ->
+ * rgb_map [n_rays,3], disp_map / acc_map / depth_map [n_rays] (each may be NULL), weights [n_rays,S] (may be NULL).
+ * Two routes, same bits: r2l_nerf_forward into a workspace of the handle + r2l_raw2outputs (default), or — fused mode,
+ * CTA-pair kernel, S in {64,128,192,256} — the MLP kernel composites the rays itself and raw [n_rays,S,4] is never
+ * written (tests/test_gpu_frames.py).  The far-sample fix-up applies as in r2l_nerf_forward. */
+int r2l_nerf_render(void* handle, long long n_rays, int S, const float* rays_o, long long o_stride,
+                    const float* rays_d, long long d_stride, const float* viewdirs, long long v_stride,
+                    const float* z_vals, int white_bkgd, float* rgb_map, float* disp_map, float* acc_map,
+                    float* weights, float* depth_map, void* stream);
+/* fused = 0 (default; environment R2L_NERF_FUSED=1 changes it): two-step route; 1: fused where it applies.  Fused
+ * saves the raw round trip (1.3 GB of HBM traffic per 400x400 frame) but is ~1 % slower per frame. */
+int r2l_nerf_render_mode(void* handle, int fused);
+
 /* Far-sample sigma fix-up (main.py:578-581, 598: the last sample's 1e10 interval makes its alpha a step function of
  * sign(sigma)).  mode 1 (default): r2l_nerf_forward flags the rays whose last sample has
  * |sigma| < max(abs_band, rel_band * sum_i |alpha_w_i| relu(h7_i)) and re-evaluates those points in fp32 (bit-identical

@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol(E):
 def test_python_binding_covers_the_header(E):
     assert sorted(E._lib.SIGNATURES) == header_symbols()
     lib = E._lib.load()
-    assert lib.r2l_abi_version() == E._lib.ABI_VERSION == 6
+    assert lib.r2l_abi_version() == E._lib.ABI_VERSION == 7
 
 
 def test_argument_validation_needs_no_gpu(E):
