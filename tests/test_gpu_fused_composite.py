@@ -120,3 +120,40 @@ def test_fern_ndc_frame_fused_equals_two_step(E, O):
         coarse.set_fused_compositing(True), fine.set_fused_compositing(True)
     for k in out[True]:
         assert same(out[True][k], out[False][k]), k
+
+
+@pytest.mark.parametrize("S", [2, 33, 65, 96, 160])
+def test_render_samples_other_sample_counts_take_the_two_step_route(E, O, S):
+    """Sample counts without a fused shape: r2l_nerf_render falls back to MLP -> workspace -> raw2outputs in BOTH modes."""
+    sdc, _ = O.nerf_state_dicts(0)
+    net = load_nerf(E, sdc)
+    o, d, v, z = rays(777, S, seed=S)
+    fused, twostep, plain, _ = both_routes(E, net, o, d, v, z, True)
+    for f, t, pl in zip(fused, twostep, plain):
+        assert same(f, t) and same(t, pl)
+
+
+def test_fused_compositing_without_the_far_fixup_and_without_optional_outputs(E, O):
+    sdc, _ = O.nerf_state_dicts(0)
+    net = load_nerf(E, sdc)
+    o, d, v, z = rays(3001, 192, seed=11)
+    with torch.no_grad():
+        net.set_far_fixup(False)
+        fused, twostep, plain, n_flag = both_routes(E, net, o, d, v, z, False)
+        for f, t in zip(fused, twostep):
+            assert same(f, t)
+        # no weights wanted (the fine pass): the other maps do not change
+        net.set_fused_compositing(True)
+        rgb, disp, acc, w, depth = net.render_samples(o, d, v, z, False, want_weights=False)
+        assert w is None and same(rgb, fused[0]) and same(disp, fused[1]) and same(acc, fused[2]) and same(depth, fused[4])
+        net.set_far_fixup(True)
+        net.set_fused_compositing(False)
+
+
+def test_render_samples_empty_batch(E, O):
+    sdc, _ = O.nerf_state_dicts(0)
+    net = load_nerf(E, sdc)
+    o, d, v, z = rays(0, 64, seed=1)
+    with torch.no_grad():
+        rgb, disp, acc, w, depth = net.render_samples(o, d, v, z, True)
+    assert rgb.shape == (0, 3) and w.shape == (0, 64) and depth.shape == (0,)
