@@ -116,9 +116,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugB
 }
 
 // ------------------------------- CTA pairs (cluster of 2) --------------------------
+// (NOT volatile: the rank never changes, so the compiler may read the special register once and keep it — as a
+// volatile asm it was re-read (S2UR, tens of cycles) in front of every operand-group arrive of the epilogue)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {

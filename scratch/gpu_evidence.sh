@@ -12,6 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_nerf.csv python bench.py --workload nerf --steps 1 --warmup 3 --no-cpu-baseline --no-extras > $O/ncu_nerf.log 2>&1; echo "ncu list nerf rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:r2l_mlp_kernel -s 3 -c 1 -o $O/prof_r2l -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $O/ncu_r2l_full.log 2>&1; echo "ncu full r2l rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:nerf_mlp -s 6 -c 2 -o $O/prof_nerf -f python bench.py --workload nerf --steps 1 --warmup 3 --no-cpu-baseline --no-extras > $O/ncu_nerf_full.log 2>&1; echo "ncu full nerf rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:r2l_mlp_kernel -s 3 -c 1 -o $O/prof_r2l_bf16 -f python bench.py --precision bf16 --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $O/ncu_r2l_bf16_full.log 2>&1; echo "ncu full r2l bf16 rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"raw2outputs|sample|merge|far_fixup" -c 8 -o $O/prof_hbm -f python bench.py --workload nerf --steps 1 --warmup 3 --no-cpu-baseline --no-extras > $O/ncu_hbm_full.log 2>&1; echo "ncu full hbm rc=$?"
 fi
 tail -n 3 $O/tests_gpu.log; cat $O/bench_r2l.json | cut -c1-300; python - <<PY
