@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
       uint32_t g = 0, gb = 0;
       uint32_t par_a = 0;   // parity of the a_ready phase the next layer / chunk waits for (all 4 groups in step)
       const bool prof = DBG && p.prof != nullptr;
-      long long t_a = 0, t_w = 0;
+      long long t_a = 0, t_w = 0, t_a0 = 0;   // t_a0: the part of t_a spent on a layer's FIRST stage
       const long long t_start = prof ? clock64() : 0;
       // the K=16 bias step of a layer (needs no activations)
       auto bias_step = [&](uint32_t d_tmem, bool fresh) {
@@ -198,7 +198,11 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
           const uint32_t slot = g % kRing;
           const long long c0 = prof ? clock64() : 0;
           mbar_wait2<PAIR>(&a_ready[st], par_a, &w_full[slot], (g / kRing) & 1, p.dbg, 210 + st);
-          if (prof) t_a += clock64() - c0;
+          if (prof) {
+            const long long dt = clock64() - c0;
+            t_a += dt;
+            if (st == 0) t_a0 += dt;
+          }
           tc_fence_after_sync();
           issue_stage<4, PAIR>(d_tmem, aA + st * kGroupBytes, aRing + slot * kStageB, kLboB, idesc, false);
           umma_commit_x<PAIR>(&w_empty[slot]);
@@ -233,6 +237,7 @@ __global__ void __launch_bounds__(kR2lThreads, 1) r2l_mlp_kernel(const R2lParams
         o[0] = clock64() - t_start;   // MMA thread: total
         o[1] = t_a;                   // waiting for A groups + weight stages (joint wait)
         o[2] = t_w;                   // waiting for bias stages
+        if (PAIR) o[8] = t_a0;        // (the peer CTA's unused slot 0) the first-stage share of o[1]
       }
     }
   } else {

@@ -107,6 +107,20 @@ static __device__ __noinline__ void mbar_watchdog_fire(DebugBuf* dbg, uint32_t i
   }
   __trap();
 }
+// non-blocking probe of a phase (mbarrier.test_wait returns at once; try_wait may suspend the thread)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugBuf* dbg, uint32_t id,
                                           uint32_t patience = 1) {
   uint32_t spins = 0;
