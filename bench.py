@@ -409,12 +409,10 @@ def e2e_run(wl, poses, warmup, steps, run_step, barrier, rank, by_rays=False, fu
     c2w_buf = torch.empty((P, 3, 4), dtype=torch.float32, device="cuda")
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     copied = [None, None]
-    for i in range(steps):
-        c2w_buf.copy_(pose_host[warmup + i], non_blocking=True)          # H2D of this step's input
+
+    def one(i, pose):
+        c2w_buf.copy_(pose, non_blocking=True)                            # H2D of this step's input
         # fused gather: peers overwrite symmetric buffer (i + 1) & 1 once they pass publish(i); the read-back of
         # the frame it still holds (step i - 1) must be over before this rank joins that barrier
         wait_prev = (lambda: main_stream.wait_event(copied[(i + 1) & 1])) if fused and copied[(i + 1) & 1] else None
@@ -429,9 +427,29 @@ def e2e_run(wl, poses, warmup, steps, run_step, barrier, rank, by_rays=False, fu
                     out.record_stream(copy_stream)
                 copied[i & 1] = torch.cuda.Event()
                 copied[i & 1].record(copy_stream)
+
+    # untimed warm-up of THIS loop (an even number of steps, so the double buffering and the fused gather's buffer
+    # parity continue seamlessly): first use of the copy stream and of the pinned buffers — a 2-GPU run once lost
+    # 330 ms of a 240 ms timed region to it
+    n_w = 2 * max(1, min(warmup, 4) // 2)
+    for i in range(n_w):
+        one(i, pose_host[i % max(1, warmup)])
+    main_stream.wait_stream(copy_stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    verbose = bool(os.environ.get("BENCH_VERBOSE"))
+    t_host = []
+    for i in range(steps):
+        if verbose:
+            t_host.append(time.perf_counter())
+        one(n_w + i, pose_host[warmup + i])
     main_stream.wait_stream(copy_stream)
     e1.record()
     barrier()
+    if verbose and len(t_host) > 1:      # host-side pacing of the loop: where an end-to-end step loses time
+        d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]
+        print(f"[e2e rank {rank}] host ms between step launches: " + " ".join(f"{x:.2f}" for x in d[:60]), file=sys.stderr)
     return e0.elapsed_time(e1)
 
 
