@@ -16,7 +16,12 @@
  *     row-major and contiguous, `*_stride` arguments are row strides in ELEMENTS.
  *   - `stream` is a cudaStream_t (as void*); calls are asynchronous on that stream.
  *   - the library never allocates on the hot path: workspaces are passed in by the caller;
- *     only the *_create functions allocate (packed weights).
+ *     only the *_create functions allocate (packed weights).  Exception: a NeRF handle owns three
+ *     workspaces that GROW to the largest call seen (per-ray view bias, flagged-ray list, and for
+ *     r2l_nerf_render the raw / staging buffers); growing synchronises the stream once.
+ *   - a model handle serves ONE call at a time: calls on the same handle from several streams or
+ *     threads must be serialised by the caller (they share the handle's workspaces and its status
+ *     record).  Different handles are independent.
  */
 #ifndef R2L_B200_H_
 #define R2L_B200_H_
