@@ -786,25 +786,32 @@ nerf_mlp_pp_kernel(const __grid_constant__ NerfParams p, const __grid_constant__
 // Per-ray view-branch bias: vb[ray][n] = bv[n] + sum_j Wvd[n][j] * embed4(viewdir)[j]   (fp32)
 // embed4 = NeRF Embedder with L = 4 on the unit view direction (27 features, helpers:24-74); the view half of
 // views_linears[0] is constant along a ray, so it is evaluated once per ray (model/nerf_raybased.py:390-394).
+// One thread per output neuron n: its 27 weights stay in registers, a block works on 32 rays per iteration (96 threads
+// embed one (ray, coordinate) each; every ray's 128 outputs leave as one coalesced 512-byte row).  The accumulation
+// order (bias first, features ascending) is that of the earlier 8-rays-per-iteration version: same bits.
+constexpr int kVbRays = 32;
 __global__ void __launch_bounds__(128)
 nerf_view_bias_kernel(long long n_rays, const float* __restrict__ viewdirs, long long v_stride, int pre_embedded,
                       const float* __restrict__ wvd /*[128][27]*/, const float* __restrict__ bv, float* __restrict__ vb) {
-  __shared__ float s_w[128 * 27];
-  __shared__ float s_e[8][28];
-  for (int i = threadIdx.x; i < 128 * 27; i += 128) s_w[i] = wvd[i];
+  __shared__ __align__(16) float s_e[kVbRays][28];
   const int n = threadIdx.x;
+  float w[27];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) w[j] = __ldg(wvd + n * 27 + j);
   const float b = bv[n];
-  for (long long r0 = static_cast<long long>(blockIdx.x) * 8; r0 < n_rays; r0 += static_cast<long long>(gridDim.x) * 8) {
+  if (threadIdx.x < kVbRays) s_e[threadIdx.x][27] = 0.0f;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * kVbRays; r0 < n_rays;
+       r0 += static_cast<long long>(gridDim.x) * kVbRays) {
     __syncthreads();
     if (pre_embedded) {
       // rows already hold the 27 embedded view features
-      for (int it = threadIdx.x; it < 8 * 27; it += 128) {
+      for (int it = threadIdx.x; it < kVbRays * 27; it += 128) {
         const int rr = it / 27, j = it % 27;
         const long long ray = r0 + rr;
         if (ray < n_rays) s_e[rr][j] = viewdirs[ray * v_stride + j];
       }
-    } else if (threadIdx.x < 24) {
-      // 8 rays x 3 coords: identity + 4 sincos each
+    } else if (threadIdx.x < kVbRays * 3) {
+      // one (ray, coordinate) per thread: identity + 4 sincos
       const int rr = threadIdx.x / 3, c = threadIdx.x % 3;
       const long long ray = r0 + rr;
       if (ray < n_rays) {
@@ -812,21 +819,27 @@ nerf_view_bias_kernel(long long n_rays, const float* __restrict__ viewdirs, long
         s_e[rr][c] = v;
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-          float s, co;
-          sincosf(v * static_cast<float>(1 << f), &s, &co);
-          s_e[rr][3 + 6 * f + c] = s;
+          float sn, co;
+          sincosf(v * static_cast<float>(1 << f), &sn, &co);
+          s_e[rr][3 + 6 * f + c] = sn;
           s_e[rr][3 + 6 * f + 3 + c] = co;
         }
       }
     }
     __syncthreads();
-    for (int rr = 0; rr < 8; ++rr) {
-      const long long ray = r0 + rr;
-      if (ray >= n_rays) break;
+    const int n_here = static_cast<int>(n_rays - r0 < kVbRays ? n_rays - r0 : kVbRays);
+    for (int rr = 0; rr < n_here; ++rr) {
+      const float4* e4 = reinterpret_cast<const float4*>(s_e[rr]);
       float acc = b;
 #pragma unroll
-      for (int j = 0; j < 27; ++j) acc = fmaf(s_w[n * 27 + j], s_e[rr][j], acc);
-      vb[ray * 128 + n] = acc;
+      for (int q = 0; q < 7; ++q) {
+        const float4 e = e4[q];   // broadcast: every thread reads the same row
+        acc = fmaf(w[4 * q + 0], e.x, acc);
+        acc = fmaf(w[4 * q + 1], e.y, acc);
+        acc = fmaf(w[4 * q + 2], e.z, acc);
+        if (4 * q + 3 < 27) acc = fmaf(w[4 * q + 3], e.w, acc);
+      }
+      vb[(r0 + rr) * 128 + n] = acc;
     }
   }
 }
@@ -868,7 +881,7 @@ int nerf_mlp_pp_launch(bool bf16, const NerfParams& p, const NerfPpMaps& maps, c
 
 int nerf_view_bias_launch(long long n_rays, const float* viewdirs, long long v_stride, int pre_embedded,
                           const float* wvd, const float* bv, float* vb, cudaStream_t st) {
-  long long blocks = (n_rays + 7) / 8;
+  long long blocks = (n_rays + kVbRays - 1) / kVbRays;
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   nerf_view_bias_kernel<<<static_cast<int>(blocks), 128, 0, st>>>(n_rays, viewdirs, v_stride, pre_embedded, wvd, bv, vb);
