@@ -62,12 +62,10 @@ __device__ __forceinline__ void track_max(float v) {
   if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1) && m > 0x477fe000u) atomicMax(&g_pack_max, m);   // > 65504
 }
 
-__global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, int N, int K_src, int Kpad,
-                                  const int* __restrict__ kmap, float scale, uint16_t* __restrict__ dst, int bf16,
-                                  int pair) {
-  const long long total = static_cast<long long>(N) * Kpad;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+__device__ __forceinline__ void pack_layer_elem(const float* __restrict__ W, long long ldw, int N, int K_src, int Kpad,
+                                                const int* __restrict__ kmap, float scale, uint16_t* __restrict__ dst,
+                                                int bf16, int pair, long long idx) {
+  {
     const int n = static_cast<int>(idx / Kpad), k = static_cast<int>(idx % Kpad);
     const int ks = (kmap != nullptr) ? kmap[k] : k;
     float v = 0.0f;
@@ -94,6 +92,14 @@ __global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, in
     }
   }
 }
+__global__ void pack_layer_kernel(const float* __restrict__ W, long long ldw, int N, int K_src, int Kpad,
+                                  const int* __restrict__ kmap, float scale, uint16_t* __restrict__ dst, int bf16,
+                                  int pair) {
+  const long long total = static_cast<long long>(N) * Kpad;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x)
+    pack_layer_elem(W, ldw, N, K_src, Kpad, kmap, scale, dst, bf16, pair, idx);
+}
 
 // 16-bit hi / lo split of a bias value: hi = rn16(b), lo = rn16(b - hi); hi + lo reproduces b to ~2^-22 relative
 // (fp16) / 2^-16 (bf16).  Both are multiplied by exact 1.0 operands and accumulated in fp32 by the MMA.
@@ -108,10 +114,8 @@ __device__ __forceinline__ uint16_t bias_part(float b, int part, int bf16) {
 
 // Bias step of a layer: one K=16 stage [N x 16] whose k=0 / k=1 columns hold the hi / lo split of scale*bias
 // (the matching A operand is the constant ones block), all other columns zero.
-__global__ void pack_bias_kernel(const float* __restrict__ bias, int N, float scale, uint16_t* __restrict__ dst,
-                                 int bf16, int pair) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * 16) return;
+__device__ __forceinline__ void pack_bias_elem(const float* __restrict__ bias, int N, float scale,
+                                               uint16_t* __restrict__ dst, int bf16, int pair, int idx) {
   const int n = idx / 16, k = idx % 16;
   track_max(k == 0 ? bias[n] * scale : 0.0f);
   const uint16_t bits = (k < 2) ? bias_part(bias[n] * scale, k, bf16) : static_cast<uint16_t>(0);
@@ -123,6 +127,29 @@ __global__ void pack_bias_kernel(const float* __restrict__ bias, int N, float sc
     dst[h * (Nh * 16) + (k >> 3) * (Nh * 8) + nn * 8 + (k & 7)] = bits;
   } else {
     dst[(k >> 3) * (N * 8) + n * 8 + (k & 7)] = bits;
+  }
+}
+__global__ void pack_bias_kernel(const float* __restrict__ bias, int N, float scale, uint16_t* __restrict__ dst,
+                                 int bf16, int pair) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 16) return;
+  pack_bias_elem(bias, N, scale, dst, bf16, pair, idx);
+}
+// The 2 * n_blocks body layers of an R2L net (all 256 x 256, each [bias stage][weight stages]) in ONE launch:
+// blockIdx.y = body layer l (even: W1 / b1 of block l / 2, odd: W2 / b2 scaled by res_scale).  ptrs = device array
+// [w1 (n_blocks) | b1 | w2 | b2] of the caller's parameter pointers.
+__global__ void pack_r2l_body_kernel(const float* const* __restrict__ ptrs, int n_blocks, float res_scale,
+                                     uint16_t* __restrict__ dst, int bf16, int pair) {
+  const int l = blockIdx.y, b = l >> 1, second = l & 1;
+  const float* W = ptrs[(second ? 2 : 0) * n_blocks + b];
+  const float* bias = ptrs[(second ? 3 : 1) * n_blocks + b];
+  const float scale = second ? res_scale : 1.0f;
+  uint16_t* d = dst + static_cast<long long>(l) * (256 * 16 + 256 * 256);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 256 * 16 + 256 * 256; idx += gridDim.x * blockDim.x) {
+    if (idx < 256 * 16)
+      pack_bias_elem(bias, 256, scale, d, bf16, pair, idx);
+    else
+      pack_layer_elem(W, 256, 256, 256, 256, nullptr, scale, d + 256 * 16, bf16, pair, idx - 256 * 16);
   }
 }
 
@@ -1108,20 +1135,24 @@ int r2l_resmlp_create(void** out_handle, int dtype, int n_points, int n_blocks, 
                     m->bf16, st, scratch, pr);
   off += 256ull * K_head;
   for (int b = 0; b < n_blocks && rc == R2L_OK; ++b) {
-    if (!(w1[b] && b1[b] && w2[b] && b2[b])) {
-      rc = fail(R2L_ERR_INVALID, "r2l_resmlp_create: null block %d", b);
-      break;
-    }
-    rc = pack_bias(b1[b], 256, 1.0f, dst + off, m->bf16, st, pr);
-    off += 256ull * 16;
-    if (rc == R2L_OK) rc = pack_layer(w1[b], 256, 256, 256, 256, nullptr, 1.0f, dst + off, m->bf16, st, scratch, pr);
-    off += 256ull * 256;
-    if (rc == R2L_OK) rc = pack_bias(b2[b], 256, static_cast<float>(res_scale), dst + off, m->bf16, st, pr);
-    off += 256ull * 16;
-    if (rc == R2L_OK)
-      rc = pack_layer(w2[b], 256, 256, 256, 256, nullptr, static_cast<float>(res_scale), dst + off, m->bf16, st,
-                      scratch, pr);
-    off += 256ull * 256;
+    if (!(w1[b] && b1[b] && w2[b] && b2[b])) rc = fail(R2L_ERR_INVALID, "r2l_resmlp_create: null block %d", b);
+  }
+  if (rc == R2L_OK) {
+    // the 2 * n_blocks body layers in one launch (was four launches per block)
+    const float** d_ptrs = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&d_ptrs), sizeof(float*) * 4 * n_blocks) != cudaSuccess)
+      return cleanup(fail(R2L_ERR_CUDA, "r2l_resmlp_create: cudaMalloc failed"));
+    scratch.push_back(reinterpret_cast<int*>(d_ptrs));
+    const float* const* groups[4] = {w1, b1, w2, b2};
+    cudaError_t e1 = cudaSuccess;
+    for (int g = 0; g < 4 && e1 == cudaSuccess; ++g)
+      e1 = cudaMemcpyAsync(d_ptrs + g * n_blocks, groups[g], sizeof(float*) * n_blocks, cudaMemcpyHostToDevice, st);
+    if (e1 != cudaSuccess) return cleanup(fail(R2L_ERR_CUDA, "r2l_resmlp_create: %s", cudaGetErrorString(e1)));
+    pack_r2l_body_kernel<<<dim3(64, 2 * n_blocks), 256, 0, st>>>(d_ptrs, n_blocks, static_cast<float>(res_scale), dst + off,
+                                                                 m->bf16 ? 1 : 0, pr);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) rc = fail(R2L_ERR_CUDA, "r2l_resmlp_create: body pack launch failed");
+    off += static_cast<size_t>(2 * n_blocks) * (256ull * 16 + 256ull * 256);
   }
   if (rc != R2L_OK) return cleanup(rc);
   if (m->pair == 1) {
